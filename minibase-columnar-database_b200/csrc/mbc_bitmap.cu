@@ -1,0 +1,512 @@
+// mbc_bitmap.cu -- K3 bitmap-index build and K4 bitmap CNF combine.
+//
+// K3 replaces columnar/Columnarfile.java:698-753 createBitMapIndex(): one UNCOMPRESSED bitset per
+// distinct value of a column (bit p set iff column[p] == value and p was not deleted at build time;
+// the reference's ColumnScan skips deleted rows, columnar/ColumnScan.java:49-65).  Bit order is
+// java.util.BitSet's: bit p lives in byte p/8, bit p%8 (bitmap/BM.java:64-129 persists
+// BitSet.toByteArray()), which is also bit p%32 of little-endian uint32 word p/32.
+//
+// K4 replaces index/ColumnarIndexScan.java:130-181 (OR inside a conjunct, AND across conjuncts) with
+// each term resolved as index/ColumnIndexScan.java:656-740 getBitSet(): EQ -> that value's bitmap,
+// LT/LE/GT/GE/NE -> OR of the bitmaps of every indexed value that satisfies the operator; rows in
+// markedDeleted are dropped (ColumnIndexScan.java:600-624).
+//
+// Build kernel: a CTA owns a chunk of R rows and an smem matrix [values][R/32] of bitmap words.  A
+// warp's 32 rows are exactly one word column; __match_any_sync groups the lanes that hold the same
+// value, and the group leader stores the group's lane mask as the finished word -- no atomics, every
+// word is written once.  The matrix (zeros included: the index is uncompressed by definition) is
+// then streamed out with 128-bit stores, R/8 contiguous bytes per value.  The kernel is bound by
+// HBM writes: D*N/8 bytes out for 4*N bytes in.
+#include <algorithm>
+#include <cstring>
+#include <numeric>
+
+#include "mbc_internal.cuh"
+
+namespace mbc {
+
+// ---- distinct values: open-addressing hash set in global memory ---------------------------------
+// ints   : slot = (1<<32) | (uint32)value
+// strings: slot = row index + 1 of a representative row
+struct HashTab {
+    unsigned long long* slots;
+    uint32_t* slot_id;       // dense id per slot, filled by the host after sorting the values
+    uint32_t mask;           // capacity - 1
+};
+
+__device__ __forceinline__ uint32_t hash32(uint32_t x) {
+    x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+    return x;
+}
+
+__device__ __forceinline__ uint32_t hash_row(const uint32_t* row, int words) {
+    uint32_t h = 0x811C9DC5u;
+    for (int w = 0; w < words; ++w) h = hash32(h ^ row[w]);
+    return h;
+}
+
+__device__ __forceinline__ bool rows_equal(const uint32_t* a, const uint32_t* b, int words) {
+    for (int w = 0; w < words; ++w)
+        if (a[w] != b[w]) return false;
+    return true;
+}
+
+// returns the slot of the value of row `r`, inserting it when INSERT; -1 when the table is full
+template <bool INSERT>
+__device__ __forceinline__ int probe(const HashTab& h, const void* col, int stride, bool is_str, int64_t r) {
+    if (!is_str) {
+        const uint32_t v = reinterpret_cast<const uint32_t*>(col)[r];
+        const unsigned long long key = (1ull << 32) | v;
+        uint32_t s = hash32(v) & h.mask;
+        for (uint32_t n = 0; n <= h.mask; ++n, s = (s + 1) & h.mask) {
+            unsigned long long cur = INSERT ? *reinterpret_cast<volatile unsigned long long*>(h.slots + s)
+                                            : __ldg(h.slots + s);
+            if (cur == key) return (int)s;
+            if (cur == 0) {
+                if (!INSERT) return -1;
+                unsigned long long old = atomicCAS(h.slots + s, 0ull, key);
+                if (old == 0 || old == key) return (int)s;
+            }
+        }
+        return -1;
+    } else {
+        const int words = stride >> 2;
+        const uint32_t* row = reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(col) + r * stride);
+        uint32_t s = hash_row(row, words) & h.mask;
+        for (uint32_t n = 0; n <= h.mask; ++n, s = (s + 1) & h.mask) {
+            unsigned long long cur = INSERT ? *reinterpret_cast<volatile unsigned long long*>(h.slots + s)
+                                            : __ldg(h.slots + s);
+            if (cur == 0) {
+                if (!INSERT) return -1;
+                unsigned long long old = atomicCAS(h.slots + s, 0ull, (unsigned long long)(r + 1));
+                if (old == 0) return (int)s;
+                cur = old;
+            }
+            const uint32_t* rep = reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(col) + (int64_t)(cur - 1) * stride);
+            if (rows_equal(row, rep, words)) return (int)s;
+        }
+        return -1;
+    }
+}
+
+__global__ void distinct_insert_kernel(HashTab h, const void* col, int stride, int is_str, int64_t nrows,
+                                       const uint32_t* deleted, int* overflow) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t step = (int64_t)gridDim.x * blockDim.x;
+    for (; i < nrows; i += step) {
+        if (deleted && ((deleted[i >> 5] >> (i & 31)) & 1u)) continue;
+        if (probe<true>(h, col, stride, is_str != 0, i) < 0) { *overflow = 1; return; }
+    }
+}
+
+// ---- K3 build -------------------------------------------------------------------------------------
+
+constexpr int kBuildThreads = 512;
+
+struct BuildParams {
+    HashTab h;
+    const void* col;
+    const uint32_t* deleted;
+    uint32_t* bitmaps;        // [nvalues][words_pad]
+    int64_t nrows;
+    int64_t words_pad;
+    int64_t nchunks;
+    int32_t stride, is_str;
+    int32_t chunk_rows;       // R (multiple of 1024)
+    int32_t v0, nv;           // value ids handled by this pass: [v0, v0+nv)
+    unsigned int* ticket;
+};
+
+__global__ void __launch_bounds__(kBuildThreads, 1) bitmap_build_kernel(const __grid_constant__ BuildParams p) {
+    extern __shared__ uint4 sm4[];
+    uint32_t* sm = reinterpret_cast<uint32_t*>(sm4);
+    __shared__ long long s_chunk;
+    const int wpc = p.chunk_rows >> 5;                    // words per value per chunk
+    const int total_words = p.nv * wpc;
+    const int lane = threadIdx.x & 31;
+
+    while (true) {
+        if (threadIdx.x == 0) s_chunk = (long long)atomicAdd(p.ticket, 1u);
+        __syncthreads();
+        const int64_t chunk = s_chunk;
+        if (chunk >= p.nchunks) break;
+        for (int i = threadIdx.x; i < total_words / 4; i += kBuildThreads) sm4[i] = make_uint4(0, 0, 0, 0);
+        __syncthreads();
+
+        const int64_t row0 = chunk * p.chunk_rows;
+        for (int r = threadIdx.x; r < p.chunk_rows; r += kBuildThreads) {   // a warp's 32 rows = one word column
+            const int64_t row = row0 + r;
+            int id = -1;
+            if (row < p.nrows && !(p.deleted && ((p.deleted[row >> 5] >> (row & 31)) & 1u))) {
+                int s = probe<false>(p.h, p.col, p.stride, p.is_str != 0, row);
+                if (s >= 0) id = (int)p.h.slot_id[s] - p.v0;
+                if (id < 0 || id >= p.nv) id = -1;
+            }
+            const uint32_t group = __match_any_sync(0xFFFFFFFFu, id);
+            if (id >= 0 && (group & ((1u << lane) - 1)) == 0)               // leader of its value group
+                sm[id * wpc + (r >> 5)] = group;
+        }
+        __syncthreads();
+
+        // stream the finished words out: wpc*4 contiguous bytes per value
+        const int quads_per_value = wpc >> 2;
+        uint32_t* dst0 = p.bitmaps + (int64_t)p.v0 * p.words_pad + chunk * wpc;
+        for (int i = threadIdx.x; i < total_words / 4; i += kBuildThreads) {
+            const int v = i / quads_per_value, q = i - v * quads_per_value;
+            reinterpret_cast<uint4*>(dst0 + (int64_t)v * p.words_pad)[q] = sm4[i];
+        }
+        __syncthreads();
+    }
+}
+
+// ---- K4 combine -------------------------------------------------------------------------------------
+
+constexpr int kMaxInlineBitmaps = 96;
+
+struct CnfParams {
+    int64_t nquads;                       // words_pad / 4
+    uint4* out;
+    const uint4* deleted;
+    const uint4* const* list;             // device list when there are more than kMaxInlineBitmaps
+    int32_t nconj, nbitmaps;
+    int32_t conj_end[kMaxTerms];          // exclusive end index of each conjunct in the bitmap list
+    const uint4* inl[kMaxInlineBitmaps];  // NULL pointer = empty bitmap (value never indexed)
+};
+
+__global__ void __launch_bounds__(256) bitmap_cnf_kernel(const __grid_constant__ CnfParams p) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t step = (int64_t)gridDim.x * blockDim.x;
+    const uint4* const* list = p.list ? p.list : p.inl;
+    for (; i < p.nquads; i += step) {
+        uint4 acc = make_uint4(~0u, ~0u, ~0u, ~0u);
+        int j = 0;
+        for (int g = 0; g < p.nconj; ++g) {
+            uint4 d = make_uint4(0, 0, 0, 0);
+            for (; j < p.conj_end[g]; ++j) {
+                const uint4* bm = list[j];
+                if (bm) {
+                    uint4 w = __ldg(bm + i);
+                    d.x |= w.x; d.y |= w.y; d.z |= w.z; d.w |= w.w;
+                }
+            }
+            acc.x &= d.x; acc.y &= d.y; acc.z &= d.z; acc.w &= d.w;
+        }
+        if (p.deleted) {
+            uint4 w = __ldg(p.deleted + i);
+            acc.x &= ~w.x; acc.y &= ~w.y; acc.z &= ~w.z; acc.w &= ~w.w;
+        }
+        p.out[i] = acc;
+    }
+}
+
+// ---- host side ----------------------------------------------------------------------------------------
+
+static int cmp_bytes(const uint8_t* a, const uint8_t* b, int n) { return memcmp(a, b, n); }
+
+}  // namespace mbc
+
+using namespace mbc;
+
+extern "C" int32_t mbc_bitmap_exists(const mbc_table* t, int32_t col) {
+    if (!t || col < 0 || col >= (int)t->cols.size()) return 0;
+    return t->bm[col].exists ? 1 : 0;
+}
+
+extern "C" int32_t mbc_bitmap_build(mbc_table* t, int32_t col) {
+    if (!t || col < 0 || col >= (int)t->cols.size()) MBC_FAIL(MBC_ERR_ARG, "mbc_bitmap_build: bad column");
+    mbc_ctx* ctx = t->ctx;
+    MBC_CUDA(cudaSetDevice(ctx->device));
+    BitmapIndex& bi = t->bm[col];
+    if (bi.exists) return MBC_OK;                       // Columnarfile.java:699: no-op when it exists
+    const Column& c = t->cols[col];
+    if (c.type == MBC_ATTR_REAL) MBC_FAIL(MBC_ERR_UNSUPPORTED, "bitmap index on a real column (the reference indexes int and string only)");
+    const bool is_str = c.type == MBC_ATTR_STRING;
+    const uint32_t* deleted = t->has_deleted ? t->d_deleted : nullptr;
+
+    // 1. distinct values
+    HashTab h{};
+    int* d_overflow = nullptr;
+    MBC_TRY(dev_alloc(ctx, (void**)&d_overflow, 4, true));
+    std::vector<unsigned long long> slots;
+    uint32_t cap = 0;
+    begin_timing(ctx);
+    for (uint32_t try_cap : {1u << 12, 1u << 16, 1u << 20}) {
+        cap = try_cap;
+        MBC_TRY(dev_alloc(ctx, (void**)&h.slots, (size_t)cap * 8, true));
+        h.mask = cap - 1;
+        MBC_CUDA(cudaMemsetAsync(d_overflow, 0, 4, ctx->stream));
+        if (t->nrows > 0) {
+            int grid = (int)std::min<int64_t>((t->nrows + 255) / 256, (int64_t)ctx->sm_count * 8);
+            distinct_insert_kernel<<<grid, 256, 0, ctx->stream>>>(h, c.d, c.stride, is_str, t->nrows, deleted, d_overflow);
+            ctx->launches++;
+        }
+        int overflow = 0;
+        MBC_CUDA(cudaMemcpyAsync(&overflow, d_overflow, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        slots.resize(cap);
+        MBC_CUDA(cudaMemcpyAsync(slots.data(), h.slots, (size_t)cap * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        MBC_CUDA(cudaStreamSynchronize(ctx->stream));
+        size_t used = 0;
+        for (auto s : slots) used += s != 0;
+        if (!overflow && used <= cap / 2) break;
+        dev_free(ctx, h.slots);
+        h.slots = nullptr;
+        if (try_cap == (1u << 20)) {
+            dev_free(ctx, d_overflow);
+            MBC_FAIL(MBC_ERR_UNSUPPORTED, "bitmap index: more than %u distinct values", 1u << 19);
+        }
+    }
+    dev_free(ctx, d_overflow);
+
+    // 2. sort the values, give every slot its dense id
+    std::vector<int> used_slots;
+    for (uint32_t s = 0; s < cap; ++s) if (slots[s]) used_slots.push_back((int)s);
+    const int64_t D = (int64_t)used_slots.size();
+    std::vector<uint8_t> rep_bytes;                      // strings: representative rows
+    if (is_str && D > 0) {
+        rep_bytes.resize((size_t)D * c.stride);
+        for (int64_t k = 0; k < D; ++k) {
+            int64_t row = (int64_t)slots[used_slots[k]] - 1;
+            MBC_CUDA(cudaMemcpyAsync(rep_bytes.data() + k * c.stride, (const char*)c.d + row * c.stride, c.stride,
+                                     cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        MBC_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    std::vector<int> order(D);
+    std::iota(order.begin(), order.end(), 0);
+    if (is_str) {
+        std::sort(order.begin(), order.end(), [&](int a, int b) {
+            return cmp_bytes(rep_bytes.data() + (size_t)a * c.stride, rep_bytes.data() + (size_t)b * c.stride, c.stride) < 0;
+        });
+    } else {
+        std::sort(order.begin(), order.end(), [&](int a, int b) {
+            return (int32_t)(uint32_t)slots[used_slots[a]] < (int32_t)(uint32_t)slots[used_slots[b]];
+        });
+    }
+    std::vector<uint32_t> slot_id(cap, 0xFFFFFFFFu);
+    bi.ivals.clear();
+    bi.svals.clear();
+    for (int64_t k = 0; k < D; ++k) {
+        int src = order[k];
+        slot_id[used_slots[src]] = (uint32_t)k;
+        if (is_str) bi.svals.insert(bi.svals.end(), rep_bytes.begin() + (size_t)src * c.stride,
+                                    rep_bytes.begin() + (size_t)src * c.stride + c.width);
+        else bi.ivals.push_back((int32_t)(uint32_t)slots[used_slots[src]]);
+    }
+    bi.nvalues = D;
+    MBC_TRY(dev_alloc(ctx, (void**)&h.slot_id, (size_t)cap * 4, false));
+    MBC_CUDA(cudaMemcpyAsync(h.slot_id, slot_id.data(), (size_t)cap * 4, cudaMemcpyHostToDevice, ctx->stream));
+
+    // 3. build
+    if (D > 0) {
+        size_t free_b = 0, total_b = 0;
+        MBC_CUDA(cudaMemGetInfo(&free_b, &total_b));
+        const size_t need = (size_t)D * t->words_pad * 4;
+        // (the stream-ordered pool may already hold reusable memory, so only refuse the impossible)
+        if (need > total_b) MBC_FAIL(MBC_ERR_UNSUPPORTED, "bitmap index needs %zu bytes (%lld values x %lld rows), device has %zu",
+                                     need, (long long)D, (long long)t->nrows_pad, total_b);
+        MBC_TRY(dev_alloc(ctx, (void**)&bi.d_words, need, false));
+        const size_t smem_budget = 200 * 1024;
+        // rows per chunk: as many as fit for the values of one pass, power of two in [1024, 8192]
+        int R = 8192;
+        while (R > 1024 && (size_t)std::min<int64_t>(D, 4096) * (R / 8) > smem_budget) R >>= 1;
+        const int max_nv = (int)std::min<int64_t>(D, (int64_t)(smem_budget / (R / 8)));
+        unsigned int* d_ticket = nullptr;
+        MBC_TRY(dev_alloc(ctx, (void**)&d_ticket, 4, true));
+        MBC_CUDA(cudaFuncSetAttribute(bitmap_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_budget));
+        for (int64_t v0 = 0; v0 < D; v0 += max_nv) {
+            BuildParams p{};
+            p.h = h;
+            p.col = c.d;
+            p.deleted = deleted;
+            p.bitmaps = bi.d_words;
+            p.nrows = t->nrows;
+            p.words_pad = t->words_pad;
+            p.chunk_rows = R;
+            p.nchunks = t->nrows_pad / R;                // nrows_pad is a multiple of kPadRows = 8192 >= R
+            p.stride = c.stride;
+            p.is_str = is_str;
+            p.v0 = (int)v0;
+            p.nv = (int)std::min<int64_t>(max_nv, D - v0);
+            p.ticket = d_ticket;
+            MBC_CUDA(cudaMemsetAsync(d_ticket, 0, 4, ctx->stream));
+            size_t smem = (size_t)p.nv * (R / 8);
+            int grid = (int)std::min<int64_t>(p.nchunks, ctx->sm_count);
+            bitmap_build_kernel<<<grid, kBuildThreads, smem, ctx->stream>>>(p);
+            ctx->launches++;
+        }
+        dev_free(ctx, d_ticket);
+    }
+    end_timing(ctx);
+    MBC_CUDA(cudaGetLastError());
+    MBC_CUDA(cudaStreamSynchronize(ctx->stream));
+    dev_free(ctx, h.slots);
+    dev_free(ctx, h.slot_id);
+    bi.exists = true;
+    return MBC_OK;
+}
+
+extern "C" int32_t mbc_bitmap_values(mbc_table* t, int32_t col, const void** values, int64_t* n) {
+    if (!t || col < 0 || col >= (int)t->cols.size() || !values || !n) MBC_FAIL(MBC_ERR_ARG, "mbc_bitmap_values: bad argument");
+    const BitmapIndex& bi = t->bm[col];
+    if (!bi.exists) MBC_FAIL(MBC_ERR_NOINDEX, "column %d has no bitmap index", col);
+    *n = bi.nvalues;
+    *values = t->cols[col].type == MBC_ATTR_STRING ? (const void*)bi.svals.data() : (const void*)bi.ivals.data();
+    return MBC_OK;
+}
+
+namespace mbc {
+
+// index of `value` among the sorted distinct values, or -1
+static int64_t find_value(const mbc_table* t, int col, const void* value) {
+    const BitmapIndex& bi = t->bm[col];
+    const Column& c = t->cols[col];
+    if (c.type == MBC_ATTR_STRING) {
+        const uint8_t* v = (const uint8_t*)value;
+        int64_t lo = 0, hi = bi.nvalues;
+        while (lo < hi) {
+            int64_t mid = (lo + hi) / 2;
+            int r = memcmp(bi.svals.data() + mid * c.width, v, c.width);
+            if (r == 0) return mid;
+            if (r < 0) lo = mid + 1; else hi = mid;
+        }
+        return -1;
+    }
+    int32_t v = *(const int32_t*)value;
+    auto it = std::lower_bound(bi.ivals.begin(), bi.ivals.end(), v);
+    if (it == bi.ivals.end() || *it != v) return -1;
+    return it - bi.ivals.begin();
+}
+
+}  // namespace mbc
+
+extern "C" int32_t mbc_bitmap_get(mbc_table* t, int32_t col, const void* value, uint64_t* out_words, int64_t nwords) {
+    if (!t || col < 0 || col >= (int)t->cols.size() || !value || (!out_words && nwords > 0))
+        MBC_FAIL(MBC_ERR_ARG, "mbc_bitmap_get: bad argument");
+    const BitmapIndex& bi = t->bm[col];
+    if (!bi.exists) MBC_FAIL(MBC_ERR_NOINDEX, "column %d has no bitmap index", col);
+    MBC_CUDA(cudaSetDevice(t->ctx->device));
+    memset(out_words, 0, (size_t)nwords * 8);
+    int64_t k = find_value(t, col, value);
+    if (k < 0) return MBC_OK;                            // Columnarfile.java:1103-1127: empty BitMapFile
+    int64_t n = std::min<int64_t>(nwords, t->words_pad / 2);
+    MBC_CUDA(cudaMemcpyAsync(out_words, bi.d_words + k * t->words_pad, (size_t)n * 8, cudaMemcpyDeviceToHost, t->ctx->stream));
+    MBC_CUDA(cudaStreamSynchronize(t->ctx->stream));
+    return MBC_OK;
+}
+
+namespace mbc {
+
+// ColumnIndexScan.java:656-740: which indexed values does `column op literal` select?
+static bool value_selected(int op, int cmp /* sign of compare(indexed value, literal) */) {
+    switch (op) {
+        case MBC_OP_EQ: return cmp == 0;
+        case MBC_OP_LT: return cmp < 0;
+        case MBC_OP_LE: return cmp <= 0;
+        case MBC_OP_GT: return cmp > 0;
+        case MBC_OP_GE: return cmp >= 0;
+        case MBC_OP_NE: return cmp != 0;
+        default: return false;                           // getBitSet() has no branch for aopNOT/NOP/RANGE: empty set
+    }
+}
+
+int32_t resolve_bitmap_terms(mbc_table* t, const mbc_term* terms, int32_t nterms, std::vector<const uint4*>* list,
+                             std::vector<int>* conj_end) {
+    if (nterms <= 0) MBC_FAIL(MBC_ERR_ARG, "bitmap scan needs at least one term (ColumnarIndexScan dereferences selects[0])");
+    for (int k = 0; k < nterms; ++k) {
+        const mbc_term& s = terms[k];
+        if (k > 0 && s.conj_id < terms[k - 1].conj_id) MBC_FAIL(MBC_ERR_ARG, "terms must be sorted by conj_id");
+        if (k > 0 && s.conj_id != terms[k - 1].conj_id) conj_end->push_back((int)list->size());
+        // ColumnarIndexScan.java:137-142: exactly one side is a column; the literal is operand2
+        if (s.lhs.kind != MBC_OPERAND_OUTER || s.rhs.kind != MBC_OPERAND_LITERAL)
+            MBC_FAIL(MBC_ERR_ARG, "bitmap term %d must be `column op literal`", k);
+        int col = s.lhs.col;
+        if (col < 0 || col >= (int)t->cols.size()) MBC_FAIL(MBC_ERR_ARG, "bitmap term %d: column %d out of range", k, col);
+        const BitmapIndex& bi = t->bm[col];
+        if (!bi.exists) MBC_FAIL(MBC_ERR_NOINDEX, "bitmap term %d: column %d has no bitmap index", k, col);
+        const Column& c = t->cols[col];
+        const size_t before = list->size();
+        if (c.type == MBC_ATTR_STRING) {
+            if (s.rhs.type != MBC_ATTR_STRING) MBC_FAIL(MBC_ERR_ARG, "bitmap term %d: string column needs a string literal", k);
+            std::vector<uint8_t> lit(std::max(c.width, s.rhs.lit_slen), 0);
+            if (s.rhs.lit_slen) memcpy(lit.data(), s.rhs.lit_s, s.rhs.lit_slen);
+            for (int64_t v = 0; v < bi.nvalues; ++v) {
+                // String.compareTo over zero padded bytes; an over-long literal can only be greater on a tie
+                int cmp = memcmp(bi.svals.data() + v * c.width, lit.data(), c.width);
+                if (cmp == 0 && s.rhs.lit_slen > c.width) cmp = -1;
+                if (value_selected(s.op, cmp)) list->push_back(reinterpret_cast<const uint4*>(bi.d_words + v * t->words_pad));
+            }
+        } else {
+            if (s.rhs.type != MBC_ATTR_INTEGER) MBC_FAIL(MBC_ERR_ARG, "bitmap term %d: int column needs an int literal", k);
+            for (int64_t v = 0; v < bi.nvalues; ++v) {
+                int cmp = bi.ivals[v] < s.rhs.lit_i ? -1 : bi.ivals[v] > s.rhs.lit_i ? 1 : 0;
+                if (value_selected(s.op, cmp)) list->push_back(reinterpret_cast<const uint4*>(bi.d_words + v * t->words_pad));
+            }
+        }
+        if (list->size() == before) list->push_back(nullptr);   // nothing selected: an empty bitset takes the term's place
+    }
+    conj_end->push_back((int)list->size());
+    if ((int)conj_end->size() > kMaxTerms) MBC_FAIL(MBC_ERR_UNSUPPORTED, "%d conjuncts (max %d)", (int)conj_end->size(), kMaxTerms);
+    return MBC_OK;
+}
+
+// runs K4 into a fresh device bitmap of t->words_pad words
+int32_t run_bitmap_cnf(mbc_table* t, const mbc_term* terms, int32_t nterms, uint32_t** d_out) {
+    mbc_ctx* ctx = t->ctx;
+    std::vector<const uint4*> list;
+    std::vector<int> conj_end;
+    MBC_TRY(resolve_bitmap_terms(t, terms, nterms, &list, &conj_end));
+    MBC_TRY(dev_alloc(ctx, (void**)d_out, (size_t)t->words_pad * 4, false));
+    CnfParams p{};
+    p.nquads = t->words_pad / 4;
+    p.out = reinterpret_cast<uint4*>(*d_out);
+    p.deleted = t->has_deleted ? reinterpret_cast<const uint4*>(t->d_deleted) : nullptr;
+    p.nconj = (int)conj_end.size();
+    p.nbitmaps = (int)list.size();
+    for (int g = 0; g < p.nconj; ++g) p.conj_end[g] = conj_end[g];
+    const uint4** d_list = nullptr;
+    if ((int)list.size() <= kMaxInlineBitmaps) {
+        for (size_t j = 0; j < list.size(); ++j) p.inl[j] = list[j];
+    } else {
+        MBC_TRY(dev_alloc(ctx, (void**)&d_list, list.size() * sizeof(void*), false));
+        MBC_CUDA(cudaMemcpyAsync(d_list, list.data(), list.size() * sizeof(void*), cudaMemcpyHostToDevice, ctx->stream));
+        MBC_CUDA(cudaStreamSynchronize(ctx->stream));    // `list` is pageable host memory
+        p.list = d_list;
+    }
+    int grid = (int)std::max<int64_t>(1, std::min<int64_t>((p.nquads + 255) / 256, (int64_t)ctx->sm_count * 8));
+    bitmap_cnf_kernel<<<grid, 256, 0, ctx->stream>>>(p);
+    ctx->launches++;
+    MBC_CUDA(cudaGetLastError());
+    if (d_list) dev_free(ctx, d_list);
+    return MBC_OK;
+}
+
+}  // namespace mbc
+
+extern "C" int32_t mbc_bitmap_scan(mbc_table* t, const mbc_term* terms, int32_t nterms, const int32_t* proj_cols,
+                                   int32_t nproj, uint32_t want, const mbc_aggspec* aggs, int32_t nagg,
+                                   mbc_result** out) {
+    if (!t || !out) MBC_FAIL(MBC_ERR_ARG, "mbc_bitmap_scan: table/out is NULL");
+    if (!terms && nterms > 0) MBC_FAIL(MBC_ERR_ARG, "mbc_bitmap_scan: terms is NULL");
+    mbc_ctx* ctx = t->ctx;
+    MBC_CUDA(cudaSetDevice(ctx->device));
+    uint32_t* d_sel = nullptr;
+    cudaEvent_t ev0;
+    MBC_CUDA(cudaEventCreate(&ev0));
+    cudaEventRecord(ev0, ctx->stream);
+    int32_t s = run_bitmap_cnf(t, terms, nterms, &d_sel);
+    if (s != MBC_OK) { cudaEventDestroy(ev0); return s; }
+    ScanRequest rq;
+    rq.table = t;
+    rq.d_sel_bitmap = d_sel;
+    rq.proj_cols = proj_cols;
+    rq.nproj = nproj;
+    rq.want = want;
+    rq.aggs = aggs;
+    rq.nagg = nagg;
+    s = run_scan(rq, out);
+    // account the combine kernel into the reported device time
+    std::swap(ev0, ctx->ev_begin);
+    cudaEventDestroy(ev0);
+    dev_free(ctx, d_sel);
+    return s;
+}

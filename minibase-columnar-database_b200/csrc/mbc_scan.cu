@@ -1,0 +1,505 @@
+// mbc_scan.cu -- host side of K2/K5 (kernels in mbc_scan_kernels.cuh): builds the term program,
+// owns the result buffers, launches the fused scan, and implements the two public entry points
+// mbc_scan (table resident in HBM) and mbc_scan_host (host-resident columns streamed through HBM).
+#include <cstring>
+#include <algorithm>
+
+#include "mbc_internal.cuh"
+#include "mbc_scan_kernels.cuh"
+
+namespace mbc {
+
+static int32_t fill_operand(const mbc_table* t, const mbc_operand& o, int cmp_type, DevOperand* d, DevTerm* term,
+                            int k) {
+    memset(d, 0, sizeof(*d));
+    d->col = -1;
+    if (o.kind == MBC_OPERAND_LITERAL) {
+        d->kind = 0;
+        if (cmp_type == MBC_ATTR_STRING) {
+            if (o.type != MBC_ATTR_STRING)
+                MBC_FAIL(MBC_ERR_UNSUPPORTED, "term %d: string comparison against a non-string literal", k);
+            if (o.lit_slen < 0 || o.lit_slen > kMaxLit || (o.lit_slen > 0 && !o.lit_s))
+                MBC_FAIL(MBC_ERR_UNSUPPORTED, "term %d: string literal of %d bytes (max %d)", k, o.lit_slen, kMaxLit);
+            for (int i = 0; i < o.lit_slen; ++i)
+                if (o.lit_s[i] == 0) MBC_FAIL(MBC_ERR_UNSUPPORTED, "term %d: NUL byte in a string literal", k);
+            memset(term->lit, 0, sizeof(term->lit));
+            if (o.lit_slen) memcpy(term->lit, o.lit_s, o.lit_slen);
+            term->lit_words = (o.lit_slen + 3) / 4;
+        } else {
+            // PredEval builds a one-field tuple of the literal's own type and the compare reads it
+            // with the comparison type's getter (PredEval.java:60-78,101-116): the raw 4 bytes are
+            // what is compared.
+            if (o.type == MBC_ATTR_INTEGER) d->bits = (uint32_t)o.lit_i;
+            else if (o.type == MBC_ATTR_REAL) memcpy(&d->bits, &o.lit_f, 4);
+            else MBC_FAIL(MBC_ERR_UNSUPPORTED, "term %d: numeric comparison against a string literal", k);
+        }
+        return MBC_OK;
+    }
+    if (o.kind != MBC_OPERAND_OUTER) MBC_FAIL(MBC_ERR_ARG, "term %d: a single-table scan only has outer columns", k);
+    if (o.col < 0 || o.col >= (int)t->cols.size()) MBC_FAIL(MBC_ERR_ARG, "term %d: column %d out of range", k, o.col);
+    const Column& c = t->cols[o.col];
+    if ((cmp_type == MBC_ATTR_STRING) != (c.type == MBC_ATTR_STRING))
+        MBC_FAIL(MBC_ERR_UNSUPPORTED, "term %d: column %d of type %d compared as type %d", k, o.col, c.type, cmp_type);
+    if (cmp_type == MBC_ATTR_STRING && c.stride > kMaxLit)
+        MBC_FAIL(MBC_ERR_UNSUPPORTED, "term %d: char(%d) predicate column wider than %d", k, c.width, kMaxLit);
+    d->kind = 1;
+    d->col = o.col;
+    d->ptr = c.d;
+    d->stride = c.stride;
+    return MBC_OK;
+}
+
+int32_t build_terms(const mbc_table* t, const mbc_term* terms, int32_t nterms, DevTerm* out) {
+    if (nterms < 0 || nterms > kMaxTerms) MBC_FAIL(MBC_ERR_UNSUPPORTED, "%d predicate terms (max %d)", nterms, kMaxTerms);
+    for (int k = 0; k < nterms; ++k) {
+        const mbc_term& s = terms[k];
+        DevTerm& d = out[k];
+        memset(&d, 0, sizeof(d));
+        if (k > 0 && s.conj_id < terms[k - 1].conj_id) MBC_FAIL(MBC_ERR_ARG, "terms must be sorted by conj_id");
+        d.op = s.op;
+        if (s.op < 0 || s.op > MBC_OP_RANGE) MBC_FAIL(MBC_ERR_ARG, "term %d: unknown operator %d", k, s.op);
+        // comparison type = type of the lhs (PredEval.java:64,70,77,84,89)
+        int cmp_type;
+        if (s.lhs.kind == MBC_OPERAND_LITERAL) cmp_type = s.lhs.type;
+        else {
+            if (s.lhs.col < 0 || s.lhs.col >= (int)t->cols.size())
+                MBC_FAIL(MBC_ERR_ARG, "term %d: column %d out of range", k, s.lhs.col);
+            cmp_type = t->cols[s.lhs.col].type;
+        }
+        if (cmp_type != MBC_ATTR_INTEGER && cmp_type != MBC_ATTR_REAL && cmp_type != MBC_ATTR_STRING)
+            MBC_FAIL(MBC_ERR_ARG, "term %d: comparison type %d", k, cmp_type);
+        if (s.lhs.kind == MBC_OPERAND_LITERAL && s.rhs.kind == MBC_OPERAND_LITERAL && cmp_type == MBC_ATTR_STRING)
+            MBC_FAIL(MBC_ERR_UNSUPPORTED, "term %d: literal-vs-literal string comparison (fold it on the host)", k);
+        d.cmp_type = cmp_type;
+        MBC_TRY(fill_operand(t, s.lhs, cmp_type, &d.lhs, &d, k));
+        MBC_TRY(fill_operand(t, s.rhs, cmp_type, &d.rhs, &d, k));
+        d.end_conj = (k == nterms - 1 || terms[k + 1].conj_id != s.conj_id) ? 1 : 0;
+    }
+    return MBC_OK;
+}
+
+static int scan_grid(mbc_ctx* ctx, int ntiles) {
+    static int blocks_per_sm = 0;
+    if (blocks_per_sm == 0) {
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, scan_kernel, kScanThreads, 0) != cudaSuccess ||
+            blocks_per_sm < 1)
+            blocks_per_sm = 1;
+    }
+    return std::max(1, std::min(ntiles, ctx->sm_count * blocks_per_sm));
+}
+
+// tuple layout of a projected field list (iterator/TupleUtils.java:295-341 setup_op_tuple)
+static int32_t tuple_layout(const std::vector<mbc_result::Col>& cols, TupleParams* tp) {
+    int n = (int)cols.size();
+    int off = (n + 2) * 2;
+    tp->nfields = n;
+    for (int i = 0; i < n; ++i) {
+        tp->f[i].src = cols[i].d;
+        tp->f[i].type = cols[i].type;
+        tp->f[i].width = cols[i].width;
+        tp->f[i].stride = cols[i].stride;
+        tp->f[i].offset = off;
+        off += cols[i].type == MBC_ATTR_STRING ? cols[i].width + 2 : 4;
+    }
+    if (off > 1024) MBC_FAIL(MBC_ERR_UNSUPPORTED, "projected tuple of %d bytes exceeds the reference's 1024-byte Tuple", off);
+    tp->tuple_len = off;
+    return MBC_OK;
+}
+
+int32_t encode_tuples(mbc_result* r) {
+    mbc_ctx* ctx = r->ctx;
+    TupleParams tp;
+    memset(&tp, 0, sizeof(tp));
+    MBC_TRY(tuple_layout(r->cols, &tp));
+    r->tuple_len = tp.tuple_len;
+    if (r->count == 0) return MBC_OK;
+    MBC_TRY(dev_alloc(ctx, (void**)&r->d_tuples, (size_t)r->count * tp.tuple_len, false));
+    tp.count = r->count;
+    tp.out = r->d_tuples;
+    int rows = std::max(16, std::min(128, (40 * 1024 / tp.tuple_len) / 16 * 16));
+    tp.rows_per_cta = rows;
+    int64_t grid = (r->count + rows - 1) / rows;
+    size_t smem = (size_t)rows * tp.tuple_len;
+    tuple_encode_kernel<<<(unsigned)grid, 128, smem, ctx->stream>>>(tp);
+    ctx->launches++;
+    MBC_CUDA(cudaGetLastError());
+    return MBC_OK;
+}
+
+static int32_t pinned_for(mbc_result* r, void** p, size_t bytes) {
+    size_t actual = 0;
+    MBC_TRY(pinned_alloc(r->ctx, p, bytes, &actual));
+    r->pinned.push_back({*p, actual});
+    return MBC_OK;
+}
+
+int32_t finish_result_host(mbc_result* r) {
+    mbc_ctx* ctx = r->ctx;
+    if ((r->want & MBC_WANT_TUPLES) && !r->cols.empty()) MBC_TRY(encode_tuples(r));
+    if (!(r->want & MBC_WANT_HOST)) return MBC_OK;
+    const size_t n = (size_t)r->count;
+    if ((r->want & MBC_WANT_POSITIONS) && r->d_pos) {
+        MBC_TRY(pinned_for(r, (void**)&r->h_pos, n * 8));
+        if (n) MBC_CUDA(cudaMemcpyAsync(r->h_pos, r->d_pos, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        if (r->d_pos2) {
+            MBC_TRY(pinned_for(r, (void**)&r->h_pos2, n * 8));
+            if (n) MBC_CUDA(cudaMemcpyAsync(r->h_pos2, r->d_pos2, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        }
+    }
+    if (r->want & MBC_WANT_COLUMNS) {
+        for (auto& c : r->cols) {
+            MBC_TRY(pinned_for(r, &c.h, n * c.width));
+            if (!n) continue;
+            if (c.stride == c.width)
+                MBC_CUDA(cudaMemcpyAsync(c.h, c.d, n * c.width, cudaMemcpyDeviceToHost, ctx->stream));
+            else
+                MBC_CUDA(cudaMemcpy2DAsync(c.h, c.width, c.d, c.stride, c.width, n, cudaMemcpyDeviceToHost, ctx->stream));
+        }
+    }
+    if ((r->want & MBC_WANT_TUPLES) && !r->cols.empty()) {
+        MBC_TRY(pinned_for(r, (void**)&r->h_tuples, n * r->tuple_len));
+        if (n) MBC_CUDA(cudaMemcpyAsync(r->h_tuples, r->d_tuples, n * r->tuple_len, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    if ((r->want & MBC_WANT_BITMAP) && r->d_bitmap) {
+        size_t words64 = (size_t)(r->nrows + 63) / 64;
+        MBC_TRY(pinned_for(r, (void**)&r->h_bitmap, words64 * 8 + 8));
+        if (words64) MBC_CUDA(cudaMemcpyAsync(r->h_bitmap, r->d_bitmap, words64 * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    MBC_CUDA(cudaStreamSynchronize(ctx->stream));
+    return MBC_OK;
+}
+
+static int32_t build_aggs(const mbc_table* t, const mbc_aggspec* aggs, int32_t nagg, DevAgg* dev) {
+    if (nagg < 0 || nagg > kMaxAgg) MBC_FAIL(MBC_ERR_UNSUPPORTED, "%d aggregates (max %d)", nagg, kMaxAgg);
+    memset(dev, 0, sizeof(DevAgg) * kMaxAgg);
+    for (int a = 0; a < nagg; ++a) {
+        DevAgg& d = dev[a];
+        d.kind = aggs[a].kind;
+        d.col = -1;
+        if (d.kind == MBC_AGG_COUNT) { d.type = MBC_ATTR_INTEGER; continue; }
+        if (d.kind < 0 || d.kind > MBC_AGG_MAX) MBC_FAIL(MBC_ERR_ARG, "aggregate %d: unknown kind %d", a, d.kind);
+        int c = aggs[a].col;
+        if (c < 0 || c >= (int)t->cols.size()) MBC_FAIL(MBC_ERR_ARG, "aggregate %d: column %d out of range", a, c);
+        if (t->cols[c].type == MBC_ATTR_STRING) MBC_FAIL(MBC_ERR_UNSUPPORTED, "aggregate %d over a string column", a);
+        d.type = t->cols[c].type;
+        d.col = c;
+        d.src = t->cols[c].d;
+    }
+    return MBC_OK;
+}
+
+void decode_aggs(mbc_result* r, const DevAgg* dev, int nagg, const unsigned long long* raw) {
+    r->aggs.resize(nagg);
+    for (int a = 0; a < nagg; ++a) {
+        mbc_result::Agg& g = r->aggs[a];
+        g.kind = dev[a].kind;
+        g.type = dev[a].type;
+        bool integral = g.kind == MBC_AGG_COUNT || g.type == MBC_ATTR_INTEGER;
+        if (integral) {
+            g.i = (int64_t)raw[a];
+            g.f = (double)g.i;
+        } else {
+            double d;
+            memcpy(&d, &raw[a], 8);
+            g.f = d;
+            g.i = (int64_t)d;
+        }
+        g.valid = (g.kind == MBC_AGG_COUNT || g.kind == MBC_AGG_SUM) ? 1 : (r->count > 0);
+        if (!g.valid) { g.i = 0; g.f = 0.0; }
+    }
+}
+
+// Workspace layout: [ticket:u32 @0][count:i64 @16][status: max_launch_tiles u64 @64][partials: nagg*total_tiles u64][agg out: 8 u64]
+struct Workspace {
+    unsigned int* ticket;
+    long long* count;
+    unsigned long long* status;
+    unsigned long long* partials;
+    unsigned long long* agg_out;
+};
+
+static int32_t carve_workspace(mbc_ctx* ctx, int64_t launch_tiles, int64_t total_tiles, int nagg, Workspace* w) {
+    size_t status_bytes = (size_t)launch_tiles * 8;
+    size_t partial_bytes = (size_t)std::max(nagg, 1) * total_tiles * 8;
+    size_t total = 64 + status_bytes + partial_bytes + kMaxAgg * 8 + 64;
+    MBC_TRY(ensure_workspace(ctx, total));
+    char* b = (char*)ctx->ws;
+    w->ticket = (unsigned int*)b;
+    w->count = (long long*)(b + 16);
+    w->status = (unsigned long long*)(b + 64);
+    w->partials = (unsigned long long*)(b + 64 + status_bytes);
+    w->agg_out = (unsigned long long*)(b + 64 + status_bytes + partial_bytes);
+    return MBC_OK;
+}
+
+// A scan job: the parameter block, the result that owns the output buffers, and the workspace.
+// `schema` supplies column types/strides; bind_table() points the job at the table whose rows the
+// next launch reads (the resident table, or one of the staging tables of mbc_scan_host).
+struct ScanJob {
+    ScanParams p;
+    mbc_result* r = nullptr;
+    Workspace w;
+    int64_t total_tiles = 0;
+};
+
+static int32_t prepare_job(const mbc_table* schema, const ScanRequest& rq, int64_t capacity_rows, int64_t launch_tiles,
+                           int64_t total_tiles, ScanJob* job) {
+    mbc_ctx* ctx = schema->ctx;
+    if (rq.nproj < 0 || rq.nproj > kMaxProj) MBC_FAIL(MBC_ERR_UNSUPPORTED, "%d projected fields (max %d)", rq.nproj, kMaxProj);
+    if ((rq.nterms > 0 && !rq.terms) || (rq.nproj > 0 && !rq.proj_cols) || (rq.nagg > 0 && !rq.aggs))
+        MBC_FAIL(MBC_ERR_ARG, "scan: NULL array with a non-zero count");
+    if (launch_tiles > INT32_MAX || total_tiles > INT32_MAX) MBC_FAIL(MBC_ERR_UNSUPPORTED, "table too large for one device scan");
+    ScanParams& p = job->p;
+    memset(&p, 0, sizeof(p));
+    MBC_TRY(build_terms(schema, rq.terms, rq.nterms, p.terms));
+    p.nterms = rq.nterms;
+    p.nagg = (rq.want & MBC_WANT_AGG) ? rq.nagg : 0;
+    MBC_TRY(build_aggs(schema, rq.aggs, p.nagg, p.aggs));
+    for (int c = 0; c < rq.nproj; ++c)
+        if (rq.proj_cols[c] < 0 || rq.proj_cols[c] >= (int)schema->cols.size())
+            MBC_FAIL(MBC_ERR_ARG, "projection field %d: column %d out of range", c, rq.proj_cols[c]);
+
+    mbc_result* r = new mbc_result();
+    job->r = r;
+    r->ctx = ctx;
+    r->want = rq.want;
+    r->capacity = capacity_rows;
+    const bool want_cols = (rq.want & (MBC_WANT_COLUMNS | MBC_WANT_TUPLES)) != 0 && rq.nproj > 0;
+    if (rq.want & MBC_WANT_POSITIONS) MBC_TRY(dev_alloc(ctx, (void**)&r->d_pos, (size_t)capacity_rows * 8, false));
+    if (want_cols) {
+        for (int c = 0; c < rq.nproj; ++c) {
+            const Column& col = schema->cols[rq.proj_cols[c]];
+            mbc_result::Col rc{col.type, col.width, col.stride, nullptr, nullptr};
+            MBC_TRY(dev_alloc(ctx, &rc.d, (size_t)capacity_rows * col.stride, false));
+            r->cols.push_back(rc);
+            p.proj[c].dst = rc.d;
+            p.proj[c].stride = col.stride;
+            p.proj[c].col = rq.proj_cols[c];
+        }
+        p.nproj = rq.nproj;
+    }
+    MBC_TRY(dev_alloc(ctx, (void**)&r->d_aggs, (kMaxAgg + 1) * 8, true));
+    MBC_TRY(carve_workspace(ctx, launch_tiles, total_tiles, p.nagg, &job->w));
+    job->total_tiles = total_tiles;
+    p.total_tiles = (int)total_tiles;
+    p.status = job->w.status;
+    p.ticket = job->w.ticket;
+    p.count = job->w.count;
+    p.partials = job->w.partials;
+    p.out_pos = r->d_pos;
+    return MBC_OK;
+}
+
+static void bind_table(ScanJob* job, const mbc_table* t) {
+    ScanParams& p = job->p;
+    for (int k = 0; k < p.nterms; ++k) {
+        if (p.terms[k].lhs.kind == 1) p.terms[k].lhs.ptr = t->cols[p.terms[k].lhs.col].d;
+        if (p.terms[k].rhs.kind == 1) p.terms[k].rhs.ptr = t->cols[p.terms[k].rhs.col].d;
+    }
+    for (int c = 0; c < p.nproj; ++c) p.proj[c].src = t->cols[p.proj[c].col].d;
+    for (int a = 0; a < p.nagg; ++a)
+        if (p.aggs[a].col >= 0) p.aggs[a].src = t->cols[p.aggs[a].col].d;
+    p.deleted = t->has_deleted ? t->d_deleted : nullptr;
+    p.nrows = t->nrows;
+    p.pos_base = t->pos_base;
+    p.ntiles = (int)((t->nrows + kTileRows - 1) / kTileRows);
+}
+
+// one launch over the bound table; its tiles occupy [tile_base, tile_base + ntiles) of the partials
+static int32_t launch_job(ScanJob* job, int tile_base, bool first) {
+    mbc_ctx* ctx = job->r->ctx;
+    ScanParams& p = job->p;
+    p.tile_base = tile_base;
+    if (p.ntiles == 0) return MBC_OK;
+    // ticket + status words are per launch; the running output offset survives between launches
+    if (first) MBC_CUDA(cudaMemsetAsync(ctx->ws, 0, 64 + (size_t)p.ntiles * 8, ctx->stream));
+    else {
+        MBC_CUDA(cudaMemsetAsync(p.ticket, 0, 4, ctx->stream));
+        MBC_CUDA(cudaMemsetAsync(p.status, 0, (size_t)p.ntiles * 8, ctx->stream));
+    }
+    scan_kernel<<<scan_grid(ctx, p.ntiles), kScanThreads, 0, ctx->stream>>>(p);
+    ctx->launches++;
+    MBC_CUDA(cudaGetLastError());
+    return MBC_OK;
+}
+
+static int32_t finish_job(ScanJob* job, int64_t tiles_done) {
+    mbc_ctx* ctx = job->r->ctx;
+    ScanParams& p = job->p;
+    mbc_result* r = job->r;
+    if (tiles_done == 0) MBC_CUDA(cudaMemsetAsync(ctx->ws, 0, 64, ctx->stream));
+    if (p.nagg > 0) {
+        AggList list;
+        memcpy(list.g, p.aggs, sizeof(list.g));
+        agg_finish_kernel<<<p.nagg, 256, 0, ctx->stream>>>(job->w.partials, (int)job->total_tiles, (int)tiles_done, list,
+                                                          job->w.agg_out);
+        ctx->launches++;
+        MBC_CUDA(cudaGetLastError());
+    }
+    end_timing(ctx);
+    // count + aggregates come back in one small copy
+    unsigned long long host_small[kMaxAgg + 1];
+    MBC_CUDA(cudaMemcpyAsync(r->d_aggs, job->w.agg_out, kMaxAgg * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    MBC_CUDA(cudaMemcpyAsync(r->d_aggs + kMaxAgg, job->w.count, 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    MBC_CUDA(cudaMemcpyAsync(host_small, r->d_aggs, sizeof(host_small), cudaMemcpyDeviceToHost, ctx->stream));
+    MBC_CUDA(cudaStreamSynchronize(ctx->stream));
+    r->count = (int64_t)host_small[kMaxAgg];
+    decode_aggs(r, p.aggs, p.nagg, host_small);
+    return finish_result_host(r);
+}
+
+int32_t run_scan(const ScanRequest& rq, mbc_result** out) {
+    mbc_table* t = rq.table;
+    if (!t || !out) MBC_FAIL(MBC_ERR_ARG, "scan: table/out is NULL");
+    *out = nullptr;
+    mbc_ctx* ctx = t->ctx;
+    MBC_CUDA(cudaSetDevice(ctx->device));
+    const int64_t ntiles = (t->nrows + kTileRows - 1) / kTileRows;
+    ScanJob job;
+    int32_t s = prepare_job(t, rq, t->nrows, std::max<int64_t>(ntiles, 1), std::max<int64_t>(ntiles, 1), &job);
+    if (s == MBC_OK) {
+        mbc_result* r = job.r;
+        r->nrows = t->nrows;
+        job.p.sel_bitmap = rq.d_sel_bitmap;
+        if (rq.want & MBC_WANT_BITMAP) {
+            s = dev_alloc(ctx, (void**)&r->d_bitmap, (size_t)t->words_pad * 4, true);
+            r->bitmap_words32 = t->words_pad;
+            job.p.out_bitmap = r->d_bitmap;
+        }
+    }
+    if (s == MBC_OK) {
+        bind_table(&job, t);
+        begin_timing(ctx);
+        s = launch_job(&job, 0, true);
+    }
+    if (s == MBC_OK) s = finish_job(&job, ntiles);
+    if (s != MBC_OK) {
+        if (job.r) mbc_result_free(job.r);
+        return s;
+    }
+    *out = job.r;
+    return MBC_OK;
+}
+
+// Host-resident columns: stream row chunks through two staging tables.  The copy stream uploads
+// chunk k+1 while the scan of chunk k runs; every chunk appends to the same result buffers (the
+// look-back of a chunk starts from the running output offset left by the previous one).
+static int32_t run_scan_host(mbc_ctx* ctx, int32_t ncols, const mbc_coldesc* cols, const void* const* host_cols,
+                             int64_t nrows, int64_t position_base, const ScanRequest& rq_in, mbc_result** out) {
+    *out = nullptr;
+    MBC_CUDA(cudaSetDevice(ctx->device));
+    const int64_t chunk_rows = 4 << 20;                      // 4 Mi rows per chunk (multiple of the tile)
+    const int64_t nchunks = std::max<int64_t>(1, (nrows + chunk_rows - 1) / chunk_rows);
+    const int64_t stage_rows = std::min<int64_t>(chunk_rows, std::max<int64_t>(nrows, 1));
+    mbc_table* stage[2] = {nullptr, nullptr};
+    cudaEvent_t ev_up[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+    ScanJob job;
+    int32_t s = MBC_OK;
+    auto cleanup = [&]() {
+        for (int b = 0; b < 2; ++b) {
+            if (stage[b]) mbc_table_free(stage[b]);
+            if (ev_up[b]) cudaEventDestroy(ev_up[b]);
+            if (ev_done[b]) cudaEventDestroy(ev_done[b]);
+        }
+    };
+    for (int b = 0; b < 2 && s == MBC_OK; ++b) {
+        s = mbc_table_create(ctx, ncols, cols, stage_rows, position_base, &stage[b]);
+        if (s == MBC_OK && cudaEventCreateWithFlags(&ev_up[b], cudaEventDisableTiming) != cudaSuccess) s = MBC_ERR_CUDA;
+        if (s == MBC_OK && cudaEventCreateWithFlags(&ev_done[b], cudaEventDisableTiming) != cudaSuccess) s = MBC_ERR_CUDA;
+    }
+    if (s != MBC_OK) { cleanup(); return s; }
+
+    ScanRequest rq = rq_in;
+    rq.table = stage[0];
+    const int64_t tiles_per_chunk = (stage_rows + kTileRows - 1) / kTileRows;
+    s = prepare_job(stage[0], rq, nrows, tiles_per_chunk, tiles_per_chunk * nchunks, &job);
+    if (s != MBC_OK) { if (job.r) mbc_result_free(job.r); cleanup(); return s; }
+    job.r->nrows = nrows;
+
+    // which columns does the query touch?
+    std::vector<char> used(ncols, 0);
+    for (int k = 0; k < job.p.nterms; ++k) {
+        if (job.p.terms[k].lhs.kind == 1) used[job.p.terms[k].lhs.col] = 1;
+        if (job.p.terms[k].rhs.kind == 1) used[job.p.terms[k].rhs.col] = 1;
+    }
+    for (int c = 0; c < job.p.nproj; ++c) used[job.p.proj[c].col] = 1;
+    for (int a = 0; a < job.p.nagg; ++a) if (job.p.aggs[a].col >= 0) used[job.p.aggs[a].col] = 1;
+
+    // the staging tables were zero-filled on ctx->stream; the copy stream must not overtake that
+    cudaEvent_t ev_init;
+    cudaEventCreateWithFlags(&ev_init, cudaEventDisableTiming);
+    cudaEventRecord(ev_init, ctx->stream);
+    cudaStreamWaitEvent(ctx->copy_stream, ev_init, 0);
+    cudaEventDestroy(ev_init);
+
+    begin_timing(ctx);
+    int64_t tiles_done = 0;
+    for (int64_t k = 0; k < nchunks && s == MBC_OK; ++k) {
+        const int b = (int)(k & 1);
+        const int64_t row0 = k * chunk_rows;
+        const int64_t n = std::min<int64_t>(chunk_rows, nrows - row0);
+        if (n <= 0) break;
+        mbc_table* st = stage[b];
+        if (k >= 2) cudaStreamWaitEvent(ctx->copy_stream, ev_done[b], 0);    // staging buffer is free again
+        for (int c = 0; c < ncols && s == MBC_OK; ++c) {
+            if (!used[c]) continue;
+            const Column& col = st->cols[c];
+            const char* src = (const char*)host_cols[c] + (size_t)row0 * col.width;
+            cudaError_t e = col.stride == col.width
+                ? cudaMemcpyAsync(col.d, src, (size_t)n * col.width, cudaMemcpyHostToDevice, ctx->copy_stream)
+                : cudaMemcpy2DAsync(col.d, col.stride, src, col.width, col.width, (size_t)n, cudaMemcpyHostToDevice, ctx->copy_stream);
+            if (e != cudaSuccess) { set_error("H2D chunk %lld col %d: %s", (long long)k, c, cudaGetErrorString(e)); s = MBC_ERR_CUDA; }
+        }
+        if (s != MBC_OK) break;
+        cudaEventRecord(ev_up[b], ctx->copy_stream);
+        cudaStreamWaitEvent(ctx->stream, ev_up[b], 0);
+        st->nrows = n;
+        st->pos_base = position_base + row0;
+        bind_table(&job, st);
+        s = launch_job(&job, (int)tiles_done, k == 0);
+        tiles_done += job.p.ntiles;
+        cudaEventRecord(ev_done[b], ctx->stream);
+    }
+    if (s == MBC_OK) s = finish_job(&job, tiles_done);
+    cudaStreamSynchronize(ctx->copy_stream);
+    cudaStreamSynchronize(ctx->stream);
+    cleanup();
+    if (s != MBC_OK) { if (job.r) mbc_result_free(job.r); return s; }
+    *out = job.r;
+    return MBC_OK;
+}
+
+}  // namespace mbc
+
+using namespace mbc;
+
+extern "C" int32_t mbc_scan(mbc_table* t, const mbc_term* terms, int32_t nterms, const int32_t* proj_cols,
+                            int32_t nproj, uint32_t want, const mbc_aggspec* aggs, int32_t nagg, mbc_result** out) {
+    ScanRequest rq;
+    rq.table = t;
+    rq.terms = terms;
+    rq.nterms = nterms;
+    rq.proj_cols = proj_cols;
+    rq.nproj = nproj;
+    rq.want = want;
+    rq.aggs = aggs;
+    rq.nagg = nagg;
+    return run_scan(rq, out);
+}
+
+extern "C" int32_t mbc_scan_host(mbc_ctx* ctx, int32_t ncols, const mbc_coldesc* cols, const void* const* host_cols,
+                                 int64_t nrows, int64_t position_base, const mbc_term* terms, int32_t nterms,
+                                 const int32_t* proj_cols, int32_t nproj, uint32_t want, const mbc_aggspec* aggs,
+                                 int32_t nagg, mbc_result** out) {
+    if (!ctx || !cols || !host_cols || !out || ncols <= 0 || nrows < 0) MBC_FAIL(MBC_ERR_ARG, "mbc_scan_host: bad argument");
+    if (want & MBC_WANT_BITMAP) MBC_FAIL(MBC_ERR_UNSUPPORTED, "mbc_scan_host: MBC_WANT_BITMAP needs a resident table");
+    ScanRequest rq;
+    rq.terms = terms;
+    rq.nterms = nterms;
+    rq.proj_cols = proj_cols;
+    rq.nproj = nproj;
+    rq.want = want;
+    rq.aggs = aggs;
+    rq.nagg = nagg;
+    return run_scan_host(ctx, ncols, cols, host_cols, nrows, position_base, rq, out);
+}

@@ -1,0 +1,632 @@
+// mbc_scan_kernels.cuh -- K2/K5: fused CNF filter -> ordered compaction -> projection -> aggregates.
+//
+// One launch replaces the reference's per-row loop
+//     iterator/ColumnarFileScan.java:156-172  while (scan.getNext) if (PredEval.Eval) Project
+// together with iterator/PredEval.java:25-183 (CNF evaluation, comparison type = type of the
+// lhs), iterator/TupleUtils.java:35-87 (int / float / string compare) and
+// iterator/Projection.java:103-144 (copy of the selected fields), for a whole table.
+//
+// Shape of the kernel (sm_100a; HBM-bound integer/byte work, no tensor cores):
+//   * a warp owns 512 consecutive rows; in "unit" u lane l owns rows u*128+l*4+{0..3}, so every
+//     4-byte column is read with one coalesced 128-bit load per unit (512 B per warp instruction);
+//     16-byte string rows are read lane-contiguously (row = k*32+lane, 512 B per instruction) and
+//     the result bits are transposed into the 4-rows-per-lane layout with warp ballots;
+//   * the CNF is a small term program in the kernel parameters; the operator/type switch runs once
+//     per term per 16 rows, the compares themselves are straight-line;
+//   * survivors are counted with one packed warp scan (four 8-bit unit counters in one register),
+//     a CTA scan over 8 warp totals, and a decoupled look-back over per-tile status words, so the
+//     output is written in ascending position order in a single pass (the reference emits rows in
+//     position order; bit-exact position lists need order, not atomics);
+//   * projection columns that are not predicate columns are only touched for 4-row groups that
+//     have a survivor (late materialisation: at low selectivity most sectors are never read);
+//   * COUNT/SUM/MIN/MAX partials are produced per tile and reduced in tile order by a second
+//     tiny kernel, so real-valued sums are reproducible run to run.
+#pragma once
+#include <cstring>
+#include <algorithm>
+
+#include "mbc_internal.cuh"
+
+namespace mbc {
+
+// ---- kernel parameter block ---------------------------------------------------------------
+
+struct DevOperand {
+    const void* ptr;     // column base (kind 1) or unused
+    int32_t kind;        // 0 literal, 1 column
+    int32_t stride;      // device row stride of the column
+    uint32_t bits;       // raw 32-bit literal (int or float bits)
+    int32_t col;         // host bookkeeping: table column the pointer was taken from
+};
+
+struct DevTerm {
+    int32_t op;          // MBC_OP_*
+    int32_t cmp_type;    // MBC_ATTR_INTEGER / REAL / STRING
+    int32_t end_conj;    // 1 = last term of its conjunct
+    int32_t lit_words;   // string literal length in 32-bit words (zero padded)
+    DevOperand lhs, rhs;
+    uint32_t lit[kMaxLit / 4];   // zero padded string literal (whichever side is the literal)
+};
+
+struct DevProj {
+    const void* src;
+    void* dst;
+    int32_t stride;      // 4, or the device string stride (multiple of 4)
+    int32_t col;         // host bookkeeping
+};
+
+struct DevAgg {
+    const void* src;
+    int32_t kind;        // MBC_AGG_*
+    int32_t type;        // MBC_ATTR_INTEGER / REAL
+    int32_t col;         // host bookkeeping
+    int32_t pad;
+};
+
+struct ScanParams {
+    int64_t nrows;
+    int64_t pos_base;
+    int32_t ntiles;
+    int32_t nterms;
+    int32_t nproj;
+    int32_t nagg;
+    int32_t tile_base;            // index of this launch's first tile in the partials arrays
+    int32_t total_tiles;          // stride of the partials arrays
+    const uint32_t* sel_bitmap;   // optional precomputed selection
+    const uint32_t* deleted;      // optional markedDeleted bitmap
+    int64_t* out_pos;
+    uint32_t* out_bitmap;
+    unsigned long long* status;   // one look-back word per tile
+    unsigned int* ticket;
+    long long* count;             // in: running output offset, out: offset after this launch
+    unsigned long long* partials; // [nagg][total_tiles]
+    DevTerm terms[kMaxTerms];
+    DevProj proj[kMaxProj];
+    DevAgg aggs[kMaxAgg];
+};
+
+// ---- device helpers -------------------------------------------------------------------------
+
+__device__ __forceinline__ uint4 ldg128(const void* p) {
+    return __ldg(reinterpret_cast<const uint4*>(p));
+}
+
+__device__ __forceinline__ uint32_t bswap32(uint32_t x) { return __byte_perm(x, 0, 0x0123); }
+
+// result bit of one comparison given "less" and "equal"
+__device__ __forceinline__ bool apply_op(int op, bool lt, bool eq) {
+    switch (op) {
+        case MBC_OP_EQ: return eq;
+        case MBC_OP_LT: return lt;
+        case MBC_OP_GT: return !(lt || eq);
+        case MBC_OP_NE: return !eq;
+        case MBC_OP_LE: return lt || eq;
+        case MBC_OP_GE: return !lt;
+        case MBC_OP_NOT: return !eq;      // PredEval.java:158-160: aopNOT behaves as NE
+        default: return false;            // aopNOP / opRANGE never match
+    }
+}
+
+// 16 result bits of `a op b` from per-row lt / eq bit masks
+__device__ __forceinline__ uint32_t mask_op(int op, uint32_t lt, uint32_t eq) {
+    switch (op) {
+        case MBC_OP_EQ: return eq;
+        case MBC_OP_LT: return lt;
+        case MBC_OP_GT: return ~(lt | eq) & 0xFFFFu;
+        case MBC_OP_NE: return ~eq & 0xFFFFu;
+        case MBC_OP_LE: return lt | eq;
+        case MBC_OP_GE: return ~lt & 0xFFFFu;
+        case MBC_OP_NOT: return ~eq & 0xFFFFu;
+        default: return 0u;
+    }
+}
+
+// load the 16 raw 32-bit values this thread owns (4 units x one 128-bit load), or broadcast a literal
+__device__ __forceinline__ void load_operand32(const DevOperand& o, int64_t thread_row0, uint32_t v[kRowsPerThread]) {
+    if (o.kind == 0) {
+#pragma unroll
+        for (int i = 0; i < kRowsPerThread; ++i) v[i] = o.bits;
+    } else {
+        const uint32_t* base = reinterpret_cast<const uint32_t*>(o.ptr) + thread_row0;
+#pragma unroll
+        for (int u = 0; u < kUnits; ++u) {
+            uint4 q = ldg128(base + u * kUnitRows);
+            v[u * 4 + 0] = q.x;
+            v[u * 4 + 1] = q.y;
+            v[u * 4 + 2] = q.z;
+            v[u * 4 + 3] = q.w;
+        }
+    }
+}
+
+// TupleUtils.java:48-57 (int) and :59-68 (float): 16 rows at once.  Bit u*4+j = row u*128+lane*4+j.
+__device__ __forceinline__ uint32_t eval_term32(const DevTerm& t, int64_t thread_row0) {
+    uint32_t a[kRowsPerThread], b[kRowsPerThread];
+    load_operand32(t.lhs, thread_row0, a);
+    load_operand32(t.rhs, thread_row0, b);
+    uint32_t lt = 0, eq = 0;
+    if (t.cmp_type == MBC_ATTR_INTEGER) {
+#pragma unroll
+        for (int i = 0; i < kRowsPerThread; ++i) {
+            lt |= (uint32_t)((int32_t)a[i] < (int32_t)b[i]) << i;
+            eq |= (uint32_t)(a[i] == b[i]) << i;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < kRowsPerThread; ++i) {
+            float x = __uint_as_float(a[i]), y = __uint_as_float(b[i]);
+            lt |= (uint32_t)(x < y) << i;
+            eq |= (uint32_t)(x == y) << i;
+        }
+    }
+    return mask_op(t.op, lt, eq);
+}
+
+// one string operand word w of row `row`: column word (zero beyond the stride) or literal word
+__device__ __forceinline__ uint32_t str_word(const DevOperand& o, const uint32_t* lit, int lit_words, int64_t row, int w) {
+    if (o.kind == 0) return w < lit_words ? lit[w] : 0u;
+    int words = o.stride >> 2;
+    if (w >= words) return 0u;
+    return __ldg(reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(o.ptr) + row * o.stride) + w);
+}
+
+// TupleUtils.java:70-81: String.compareTo on two zero-padded fixed-width byte strings.  For strings
+// without NUL bytes (the contract) unsigned byte order over the padded width is compareTo's order.
+// Rows are taken lane-contiguously (row = u*128 + k*32 + lane) and the 128 result bits of a unit
+// are transposed into the 4-rows-per-lane layout through ballots.
+__device__ __forceinline__ uint32_t eval_term_str(const DevTerm& t, int64_t warp_row0, int lane) {
+    int wl = t.lhs.kind == 0 ? t.lit_words : (t.lhs.stride >> 2);
+    int wr = t.rhs.kind == 0 ? t.lit_words : (t.rhs.stride >> 2);
+    int nwords = max(wl, wr);
+    const bool fast16 = (t.lhs.kind != 0) != (t.rhs.kind != 0) &&           // column vs literal
+                        (t.lhs.kind != 0 ? t.lhs.stride : t.rhs.stride) == 16 && t.lit_words <= 4;
+    uint32_t mask = 0;
+#pragma unroll
+    for (int u = 0; u < kUnits; ++u) {
+        uint32_t bal[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            int64_t row = warp_row0 + u * kUnitRows + k * 32 + lane;
+            bool lt = false, eq = true;
+            if (fast16) {
+                const DevOperand& c = t.lhs.kind != 0 ? t.lhs : t.rhs;
+                uint4 q = ldg128(reinterpret_cast<const char*>(c.ptr) + row * 16);
+                uint32_t cw[4] = {q.x, q.y, q.z, q.w};
+                bool clt = false, ceq = true;   // column vs literal
+#pragma unroll
+                for (int w = 0; w < 4; ++w) {
+                    uint32_t x = bswap32(cw[w]), y = bswap32(t.lit[w]);
+                    if (ceq && x != y) { clt = x < y; ceq = false; }
+                }
+                if (t.lhs.kind != 0) { lt = clt; eq = ceq; }
+                else { lt = !clt && !ceq; eq = ceq; }
+            } else {
+                for (int w = 0; w < nwords; ++w) {
+                    uint32_t x = bswap32(str_word(t.lhs, t.lit, t.lit_words, row, w));
+                    uint32_t y = bswap32(str_word(t.rhs, t.lit, t.lit_words, row, w));
+                    if (x != y) { lt = x < y; eq = false; break; }
+                }
+            }
+            bal[k] = __ballot_sync(0xFFFFFFFFu, apply_op(t.op, lt, eq));
+        }
+        // lane l needs bits (l*4 .. l*4+3) of the 128-bit unit: word l/8, shift (l%8)*4
+        int sel = lane >> 3;
+        uint32_t word = sel == 0 ? bal[0] : sel == 1 ? bal[1] : sel == 2 ? bal[2] : bal[3];
+        mask |= ((word >> ((lane & 7) * 4)) & 0xFu) << (u * 4);
+    }
+    return mask;
+}
+
+// the 16 bits this thread owns out of a row bitmap (bit p = word p/32, bit p%32)
+__device__ __forceinline__ uint32_t load_bits(const uint32_t* bm, int64_t warp_row0, int lane) {
+    uint32_t mask = 0;
+    const uint32_t* w = bm + (warp_row0 >> 5) + (lane >> 3);
+#pragma unroll
+    for (int u = 0; u < kUnits; ++u) {
+        uint32_t word = __ldg(w + u * (kUnitRows / 32));
+        mask |= ((word >> ((lane & 7) * 4)) & 0xFu) << (u * 4);
+    }
+    return mask;
+}
+
+__device__ __forceinline__ long long warp_sum_i64(long long v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+    return v;
+}
+
+constexpr unsigned long long kFlagAgg  = 1ull << 62;
+constexpr unsigned long long kFlagIncl = 2ull << 62;
+constexpr unsigned long long kValMask  = (1ull << 62) - 1;
+
+// Decoupled look-back (single-pass chained scan) executed by warp 0.  Tiles are handed out through
+// an atomic ticket, so every predecessor of a running tile is itself running or finished.
+__device__ __forceinline__ long long lookback(volatile unsigned long long* status, int tile, long long total,
+                                               long long init, int lane) {
+    if (tile == 0) {
+        if (lane == 0) status[0] = kFlagIncl | (unsigned long long)(init + total);
+        return init;
+    }
+    if (lane == 0) status[tile] = kFlagAgg | (unsigned long long)total;
+    long long prefix = 0;
+    int idx = tile - 1 - lane;
+    while (true) {
+        unsigned long long s = kFlagIncl;          // tiles before tile 0: inclusive, value 0
+        if (idx >= 0) {
+            do { s = status[idx]; } while ((s >> 62) == 0);
+        }
+        uint32_t incl = __ballot_sync(0xFFFFFFFFu, (s >> 62) == 2);
+        if (incl) {
+            int first = __ffs(incl) - 1;           // nearest tile with an inclusive prefix
+            prefix += warp_sum_i64(lane <= first ? (long long)(s & kValMask) : 0ll);
+            break;
+        }
+        prefix += warp_sum_i64((long long)(s & kValMask));
+        idx -= 32;
+    }
+    if (lane == 0) status[tile] = kFlagIncl | (unsigned long long)(prefix + total);
+    return prefix;
+}
+
+// ---- the kernel ------------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(kScanThreads, 4) scan_kernel(const __grid_constant__ ScanParams p) {
+    __shared__ int s_tile;
+    __shared__ uint32_t s_warp_tot[kWarpsPerCta];
+    __shared__ uint32_t s_warp_base[kWarpsPerCta];
+    __shared__ long long s_tile_base;
+    __shared__ unsigned long long s_agg[kMaxAgg][kScanThreads];
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+
+    while (true) {
+        if (tid == 0) s_tile = (int)atomicAdd(p.ticket, 1u);
+        __syncthreads();
+        const int tile = s_tile;
+        if (tile >= p.ntiles) break;
+
+        const int64_t warp_row0 = (int64_t)tile * kTileRows + warp * kWarpRows;
+        const int64_t thread_row0 = warp_row0 + lane * kVec;
+
+        // ---- 1. qualifying mask of the 16 rows this thread owns ----------------------------
+        uint32_t mask = 0xFFFFu;
+        if (p.sel_bitmap) mask &= load_bits(p.sel_bitmap, warp_row0, lane);
+        if (p.nterms > 0) {
+            uint32_t acc = 0;
+            for (int k = 0; k < p.nterms; ++k) {                  // warp-uniform term program
+                const DevTerm& t = p.terms[k];
+                acc |= (t.cmp_type == MBC_ATTR_STRING) ? eval_term_str(t, warp_row0, lane)
+                                                       : eval_term32(t, thread_row0);
+                if (t.end_conj) { mask &= acc; acc = 0; }          // OR inside, AND across (PredEval.java:164-176)
+            }
+        }
+        if (p.deleted) mask &= ~load_bits(p.deleted, warp_row0, lane);   // TupleScan.java:85
+        if (warp_row0 + kWarpRows > p.nrows) {                     // rows past the end of the table
+#pragma unroll
+            for (int u = 0; u < kUnits; ++u)
+#pragma unroll
+                for (int j = 0; j < kVec; ++j)
+                    if (thread_row0 + u * kUnitRows + j >= p.nrows) mask &= ~(1u << (u * 4 + j));
+        }
+
+        // ---- 2. ranks: packed warp scan of the four unit counters --------------------------
+        uint32_t packed = __popc(mask & 0xFu) | (__popc(mask & 0xF0u) << 8) | (__popc(mask & 0xF00u) << 16) |
+                          (__popc(mask & 0xF000u) << 24);
+        uint32_t incl = packed;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t n = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if (lane >= o) incl += n;
+        }
+        const uint32_t tot = __shfl_sync(0xFFFFFFFFu, incl, 31);   // per-unit totals, each <= 128
+        const uint32_t excl = incl - packed;
+        uint32_t unit_off[kUnits];
+        unit_off[0] = 0;
+        unit_off[1] = tot & 0xFFu;
+        unit_off[2] = unit_off[1] + ((tot >> 8) & 0xFFu);
+        unit_off[3] = unit_off[2] + ((tot >> 16) & 0xFFu);
+        const uint32_t warp_total = unit_off[3] + (tot >> 24);
+        if (lane == 0) s_warp_tot[warp] = warp_total;
+
+        // ---- 3. per-thread aggregate partials over the survivors ----------------------------
+        for (int a = 0; a < p.nagg; ++a) {
+            const DevAgg& g = p.aggs[a];
+            unsigned long long out;
+            if (g.kind == MBC_AGG_COUNT) {
+                out = (unsigned long long)__popc(mask);
+            } else {
+                uint32_t v[kRowsPerThread];
+                if (mask) {
+                    const uint32_t* base = reinterpret_cast<const uint32_t*>(g.src) + thread_row0;
+#pragma unroll
+                    for (int u = 0; u < kUnits; ++u) {
+                        if ((mask >> (u * 4)) & 0xFu) {
+                            uint4 q = ldg128(base + u * kUnitRows);
+                            v[u * 4 + 0] = q.x; v[u * 4 + 1] = q.y; v[u * 4 + 2] = q.z; v[u * 4 + 3] = q.w;
+                        }
+                    }
+                }
+                if (g.type == MBC_ATTR_INTEGER) {
+                    long long acc = g.kind == MBC_AGG_SUM ? 0ll : g.kind == MBC_AGG_MIN ? (long long)INT32_MAX
+                                                                                        : (long long)INT32_MIN;
+#pragma unroll
+                    for (int i = 0; i < kRowsPerThread; ++i) {
+                        if ((mask >> i) & 1u) {
+                            long long x = (long long)(int32_t)v[i];
+                            acc = g.kind == MBC_AGG_SUM ? acc + x : g.kind == MBC_AGG_MIN ? min(acc, x) : max(acc, x);
+                        }
+                    }
+                    out = (unsigned long long)acc;
+                } else {
+                    double acc = g.kind == MBC_AGG_SUM ? 0.0 : g.kind == MBC_AGG_MIN ? (double)INFINITY
+                                                                                      : (double)-INFINITY;
+#pragma unroll
+                    for (int i = 0; i < kRowsPerThread; ++i) {
+                        if ((mask >> i) & 1u) {
+                            double x = (double)__uint_as_float(v[i]);
+                            acc = g.kind == MBC_AGG_SUM ? acc + x : g.kind == MBC_AGG_MIN ? fmin(acc, x) : fmax(acc, x);
+                        }
+                    }
+                    out = (unsigned long long)__double_as_longlong(acc);
+                }
+            }
+            s_agg[a][tid] = out;
+        }
+
+        // ---- optional selection bitmap (BitSet-compatible, bit p = word p/32 bit p%32) ------
+        if (p.out_bitmap) {
+#pragma unroll
+            for (int u = 0; u < kUnits; ++u) {
+                uint32_t w = ((mask >> (u * 4)) & 0xFu) << ((lane & 7) * 4);
+                w |= __shfl_xor_sync(0xFFFFFFFFu, w, 1);
+                w |= __shfl_xor_sync(0xFFFFFFFFu, w, 2);
+                w |= __shfl_xor_sync(0xFFFFFFFFu, w, 4);
+                if ((lane & 7) == 0) p.out_bitmap[(warp_row0 >> 5) + u * (kUnitRows / 32) + (lane >> 3)] = w;
+            }
+        }
+        __syncthreads();
+
+        // ---- 4. CTA scan of the warp totals + look-back (warp 0); tile partials (other warps) ----
+        if (warp == 0) {
+            uint32_t v = lane < kWarpsPerCta ? s_warp_tot[lane] : 0u;
+            uint32_t inc = v;
+#pragma unroll
+            for (int o = 1; o < kWarpsPerCta; o <<= 1) {
+                uint32_t n = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+                if (lane >= o) inc += n;
+            }
+            if (lane < kWarpsPerCta) s_warp_base[lane] = inc - v;
+            const long long tile_total = (long long)__shfl_sync(0xFFFFFFFFu, inc, kWarpsPerCta - 1);
+            long long init = 0;
+            if (tile == 0) init = *p.count;
+            const long long prefix = lookback(p.status, tile, tile_total, init, lane);
+            if (lane == 0) {
+                s_tile_base = prefix;
+                if (tile == p.ntiles - 1) *p.count = prefix + tile_total;
+            }
+        } else {
+            for (int a = warp - 1; a < p.nagg; a += kWarpsPerCta - 1) {
+                const DevAgg& g = p.aggs[a];
+                unsigned long long res;
+                if (g.kind == MBC_AGG_COUNT || (g.type == MBC_ATTR_INTEGER)) {
+                    long long acc = (g.kind == MBC_AGG_COUNT || g.kind == MBC_AGG_SUM) ? 0ll
+                                    : g.kind == MBC_AGG_MIN ? (long long)INT32_MAX : (long long)INT32_MIN;
+                    for (int i = lane; i < kScanThreads; i += 32) {
+                        long long x = (long long)s_agg[a][i];
+                        acc = (g.kind == MBC_AGG_COUNT || g.kind == MBC_AGG_SUM) ? acc + x
+                              : g.kind == MBC_AGG_MIN ? min(acc, x) : max(acc, x);
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        long long x = __shfl_xor_sync(0xFFFFFFFFu, acc, o);
+                        acc = (g.kind == MBC_AGG_COUNT || g.kind == MBC_AGG_SUM) ? acc + x
+                              : g.kind == MBC_AGG_MIN ? min(acc, x) : max(acc, x);
+                    }
+                    res = (unsigned long long)acc;
+                } else {
+                    double acc = g.kind == MBC_AGG_SUM ? 0.0 : g.kind == MBC_AGG_MIN ? (double)INFINITY : (double)-INFINITY;
+                    for (int i = lane; i < kScanThreads; i += 32) {
+                        double x = __longlong_as_double((long long)s_agg[a][i]);
+                        acc = g.kind == MBC_AGG_SUM ? acc + x : g.kind == MBC_AGG_MIN ? fmin(acc, x) : fmax(acc, x);
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        double x = __shfl_xor_sync(0xFFFFFFFFu, acc, o);
+                        acc = g.kind == MBC_AGG_SUM ? acc + x : g.kind == MBC_AGG_MIN ? fmin(acc, x) : fmax(acc, x);
+                    }
+                    res = (unsigned long long)__double_as_longlong(acc);
+                }
+                if (lane == 0) p.partials[(size_t)a * p.total_tiles + p.tile_base + tile] = res;
+            }
+        }
+        __syncthreads();
+
+        // ---- 5. ordered write of positions and projected values ------------------------------
+        if (mask) {
+            const long long base = s_tile_base + s_warp_base[warp];
+            long long slot[kUnits];
+#pragma unroll
+            for (int u = 0; u < kUnits; ++u) slot[u] = base + unit_off[u] + ((excl >> (8 * u)) & 0xFFu);
+
+            if (p.out_pos) {
+#pragma unroll
+                for (int u = 0; u < kUnits; ++u) {
+                    uint32_t nib = (mask >> (u * 4)) & 0xFu;
+                    long long s = slot[u];
+#pragma unroll
+                    for (int j = 0; j < kVec; ++j)
+                        if ((nib >> j) & 1u) p.out_pos[s++] = p.pos_base + thread_row0 + u * kUnitRows + j;
+                }
+            }
+            for (int c = 0; c < p.nproj; ++c) {                    // iterator/Projection.java:103-144
+                const DevProj& pr = p.proj[c];
+                if (pr.stride == 4) {
+                    const uint32_t* src = reinterpret_cast<const uint32_t*>(pr.src) + thread_row0;
+                    uint32_t* dst = reinterpret_cast<uint32_t*>(pr.dst);
+#pragma unroll
+                    for (int u = 0; u < kUnits; ++u) {
+                        uint32_t nib = (mask >> (u * 4)) & 0xFu;
+                        if (nib) {
+                            uint4 q = ldg128(src + u * kUnitRows);
+                            uint32_t v[4] = {q.x, q.y, q.z, q.w};
+                            long long s = slot[u];
+#pragma unroll
+                            for (int j = 0; j < kVec; ++j)
+                                if ((nib >> j) & 1u) dst[s++] = v[j];
+                        }
+                    }
+                } else if ((pr.stride & 15) == 0) {
+                    const int chunks = pr.stride >> 4;
+#pragma unroll
+                    for (int u = 0; u < kUnits; ++u) {
+                        uint32_t nib = (mask >> (u * 4)) & 0xFu;
+                        long long s = slot[u];
+#pragma unroll
+                        for (int j = 0; j < kVec; ++j) {
+                            if ((nib >> j) & 1u) {
+                                const uint4* src = reinterpret_cast<const uint4*>(
+                                    reinterpret_cast<const char*>(pr.src) + (thread_row0 + u * kUnitRows + j) * pr.stride);
+                                uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<char*>(pr.dst) + s * pr.stride);
+                                for (int k = 0; k < chunks; ++k) dst[k] = __ldg(src + k);
+                                ++s;
+                            }
+                        }
+                    }
+                } else {
+                    const int words = pr.stride >> 2;
+#pragma unroll
+                    for (int u = 0; u < kUnits; ++u) {
+                        uint32_t nib = (mask >> (u * 4)) & 0xFu;
+                        long long s = slot[u];
+#pragma unroll
+                        for (int j = 0; j < kVec; ++j) {
+                            if ((nib >> j) & 1u) {
+                                const uint32_t* src = reinterpret_cast<const uint32_t*>(
+                                    reinterpret_cast<const char*>(pr.src) + (thread_row0 + u * kUnitRows + j) * pr.stride);
+                                uint32_t* dst = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(pr.dst) + s * pr.stride);
+                                for (int k = 0; k < words; ++k) dst[k] = __ldg(src + k);
+                                ++s;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    }
+}
+
+// Reduce the per-tile partials of one aggregate in tile order (fixed tree => reproducible sums).
+struct AggList {
+    DevAgg g[kMaxAgg];
+};
+
+__global__ void __launch_bounds__(256) agg_finish_kernel(const unsigned long long* partials, int total_tiles,
+                                                         int ntiles, const __grid_constant__ AggList list,
+                                                         unsigned long long* out) {
+    const DevAgg g = list.g[blockIdx.x];
+    const unsigned long long* src = partials + (size_t)blockIdx.x * total_tiles;
+    __shared__ unsigned long long sh[256];
+    const bool additive = g.kind == MBC_AGG_COUNT || g.kind == MBC_AGG_SUM;
+    const bool integral = g.kind == MBC_AGG_COUNT || g.type == MBC_ATTR_INTEGER;
+    // each thread folds a contiguous slice, then a fixed-shape tree combines the 256 slices
+    int per = (ntiles + 255) / 256;
+    int lo = min(ntiles, (int)threadIdx.x * per), hi = min(ntiles, lo + per);
+    if (integral) {
+        long long acc = additive ? 0ll : g.kind == MBC_AGG_MIN ? (long long)INT32_MAX : (long long)INT32_MIN;
+        for (int i = lo; i < hi; ++i) {
+            long long x = (long long)src[i];
+            acc = additive ? acc + x : g.kind == MBC_AGG_MIN ? min(acc, x) : max(acc, x);
+        }
+        sh[threadIdx.x] = (unsigned long long)acc;
+    } else {
+        double acc = additive ? 0.0 : g.kind == MBC_AGG_MIN ? (double)INFINITY : (double)-INFINITY;
+        for (int i = lo; i < hi; ++i) {
+            double x = __longlong_as_double((long long)src[i]);
+            acc = additive ? acc + x : g.kind == MBC_AGG_MIN ? fmin(acc, x) : fmax(acc, x);
+        }
+        sh[threadIdx.x] = (unsigned long long)__double_as_longlong(acc);
+    }
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) {
+            if (integral) {
+                long long a = (long long)sh[threadIdx.x], b = (long long)sh[threadIdx.x + s];
+                sh[threadIdx.x] = (unsigned long long)(additive ? a + b : g.kind == MBC_AGG_MIN ? min(a, b) : max(a, b));
+            } else {
+                double a = __longlong_as_double((long long)sh[threadIdx.x]);
+                double b = __longlong_as_double((long long)sh[threadIdx.x + s]);
+                double r = additive ? a + b : g.kind == MBC_AGG_MIN ? fmin(a, b) : fmax(a, b);
+                sh[threadIdx.x] = (unsigned long long)__double_as_longlong(r);
+            }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[blockIdx.x] = sh[0];
+}
+
+// SoA projected columns -> reference Tuple bytes (heap/Tuple.java:369-440 header,
+// global/Convert.java:163-275 big-endian fields, strings as [len:2][bytes][zero pad]).
+struct TupleField {
+    const void* src;
+    int32_t type, width, stride, offset;
+};
+struct TupleParams {
+    int64_t count;
+    int32_t nfields, tuple_len, rows_per_cta, pad;
+    uint8_t* out;
+    TupleField f[kMaxProj];
+};
+
+__global__ void __launch_bounds__(128) tuple_encode_kernel(const __grid_constant__ TupleParams p) {
+    extern __shared__ uint8_t sm[];
+    const int64_t row0 = (int64_t)blockIdx.x * p.rows_per_cta;
+    const int nrows = (int)min((long long)p.rows_per_cta, (long long)(p.count - row0));
+    for (int r = threadIdx.x; r < nrows; r += blockDim.x) {
+        uint8_t* t = sm + (size_t)r * p.tuple_len;
+        const int64_t row = row0 + r;
+        
+        t[0] = (uint8_t)(p.nfields >> 8);
+        t[1] = (uint8_t)p.nfields;
+        for (int f = 0; f < p.nfields; ++f) {
+            int off = p.f[f].offset;
+            t[2 + 2 * f] = (uint8_t)(off >> 8);
+            t[3 + 2 * f] = (uint8_t)off;
+        }
+        t[2 + 2 * p.nfields] = (uint8_t)(p.tuple_len >> 8);
+        t[3 + 2 * p.nfields] = (uint8_t)p.tuple_len;
+        
+        for (int f = 0; f < p.nfields; ++f) {
+            const TupleField& fd = p.f[f];
+            uint8_t* d = t + fd.offset;
+            if (fd.type != MBC_ATTR_STRING) {
+                uint32_t v = reinterpret_cast<const uint32_t*>(fd.src)[row];
+                d[0] = (uint8_t)(v >> 24); d[1] = (uint8_t)(v >> 16); d[2] = (uint8_t)(v >> 8); d[3] = (uint8_t)v;
+            } else {
+                const uint8_t* s = reinterpret_cast<const uint8_t*>(fd.src) + row * fd.stride;
+                int len = 0;
+                for (int k = 0; k < fd.width; ++k) {
+                    uint8_t b = s[k];
+                    d[2 + k] = b;
+                    if (b != 0) len = k + 1;
+                }
+                d[0] = (uint8_t)(len >> 8);
+                d[1] = (uint8_t)len;
+            }
+        }
+    }
+    __syncthreads();
+    // contiguous, coalesced copy-out of the CTA's tuples
+    const size_t bytes = (size_t)nrows * p.tuple_len;
+    uint8_t* dst = p.out + (size_t)row0 * p.tuple_len;
+    if ((((size_t)row0 * p.tuple_len) & 3) == 0) {
+        const size_t words = bytes >> 2;
+        for (size_t i = threadIdx.x; i < words; i += blockDim.x)
+            reinterpret_cast<uint32_t*>(dst)[i] = reinterpret_cast<const uint32_t*>(sm)[i];
+        for (size_t i = (words << 2) + threadIdx.x; i < bytes; i += blockDim.x) dst[i] = sm[i];
+    } else {
+        for (size_t i = threadIdx.x; i < bytes; i += blockDim.x) dst[i] = sm[i];
+    }
+}
+}  // namespace mbc

@@ -1,0 +1,179 @@
+"""Pin the CPU oracle against the reference's own golden transcript.
+
+Every `index ... bitmap`, `indexes_query`, `bmj` and `nlj` command the reference's authors ran on
+minidata.txt is replayed through the oracle; counts, position sets, row order and printed values must
+match what the Java printed.  CPU only.
+"""
+import re
+
+import numpy as np
+import pytest
+
+
+def _fmt_rows(oracle, tuples, descs):
+    return [", ".join(str(v) for v in oracle.decode_tuple(bytes(t), descs)) for t in tuples]
+
+
+def test_record_count(golden, minidata, oracle):
+    names, descs, cols = minidata
+    assert names == ["A", "B", "C", "D"]
+    assert descs == [(0, 25), (0, 25), (1, 4), (1, 4)]
+    for e in golden:
+        if e["kind"] == "batchinsert" and "record_count" in e:
+            assert e["record_count"] == oracle.nrows_of(descs, cols) == 500          # G1
+
+
+def test_bitmap_index_byte_sizes(golden, minidata, oracle):
+    """G13/G14 (+ columns A, B): BitSet.toByteArray().length of every per-value bitmap."""
+    names, descs, cols = minidata
+    checked = 0
+    for e in golden:
+        if e["kind"] != "index" or not e.get("bitmap_bytes"):
+            continue
+        col = names.index(e["cmd"].split()[3])
+        index = oracle.bitmap_build(descs[col], cols[col])
+        sizes = {v: oracle.bitset_bytearray_len(w) for v, w in index.items()}
+        assert sorted(sizes.values()) == sorted(e["bitmap_bytes"]), e["cmd"]
+        if descs[col][0] == oracle.ATTR_INTEGER:
+            # HashMap<Integer,...> iterates small ints in ascending order: exact sequence
+            assert [sizes[v] for v in sorted(sizes)] == e["bitmap_bytes"], e["cmd"]
+        # every bit set exactly once across the values (each row has one value)
+        total = np.zeros(8, dtype=np.uint64)
+        for w in index.values():
+            assert not np.any(total & w)
+            total |= w
+        assert oracle.positions_from_bits(total).tolist() == list(range(500))
+        checked += 1
+    assert checked >= 8
+
+
+def _bitmap_positions(oracle, minidata, cnf_text, emulate=True):
+    names, descs, cols = minidata
+    conj = oracle.parse_cnf(cnf_text, names, descs)
+    indexes = {c: oracle.bitmap_build(descs[c], cols[c]) for c in range(4)}
+    bits = oracle.bitmap_cnf(indexes, names, conj, 500, emulate_duplicate_cache=emulate)
+    return oracle.positions_from_bits(bits, 500), conj
+
+
+def test_indexes_query(golden, minidata, oracle):
+    """G10-G12: CNF over index scans, rows in position order."""
+    names, descs, cols = minidata
+    n = 0
+    for e in golden:
+        if e["kind"] != "indexes_query" or e.get("failed"):
+            continue
+        m = re.match(r"indexes_query \S+ \S+ \[(.*?)\] (\S+) \d+", e["cmd"])
+        targets = [names.index(x) for x in m.group(1).split(",")]
+        pos, conj = _bitmap_positions(oracle, minidata, m.group(2))
+        assert len(pos) == e["count"], e["cmd"]
+        # the same answer through the row-at-a-time ColumnarFileScan restatement, projecting the targets
+        res = oracle.scan(descs, cols, oracle.cnf_to_terms(conj, descs), proj=targets)
+        assert res["positions"].tolist() == pos.tolist()
+        rows = _fmt_rows(oracle, res["tuples"], [descs[c] for c in targets])
+        assert rows == e["rows"], e["cmd"]
+        n += 1
+    assert n >= 5
+
+
+def _parse_join_cmd(cmd, kind):
+    parts = cmd.split()
+    if kind == "bmj":
+        _, _, outer, inner, ocnf, icnf, jcnf, targets = parts[:8]
+    else:
+        _, _, outer, inner, ocnf, icnf, jcnf, _, _, targets = parts[:10]
+    return outer, inner, ocnf, icnf, jcnf, targets[1:-1].split(",")
+
+
+def _run_join(oracle, minidata, cmd, kind):
+    names, descs, cols = minidata
+    outer, inner, ocnf, icnf, jcnf, targets = _parse_join_cmd(cmd, kind)
+    opos, _ = _bitmap_positions(oracle, minidata, ocnf)
+    ipos, _ = _bitmap_positions(oracle, minidata, icnf)
+    join_terms = []
+    for ci, conj in enumerate(jcnf.split("^")):
+        for dis in conj[1:-1].split("|"):
+            a, op, b = [x.strip() for x in dis[1:-1].split(",")]
+            join_terms.append(oracle.Term(oracle.OPS[op], ("col", names.index(a)), ("icol", names.index(b)), ci))
+    proj = []
+    for t in targets:
+        rel, col = t.split(".")
+        # BitMapQuery.createProjectionsAndTuples: anything not named after the outer file is inner
+        proj.append((1 if rel == outer else 2, names.index(col)))
+    res = oracle.bitmap_join(descs, cols, descs, cols, join_terms, proj,
+                             outer_sel=oracle.bits_from_positions(opos, 500),
+                             inner_sel=oracle.bits_from_positions(ipos, 500))
+    pdescs = [descs[c] for _, c in proj]
+    return opos, ipos, res, _fmt_rows(oracle, res["tuples"], pdescs)
+
+
+def test_bmj(golden, minidata, oracle):
+    """G2-G4, G6, G7, G9: side-filter bitsets, pair count, rows and their order."""
+    n = 0
+    seen = set()
+    for e in golden:
+        if e["kind"] != "bmj" or e.get("failed") or e["cmd"] in seen:
+            continue
+        seen.add(e["cmd"])
+        opos, ipos, res, rows = _run_join(oracle, minidata, e["cmd"], "bmj")
+        assert opos.tolist() == e["outer_bitset"], e["cmd"]
+        assert ipos.tolist() == e["inner_bitset"], e["cmd"]
+        assert res["count"] == e["count"], e["cmd"]
+        assert rows == e["rows"], e["cmd"]
+        # ordering contract: outer position ascending, then inner position ascending
+        pairs = list(zip(res["outer_positions"].tolist(), res["inner_positions"].tolist()))
+        assert pairs == sorted(pairs)
+        n += 1
+    assert n >= 8
+
+
+def test_nlj_counts_and_rows(golden, minidata, oracle):
+    """G5, G8: the nested-loop join runs (any access path) give the same pair multiset as the bitmap join."""
+    import hashlib
+    n = 0
+    seen = set()
+    for e in golden:
+        if e["kind"] != "nlj" or e.get("failed"):
+            continue
+        key = re.sub(r"(FILESCAN|COLUMNSCAN|BTREE|BITMAP) (FILESCAN|COLUMNSCAN|BTREE|BITMAP)", "X X", e["cmd"])
+        key = re.sub(r"\d+ \d+$", "", key)
+        if key in seen or "ff1." in e["cmd"]:
+            continue
+        seen.add(key)
+        _, _, res, rows = _run_join(oracle, minidata, e["cmd"], "nlj")
+        assert res["count"] == e["count"], e["cmd"]
+        if "rows" in e:
+            assert sorted(rows) == sorted(e["rows"]), e["cmd"]
+        else:
+            assert e["count"] == 2284 and len(rows) == 2284
+            # block nested loop emits the same pairs in another order: compare as a multiset through sorting
+            assert hashlib.sha256("\n".join(sorted(rows)).encode()).hexdigest() == e["rows_sorted_sha256"], e["cmd"]
+        n += 1
+    assert n >= 8
+
+
+def test_duplicate_constraint_cache_is_observable(minidata, oracle):
+    """ColumnarIndexScan caches the conjunct's accumulating BitSet for repeated terms (:147-172).
+    The oracle reproduces it; this documents when it changes the answer."""
+    q = "{(A,=,South_Dakota,BM)|(B,=,South_Dakota,BM)}^{(A,=,South_Dakota,BM)|(C,=,6,BM)}"
+    with_quirk, _ = _bitmap_positions(oracle, minidata, q, emulate=True)
+    plain, _ = _bitmap_positions(oracle, minidata, q, emulate=False)
+    names, descs, cols = minidata
+    A = oracle.unpack_strings(cols[0]); B = oracle.unpack_strings(cols[1]); Cc = cols[2]
+    expect_plain = [i for i in range(500) if (A[i] == "South_Dakota" or B[i] == "South_Dakota") and (A[i] == "South_Dakota" or Cc[i] == 6)]
+    expect_quirk = [i for i in range(500) if (A[i] == "South_Dakota" or B[i] == "South_Dakota")]
+    assert plain.tolist() == expect_plain
+    assert with_quirk.tolist() == expect_quirk
+    assert expect_plain != expect_quirk
+
+
+def test_stale_padding_mode_only_changes_padding(minidata, oracle):
+    """ColumnarFileScan reuses one Jtuple and Convert.setStrValue writes len+2 bytes, so padding bytes of
+    a string slot keep older values.  Field values are identical in both modes."""
+    names, descs, cols = minidata
+    terms = [oracle.Term(oracle.OP_GE, ("col", 2), ("int", 5), 0)]
+    canon = oracle.scan(descs, cols, terms, proj=[0, 1, 2, 3])
+    stale = oracle.scan(descs, cols, terms, proj=[0, 1, 2, 3], stale_padding=True)
+    assert canon["count"] == stale["count"] > 0
+    assert not np.array_equal(canon["tuples"], stale["tuples"])
+    for a, b in zip(canon["tuples"], stale["tuples"]):
+        assert oracle.decode_tuple(bytes(a), descs) == oracle.decode_tuple(bytes(b), descs)
