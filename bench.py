@@ -1,0 +1,376 @@
+#!/usr/bin/env python
+"""bench.py -- filtered-scan rows/s (BASELINE.json metric) on N B200s of one node.
+
+One "step" = one pass of the hot path over the resident table at each of the three selectivities
+BASELINE config C2 names: `{(I1,<,t1)}^{(R,<,t2)}` at joint selectivity 1 %, 10 % and 50 %, project
+[I1,I2,R,S], COUNT / SUM(I2) / SUM(R) / MIN(I1) / MAX(I1).  So a step scans 3 x rows-per-GPU rows on
+every rank.  N=1: the C2 table (100 M rows, 2.8 GB in HBM).  N>1: every rank holds its own 100 M-row
+position range of the same table (TID-range sharding, weak scaling), scans it with no data-path
+collective, then NCCL all-reduces the aggregates, all-gathers the counts and gathers the 1 % query's
+positions + projected values on rank 0.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--rows R] [--impl ours|reference]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+`--impl reference` times the reference's CPU algorithm (oracle/: the literal C++ restatement; the Java
+original cannot run here -- no JDK in the image) on the box's host cores on a bounded sample of the same
+workload.  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+SEED = 20260101
+SELECTIVITIES = (0.01, 0.10, 0.50)
+DESCS = [(1, 4), (1, 4), (2, 4), (0, 16)]                # I1 int, I2 int, R real, S char(16)
+AGGS = [(0, 0), (1, 1), (1, 2), (2, 0), (3, 0)]          # COUNT, SUM(I2), SUM(R), MIN(I1), MAX(I1)
+ROW_BYTES_IN = 28                                        # every referenced column read once
+ROW_BYTES_OUT = 36                                       # 8 B position + 28 B projected values
+
+
+def algorithmic_bytes(nrows: int, sel: float) -> float:
+    """N * (28 + 36 * s)."""
+    return nrows * (ROW_BYTES_IN + ROW_BYTES_OUT * sel)
+
+
+def c2_terms(term_cls, sel: float):
+    r = float(np.sqrt(sel))
+    t1 = int(np.ceil(r * (1 << 20)))
+    t2 = float(np.float32(r * 1000.0))
+    return [term_cls(1, ("col", 0), ("int", t1), 0), term_cls(1, ("col", 2), ("real", t2), 1)]    # op 1 = aopLT
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.rows.append([x.strip() for x in ln.split(",")])
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_reference_run(nrows_sample: int, nthreads: int, repeats: int = 1):
+    """Time the oracle (CPU restatement of TupleScan -> PredEval -> Projection) on a sample of the workload."""
+    from oracle import oracle as orc
+    orc.build()
+    cols = [orc.synth_int(SEED, 0, nrows_sample, 1 << 20), orc.synth_int(SEED, 1, nrows_sample, 1 << 20),
+            orc.synth_real(SEED, 2, nrows_sample), orc.synth_str(SEED, 3, nrows_sample, 16)]
+    times = []
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        for s in SELECTIVITIES:
+            orc.scan(DESCS, cols, c2_terms(orc.Term, s), proj=[0, 1, 2, 3], aggs=AGGS, nthreads=nthreads)
+        times.append(time.perf_counter() - t0)
+    return 3 * nrows_sample / min(times), times
+
+
+def run_reference(args, rank: int, world: int):
+    if rank != 0:
+        return
+    from oracle import oracle as orc
+    orc.build()
+    threads = orc.max_threads()
+    sample = args.cpu_rows
+    cols = [orc.synth_int(SEED, 0, sample, 1 << 20), orc.synth_int(SEED, 1, sample, 1 << 20),
+            orc.synth_real(SEED, 2, sample), orc.synth_str(SEED, 3, sample, 16)]
+
+    def step():
+        for s in SELECTIVITIES:
+            orc.scan(DESCS, cols, c2_terms(orc.Term, s), proj=[0, 1, 2, 3], aggs=AGGS, nthreads=threads)
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    value = 3 * sample * args.steps / dt
+    sample_desc = (f"{sample} rows of the C2 table per scan (3 scans/step), oracle/mbc_oracle.cpp orc_scan with "
+                   f"{threads} std::threads; the Java reference itself cannot run (no JDK in the image)")
+    print(json.dumps({
+        "impl": "reference", "metric": "filtered_scan_rows_per_s", "value": value, "unit": "rows/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32/float32/u8x16 compare, int64/float64 aggregate",
+        "data": "synthetic", "config": workload_config(args, sample),
+        "cpu_baseline": {"value": value, "unit": "rows/s", "cores": threads, "kind": "port", "sample": sample_desc},
+        "e2e": {"value": value, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def workload_config(args, rows_per_gpu):
+    return {"workload": "C2: synthetic 4-column table (I1,I2 int in [0,2^20); R real in [0,1000); S char(16)), "
+                        "{(I1,<,t1)}^{(R,<,t2)} at 1%/10%/50% selectivity, project [I1,I2,R,S], COUNT/SUM(I2)/SUM(R)/MIN(I1)/MAX(I1)",
+            "rows_per_gpu": rows_per_gpu, "scans_per_step": 3, "selectivities": list(SELECTIVITIES),
+            "sharding": "TID range per rank, no data-path collective; NCCL all-reduce of aggregates, all-gather of counts, "
+                        "gather of the 1% query's positions+values on rank 0" if args.gpus > 1 else "single GPU",
+            "l2": "inputs (2.8 GB per GPU) are larger than the 126 MB L2; no flush needed"}
+
+
+class _CudaArray:
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3}
+
+
+def run_ours(args, rank: int, local_rank: int, world: int):
+    import torch
+    import torch.distributed as dist
+    import mbcol
+    N = mbcol._native
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    ctx = mbcol.Context(local_rank)
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)
+
+    rows = args.rows
+    table = ctx.create_table(DESCS, rows, position_base=rank * rows)
+    table.generate(0, 0, SEED, 1 << 20)
+    table.generate(1, 0, SEED, 1 << 20)
+    table.generate(2, 1, SEED)
+    table.generate(3, 2, SEED)
+    terms = {s: c2_terms(mbcol.Term, s) for s in SELECTIVITIES}
+    want_dev = N.WANT_POSITIONS | N.WANT_COLUMNS | N.WANT_AGG
+    kernel_ms = {s: [] for s in SELECTIVITIES}
+    counts = {}
+
+    def gather_results(res, sel):
+        """NCCL: aggregates all-reduced, counts all-gathered, the 1% query's positions+values to rank 0."""
+        agg = torch.tensor([res.agg(0)[0], res.agg(1)[0], res.agg(3)[0], res.agg(4)[0]], dtype=torch.int64, device=dev)
+        fsum = torch.tensor([res.agg(2)[1]], dtype=torch.float64, device=dev)
+        sums = agg[:2].clone()
+        dist.all_reduce(sums)
+        dist.all_reduce(fsum)
+        mn, mx = agg[2:3].clone(), agg[3:4].clone()
+        dist.all_reduce(mn, op=dist.ReduceOp.MIN)
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        cnt = torch.tensor([res.count], dtype=torch.int64, device=dev)
+        all_cnt = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+        dist.all_gather(all_cnt, cnt)
+        if sel != SELECTIVITIES[0]:
+            return
+        all_cnt = [int(c.item()) for c in all_cnt]
+        ptrs = res.device_pointers()
+        bufs = [(ptrs["positions"], 8)] + [res.column_device(i) for i in range(4)]
+        ops, keep = [], []
+        for ptr, stride in bufs:
+            mine = torch.as_tensor(_CudaArray(ptr, max(res.count, 1) * stride), device=dev)[:res.count * stride]
+            if rank == 0:
+                total = torch.empty(sum(all_cnt) * stride, dtype=torch.uint8, device=dev)
+                total[:all_cnt[0] * stride].copy_(mine)
+                off = all_cnt[0] * stride
+                for r in range(1, world):
+                    ops.append(dist.P2POp(dist.irecv, total[off:off + all_cnt[r] * stride], r))
+                    off += all_cnt[r] * stride
+                keep.append(total)
+            else:
+                ops.append(dist.P2POp(dist.isend, mine, 0))
+                keep.append(mine)
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+
+    def step(record=False):
+        for s in SELECTIVITIES:
+            res = table.scan(terms[s], proj=[0, 1, 2, 3], want=want_dev, aggs=AGGS)
+            if record:
+                kernel_ms[s].append(ctx.last_kernel_ms)
+                counts[s] = res.count
+            if world > 1:
+                gather_results(res, s)
+            res.close()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = ctx.kernel_launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step(record=True)
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = ctx.kernel_launches - launches0
+    tmax = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms_total = float(tmax.item())
+    value = 3.0 * rows * world * args.steps / (ms_total * 1e-3)
+
+    # ---- end to end: host-resident columns -> mbc_scan_host -> host-resident results -------------------
+    host_cols = []
+    for c, (t, w) in enumerate(DESCS):
+        dt = np.int32 if t == 1 else np.float32 if t == 2 else np.uint8
+        shape = (rows,) if t != 0 else (rows, w)
+        pinned = torch.empty(int(np.prod(shape)) * np.dtype(dt).itemsize, dtype=torch.uint8, pin_memory=True).numpy()
+        arr = pinned.view(dt).reshape(shape)
+        arr[...] = table.read_column(c)
+        host_cols.append(arr)
+    want_host = N.WANT_POSITIONS | N.WANT_COLUMNS | N.WANT_AGG | N.WANT_HOST
+    h2d = 3 * rows * ROW_BYTES_IN
+    d2h = 0
+
+    def e2e_step(count_bytes=False):
+        nonlocal d2h
+        for s in SELECTIVITIES:
+            res = ctx.scan_host(DESCS, host_cols, terms[s], proj=[0, 1, 2, 3], want=want_host, aggs=AGGS,
+                                position_base=rank * rows)
+            if count_bytes:
+                d2h += res.count * ROW_BYTES_OUT + 8 * (len(AGGS) + 1)
+            res.close()
+
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    e0.record(stream)
+    for i in range(e2e_steps):
+        e2e_step(count_bytes=(i == 0))
+    e1.record(stream)
+    barrier()
+    e2e_wall_ms = 1e3 * (time.perf_counter() - t0)
+    e2e_ms = max(e0.elapsed_time(e1), 0.0)
+    e2e_t = torch.tensor([max(e2e_ms, e2e_wall_ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_value = 3.0 * rows * world * e2e_steps / (float(e2e_t.item()) * 1e-3)
+    clocks = sampler.stop() if rank == 0 else None
+
+    if rank == 0:
+        peak, peak_src = measured_peak_gbs()
+        per_sel = {}
+        tot_bytes = tot_ms = 0.0
+        for s in SELECTIVITIES:
+            m = statistics.mean(kernel_ms[s])
+            b = algorithmic_bytes(rows, s)
+            per_sel[str(s)] = {"kernel_ms": m, "rows_per_s": rows / (m * 1e-3), "achieved_gbs": b / (m * 1e-3) / 1e9,
+                               "frac_of_measured_peak": b / (m * 1e-3) / 1e9 / peak,
+                               "frac_of_8000": b / (m * 1e-3) / 1e9 / 8000.0, "count": counts[s]}
+            tot_bytes += b
+            tot_ms += m
+        achieved = tot_bytes / (tot_ms * 1e-3) / 1e9
+        cpu = None
+        if not args.no_cpu_baseline:
+            from oracle import oracle as orc
+            v1, _ = cpu_reference_run(args.cpu_rows // 4, 1)
+            vn, _ = cpu_reference_run(args.cpu_rows, orc.max_threads())
+            cpu = {"value": vn, "unit": "rows/s", "cores": orc.max_threads(), "kind": "port",
+                   "single_thread_rows_per_s": v1,
+                   "sample": f"{args.cpu_rows} rows of the C2 table per scan x 3 selectivities (all threads) and "
+                             f"{args.cpu_rows // 4} rows (1 thread); oracle/mbc_oracle.cpp orc_scan"}
+        out = {
+            "metric": "filtered_scan_rows_per_s", "value": value, "unit": "rows/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int32/float32/u8x16 compare, int64/float64 aggregate", "data": "synthetic",
+            "config": workload_config(args, rows),
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "rows/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": e2e_steps, "api": "mbc_scan_host (pinned host columns -> chunked H2D + fused scan -> D2H results)"},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": "mbc::scan_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "frac_of_nominal_8000": achieved / 8000.0, "peak_source": peak_src,
+                         "traffic": None, "algorithmic_bytes_per_launch": tot_bytes / 3,
+                         "per_selectivity": per_sel},
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(out))
+    table.close()
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--rows", type=int, default=100_000_000, help="rows per GPU")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-rows", type=int, default=8_000_000, help="rows of the CPU sample")
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world != args.gpus and world == 1 and args.gpus > 1:
+        # launched without torchrun: re-exec under it
+        os.execvp(sys.executable, [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
+                                   f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1", "--master-port", "29577",
+                                   os.path.abspath(__file__)] + sys.argv[1:])
+    run_ours(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

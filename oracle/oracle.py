@@ -710,16 +710,16 @@ def write_columnar_file(db: DBWriter, name: str, colnames, coldescs, columns, de
         if t == ATTR_STRING:
             arrs.append(np.asarray(col, dtype=np.uint8).reshape(nrows, w))
         elif t == ATTR_INTEGER:
-            arrs.append(np.asarray(col, dtype=np.int32).astype(">i4"))
+            arrs.append(np.asarray(col, dtype=np.int32).astype(">i4").tobytes())
         else:
-            arrs.append(np.asarray(col, dtype=np.float32).astype(">f4"))
+            arrs.append(np.asarray(col, dtype=np.float32).astype(">f4").tobytes())
     for r in range(nrows):
         for c, (t, w) in enumerate(coldescs):
             if t == ATTR_STRING:
                 raw = bytes(arrs[c][r]).rstrip(b"\0")
                 rec = (struct.pack(">H", len(raw)) + raw).ljust(w + 2, b"\0")
             else:
-                rec = arrs[c][r].tobytes()
+                rec = arrs[c][4 * r:4 * r + 4]
             heaps[c].insert(rec)
 
 
