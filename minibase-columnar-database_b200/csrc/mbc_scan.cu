@@ -13,6 +13,7 @@ static int32_t fill_operand(const mbc_table* t, const mbc_operand& o, int cmp_ty
                             int k) {
     memset(d, 0, sizeof(*d));
     d->col = -1;
+    d->staged = -1;
     if (o.kind == MBC_OPERAND_LITERAL) {
         d->kind = 0;
         if (cmp_type == MBC_ATTR_STRING) {
@@ -78,14 +79,44 @@ int32_t build_terms(const mbc_table* t, const mbc_term* terms, int32_t nterms, D
     return MBC_OK;
 }
 
-static int scan_grid(mbc_ctx* ctx, int ntiles) {
-    static int blocks_per_sm = 0;
-    if (blocks_per_sm == 0) {
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, scan_kernel, kScanThreads, 0) != cudaSuccess ||
-            blocks_per_sm < 1)
-            blocks_per_sm = 1;
+// Choose which 4-byte predicate columns are staged through the TMA ring, the ring depth, the dynamic
+// shared memory size and the persistent grid.
+static int32_t plan_staging(mbc_ctx* ctx, ScanParams* p, size_t* smem_bytes, int* grid) {
+    p->nstaged = 0;
+    auto stage_of = [&](int col) -> int {
+        for (int s = 0; s < p->nstaged; ++s) if (p->staged_cols[s] == col) return s;
+        if (p->nstaged == kMaxStaged) return -1;
+        p->staged_cols[p->nstaged] = col;
+        return p->nstaged++;
+    };
+    for (int k = 0; k < p->nterms; ++k) {
+        DevTerm& t = p->terms[k];
+        if (t.cmp_type == MBC_ATTR_STRING) continue;
+        if (t.lhs.kind == 1) t.lhs.staged = stage_of(t.lhs.col);
+        if (t.rhs.kind == 1) t.rhs.staged = stage_of(t.rhs.col);
     }
-    return std::max(1, std::min(ntiles, ctx->sm_count * blocks_per_sm));
+    for (int c = 0; c < p->nproj; ++c) {
+        p->proj[c].staged = -1;
+        if (p->proj[c].stride == 4)
+            for (int s = 0; s < p->nstaged; ++s) if (p->staged_cols[s] == p->proj[c].col) p->proj[c].staged = s;
+    }
+    for (int a = 0; a < p->nagg; ++a) {
+        p->aggs[a].staged = -1;
+        for (int s = 0; s < p->nstaged; ++s) if (p->aggs[a].col >= 0 && p->staged_cols[s] == p->aggs[a].col) p->aggs[a].staged = s;
+    }
+    p->nstages = p->nstaged <= 2 ? 3 : 2;
+    *smem_bytes = (size_t)p->nstages * p->nstaged * kStageColBytes;
+    static size_t configured = 0;
+    if (*smem_bytes > configured) {
+        MBC_CUDA(cudaFuncSetAttribute(scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kMaxStages * kMaxStaged * kStageColBytes > 200 * 1024 ? 200 * 1024 : kMaxStages * kMaxStaged * kStageColBytes)));
+        configured = 200 * 1024;
+    }
+    int blocks_per_sm = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, scan_kernel, kScanThreads, *smem_bytes) != cudaSuccess || blocks_per_sm < 1)
+        blocks_per_sm = 1;
+    blocks_per_sm = std::min(blocks_per_sm, 4);
+    *grid = std::max(1, std::min(p->ntiles, ctx->sm_count * blocks_per_sm));
+    return MBC_OK;
 }
 
 // tuple layout of a projected field list (iterator/TupleUtils.java:295-341 setup_op_tuple)
@@ -240,6 +271,9 @@ struct ScanJob {
     mbc_result* r = nullptr;
     Workspace w;
     int64_t total_tiles = 0;
+    size_t smem_bytes = 0;
+    int max_grid = 1;
+    int grid_per_tiles(int ntiles) const { return std::max(1, std::min(ntiles, max_grid)); }
 };
 
 static int32_t prepare_job(const mbc_table* schema, const ScanRequest& rq, int64_t capacity_rows, int64_t launch_tiles,
@@ -287,6 +321,8 @@ static int32_t prepare_job(const mbc_table* schema, const ScanRequest& rq, int64
     p.count = job->w.count;
     p.partials = job->w.partials;
     p.out_pos = r->d_pos;
+    p.ntiles = INT32_MAX;                         // the grid bound comes from the device; bind_table sets the real count
+    MBC_TRY(plan_staging(ctx, &p, &job->smem_bytes, &job->max_grid));
     return MBC_OK;
 }
 
@@ -297,6 +333,7 @@ static void bind_table(ScanJob* job, const mbc_table* t) {
         if (p.terms[k].rhs.kind == 1) p.terms[k].rhs.ptr = t->cols[p.terms[k].rhs.col].d;
     }
     for (int c = 0; c < p.nproj; ++c) p.proj[c].src = t->cols[p.proj[c].col].d;
+    for (int s = 0; s < p.nstaged; ++s) p.staged_src[s] = t->cols[p.staged_cols[s]].d;
     for (int a = 0; a < p.nagg; ++a)
         if (p.aggs[a].col >= 0) p.aggs[a].src = t->cols[p.aggs[a].col].d;
     p.deleted = t->has_deleted ? t->d_deleted : nullptr;
@@ -317,7 +354,7 @@ static int32_t launch_job(ScanJob* job, int tile_base, bool first) {
         MBC_CUDA(cudaMemsetAsync(p.ticket, 0, 4, ctx->stream));
         MBC_CUDA(cudaMemsetAsync(p.status, 0, (size_t)p.ntiles * 8, ctx->stream));
     }
-    scan_kernel<<<scan_grid(ctx, p.ntiles), kScanThreads, 0, ctx->stream>>>(p);
+    scan_kernel<<<job->grid_per_tiles(p.ntiles), kScanThreads, job->smem_bytes, ctx->stream>>>(p);
     ctx->launches++;
     MBC_CUDA(cudaGetLastError());
     return MBC_OK;

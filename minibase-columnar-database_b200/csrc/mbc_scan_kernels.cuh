@@ -7,8 +7,11 @@
 // iterator/Projection.java:103-144 (copy of the selected fields), for a whole table.
 //
 // Shape of the kernel (sm_100a; HBM-bound integer/byte work, no tensor cores):
+//   * persistent CTAs with a ring of tile slots: the 4-byte predicate columns of the next tiles are
+//     brought into shared memory by TMA bulk copies (cp.async.bulk + mbarrier complete_tx) while the
+//     current tile is evaluated, so HBM latency is covered by the ring depth, not by occupancy;
 //   * a warp owns 512 consecutive rows; in "unit" u lane l owns rows u*128+l*4+{0..3}, so every
-//     4-byte column is read with one coalesced 128-bit load per unit (512 B per warp instruction);
+//     4-byte column is read with one 128-bit access per unit (512 B per warp instruction);
 //     16-byte string rows are read lane-contiguously (row = k*32+lane, 512 B per instruction) and
 //     the result bits are transposed into the 4-rows-per-lane layout with warp ballots;
 //   * the CNF is a small term program in the kernel parameters; the operator/type switch runs once
@@ -17,8 +20,10 @@
 //     a CTA scan over 8 warp totals, and a decoupled look-back over per-tile status words, so the
 //     output is written in ascending position order in a single pass (the reference emits rows in
 //     position order; bit-exact position lists need order, not atomics);
-//   * projection columns that are not predicate columns are only touched for 4-row groups that
-//     have a survivor (late materialisation: at low selectivity most sectors are never read);
+//   * survivors are written with one lane per SURVIVOR (a per-warp rank->row list in shared memory):
+//     projection columns that are not predicate columns are only gathered for qualifying rows (late
+//     materialisation: at low selectivity most sectors are never read), stores are coalesced, and the
+//     cost of the output phase is proportional to the selectivity;
 //   * COUNT/SUM/MIN/MAX partials are produced per tile and reduced in tile order by a second
 //     tiny kernel, so real-valued sums are reproducible run to run.
 #pragma once
@@ -37,6 +42,8 @@ struct DevOperand {
     int32_t stride;      // device row stride of the column
     uint32_t bits;       // raw 32-bit literal (int or float bits)
     int32_t col;         // host bookkeeping: table column the pointer was taken from
+    int32_t staged;      // index of the TMA-staged copy of this column in the tile slot, or -1
+    int32_t pad;
 };
 
 struct DevTerm {
@@ -53,6 +60,8 @@ struct DevProj {
     void* dst;
     int32_t stride;      // 4, or the device string stride (multiple of 4)
     int32_t col;         // host bookkeeping
+    int32_t staged;      // staged predicate column to read the value from, or -1 (gather from HBM)
+    int32_t pad;
 };
 
 struct DevAgg {
@@ -60,8 +69,11 @@ struct DevAgg {
     int32_t kind;        // MBC_AGG_*
     int32_t type;        // MBC_ATTR_INTEGER / REAL
     int32_t col;         // host bookkeeping
-    int32_t pad;
+    int32_t staged;      // staged predicate column, or -1
 };
+
+constexpr int kMaxStaged = 4;                    // 4-byte predicate columns staged through shared memory
+constexpr int kStageColBytes = kTileRows * 4;    // one column of one tile: 16 KB
 
 struct ScanParams {
     int64_t nrows;
@@ -72,6 +84,10 @@ struct ScanParams {
     int32_t nagg;
     int32_t tile_base;            // index of this launch's first tile in the partials arrays
     int32_t total_tiles;          // stride of the partials arrays
+    int32_t nstaged;              // staged predicate columns (0..kMaxStaged)
+    int32_t nstages;              // depth of the tile ring (2..kMaxStages)
+    const void* staged_src[kMaxStaged];
+    int32_t staged_cols[kMaxStaged];   // host bookkeeping: table column of every staged slot
     const uint32_t* sel_bitmap;   // optional precomputed selection
     const uint32_t* deleted;      // optional markedDeleted bitmap
     int64_t* out_pos;
@@ -122,10 +138,23 @@ __device__ __forceinline__ uint32_t mask_op(int op, uint32_t lt, uint32_t eq) {
 }
 
 // load the 16 raw 32-bit values this thread owns (4 units x one 128-bit load), or broadcast a literal
-__device__ __forceinline__ void load_operand32(const DevOperand& o, int64_t thread_row0, uint32_t v[kRowsPerThread]) {
+__device__ __forceinline__ void load_operand32(const DevOperand& o, int64_t thread_row0, const uint32_t* stage, int tile_off,
+                                               uint32_t v[kRowsPerThread]) {
     if (o.kind == 0) {
 #pragma unroll
         for (int i = 0; i < kRowsPerThread; ++i) v[i] = o.bits;
+    } else if (o.staged >= 0) {
+        // the tile's slice of this column was brought into shared memory by the TMA engine; lanes read
+        // consecutive 16-byte chunks (conflict-free LDS.128)
+        const uint32_t* base = stage + o.staged * kTileRows + tile_off;
+#pragma unroll
+        for (int u = 0; u < kUnits; ++u) {
+            uint4 q = *reinterpret_cast<const uint4*>(base + u * kUnitRows);
+            v[u * 4 + 0] = q.x;
+            v[u * 4 + 1] = q.y;
+            v[u * 4 + 2] = q.z;
+            v[u * 4 + 3] = q.w;
+        }
     } else {
         const uint32_t* base = reinterpret_cast<const uint32_t*>(o.ptr) + thread_row0;
 #pragma unroll
@@ -140,10 +169,10 @@ __device__ __forceinline__ void load_operand32(const DevOperand& o, int64_t thre
 }
 
 // TupleUtils.java:48-57 (int) and :59-68 (float): 16 rows at once.  Bit u*4+j = row u*128+lane*4+j.
-__device__ __forceinline__ uint32_t eval_term32(const DevTerm& t, int64_t thread_row0) {
+__device__ __forceinline__ uint32_t eval_term32(const DevTerm& t, int64_t thread_row0, const uint32_t* stage, int tile_off) {
     uint32_t a[kRowsPerThread], b[kRowsPerThread];
-    load_operand32(t.lhs, thread_row0, a);
-    load_operand32(t.rhs, thread_row0, b);
+    load_operand32(t.lhs, thread_row0, stage, tile_off, a);
+    load_operand32(t.rhs, thread_row0, stage, tile_off, b);
     uint32_t lt = 0, eq = 0;
     if (t.cmp_type == MBC_ATTR_INTEGER) {
 #pragma unroll
@@ -268,252 +297,305 @@ __device__ __forceinline__ long long lookback(volatile unsigned long long* statu
     return prefix;
 }
 
-// ---- the kernel ------------------------------------------------------------------------------
+// ---- TMA bulk copy + mbarrier (sm_90+/sm_100a) -----------------------------------------------------
 
-__global__ void __launch_bounds__(kScanThreads, 4) scan_kernel(const __grid_constant__ ScanParams p) {
-    __shared__ int s_tile;
-    __shared__ uint32_t s_warp_tot[kWarpsPerCta];
-    __shared__ uint32_t s_warp_base[kWarpsPerCta];
-    __shared__ long long s_tile_base;
-    __shared__ unsigned long long s_agg[kMaxAgg][kScanThreads];
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// 1-D bulk copy global -> shared through the TMA engine; completion is signalled on `bar` (complete_tx)
+__device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// ---- the kernel ------------------------------------------------------------------------------
+//
+// Persistent CTAs; each keeps a ring of kStages tile slots.  For every claimed tile the producer thread
+// issues one TMA bulk copy per staged predicate column (16 KB each) into the slot; the copies of the next
+// tiles are in flight while the current tile is evaluated, so HBM latency is hidden by the ring, not by
+// occupancy.  Every loop iteration runs phase A of the newest tile (mask, ranks, survivor list, publish the
+// tile aggregate for the look-back) and phase B of the previous tile (resolve its prefix, then write
+// positions / projected values / aggregate partials with one lane per SURVIVOR, so the cost of phase B is
+// proportional to the selectivity and the stores are coalesced).  Publishing a tile one iteration before
+// its own prefix is needed keeps the look-back chain off the critical path.
+
+constexpr int kMaxStages = 4;
+
+__global__ void __launch_bounds__(kScanThreads, 2) scan_kernel(const __grid_constant__ ScanParams p) {
+    extern __shared__ __align__(128) uint8_t stage_mem[];          // [nstages][nstaged][kTileRows] uint32
+    __shared__ __align__(8) uint64_t s_full[kMaxStages];
+    __shared__ int s_tileq[kMaxStages];
+    __shared__ uint16_t s_list[2][kWarpsPerCta][kWarpRows];        // survivor rows (within the warp's 512), by rank
+    __shared__ uint32_t s_wtot[2][kWarpsPerCta];
+    __shared__ uint32_t s_wbase[2][kWarpsPerCta];
+    __shared__ long long s_ttotal[2];
+    __shared__ long long s_tbase;
+    __shared__ unsigned long long s_aggw[kMaxAgg][kWarpsPerCta];
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
+    const int S = p.nstages;
+    const uint32_t stage_bytes = (uint32_t)p.nstaged * kStageColBytes;
+    constexpr int kProducer = 32;                                  // first lane of warp 1 (warp 0 runs the look-back)
 
-    while (true) {
-        if (tid == 0) s_tile = (int)atomicAdd(p.ticket, 1u);
-        __syncthreads();
-        const int tile = s_tile;
-        if (tile >= p.ntiles) break;
+    auto issue_tile = [&](int slot, int tile) {                    // producer thread only
+        if (p.nstaged == 0) return;
+        mbar_arrive_expect_tx(&s_full[slot], stage_bytes);
+        for (int c = 0; c < p.nstaged; ++c)
+            tma_bulk_g2s(stage_mem + (size_t)slot * stage_bytes + (size_t)c * kStageColBytes,
+                         reinterpret_cast<const uint8_t*>(p.staged_src[c]) + (size_t)tile * kStageColBytes, kStageColBytes,
+                         &s_full[slot]);
+    };
 
-        const int64_t warp_row0 = (int64_t)tile * kTileRows + warp * kWarpRows;
-        const int64_t thread_row0 = warp_row0 + lane * kVec;
-
-        // ---- 1. qualifying mask of the 16 rows this thread owns ----------------------------
-        uint32_t mask = 0xFFFFu;
-        if (p.sel_bitmap) mask &= load_bits(p.sel_bitmap, warp_row0, lane);
-        if (p.nterms > 0) {
-            uint32_t acc = 0;
-            for (int k = 0; k < p.nterms; ++k) {                  // warp-uniform term program
-                const DevTerm& t = p.terms[k];
-                acc |= (t.cmp_type == MBC_ATTR_STRING) ? eval_term_str(t, warp_row0, lane)
-                                                       : eval_term32(t, thread_row0);
-                if (t.end_conj) { mask &= acc; acc = 0; }          // OR inside, AND across (PredEval.java:164-176)
-            }
+    if (tid == kProducer) {
+        for (int s = 0; s < S; ++s) mbar_init(&s_full[s], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (tid == kProducer) {
+        for (int s = 0; s < S; ++s) {
+            int t = (int)atomicAdd(p.ticket, 1u);
+            s_tileq[s] = t;
+            if (t < p.ntiles) issue_tile(s, t);
         }
-        if (p.deleted) mask &= ~load_bits(p.deleted, warp_row0, lane);   // TupleScan.java:85
-        if (warp_row0 + kWarpRows > p.nrows) {                     // rows past the end of the table
-#pragma unroll
-            for (int u = 0; u < kUnits; ++u)
-#pragma unroll
-                for (int j = 0; j < kVec; ++j)
-                    if (thread_row0 + u * kUnitRows + j >= p.nrows) mask &= ~(1u << (u * 4 + j));
-        }
+    }
+    __syncthreads();
 
-        // ---- 2. ranks: packed warp scan of the four unit counters --------------------------
-        uint32_t packed = __popc(mask & 0xFu) | (__popc(mask & 0xF0u) << 8) | (__popc(mask & 0xF00u) << 16) |
-                          (__popc(mask & 0xF000u) << 24);
-        uint32_t incl = packed;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            uint32_t n = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-            if (lane >= o) incl += n;
-        }
-        const uint32_t tot = __shfl_sync(0xFFFFFFFFu, incl, 31);   // per-unit totals, each <= 128
-        const uint32_t excl = incl - packed;
-        uint32_t unit_off[kUnits];
-        unit_off[0] = 0;
-        unit_off[1] = tot & 0xFFu;
-        unit_off[2] = unit_off[1] + ((tot >> 8) & 0xFFu);
-        unit_off[3] = unit_off[2] + ((tot >> 16) & 0xFFu);
-        const uint32_t warp_total = unit_off[3] + (tot >> 24);
-        if (lane == 0) s_warp_tot[warp] = warp_total;
+    int tileB = INT32_MAX, slotB = 0, bufB = 0, newtile = INT32_MAX;
+    for (int it = 0;; ++it) {
+        const int slotA = it % S, bufA = it & 1;
+        const int tileA = s_tileq[slotA];
+        const bool validA = tileA < p.ntiles, validB = tileB < p.ntiles;
+        if (!validA && !validB) break;
 
-        // ---- 3. per-thread aggregate partials over the survivors ----------------------------
-        for (int a = 0; a < p.nagg; ++a) {
-            const DevAgg& g = p.aggs[a];
-            unsigned long long out;
-            if (g.kind == MBC_AGG_COUNT) {
-                out = (unsigned long long)__popc(mask);
-            } else {
-                uint32_t v[kRowsPerThread];
-                if (mask) {
-                    const uint32_t* base = reinterpret_cast<const uint32_t*>(g.src) + thread_row0;
-#pragma unroll
-                    for (int u = 0; u < kUnits; ++u) {
-                        if ((mask >> (u * 4)) & 0xFu) {
-                            uint4 q = ldg128(base + u * kUnitRows);
-                            v[u * 4 + 0] = q.x; v[u * 4 + 1] = q.y; v[u * 4 + 2] = q.z; v[u * 4 + 3] = q.w;
-                        }
-                    }
-                }
-                if (g.type == MBC_ATTR_INTEGER) {
-                    long long acc = g.kind == MBC_AGG_SUM ? 0ll : g.kind == MBC_AGG_MIN ? (long long)INT32_MAX
-                                                                                        : (long long)INT32_MIN;
-#pragma unroll
-                    for (int i = 0; i < kRowsPerThread; ++i) {
-                        if ((mask >> i) & 1u) {
-                            long long x = (long long)(int32_t)v[i];
-                            acc = g.kind == MBC_AGG_SUM ? acc + x : g.kind == MBC_AGG_MIN ? min(acc, x) : max(acc, x);
-                        }
-                    }
-                    out = (unsigned long long)acc;
-                } else {
-                    double acc = g.kind == MBC_AGG_SUM ? 0.0 : g.kind == MBC_AGG_MIN ? (double)INFINITY
-                                                                                      : (double)-INFINITY;
-#pragma unroll
-                    for (int i = 0; i < kRowsPerThread; ++i) {
-                        if ((mask >> i) & 1u) {
-                            double x = (double)__uint_as_float(v[i]);
-                            acc = g.kind == MBC_AGG_SUM ? acc + x : g.kind == MBC_AGG_MIN ? fmin(acc, x) : fmax(acc, x);
-                        }
-                    }
-                    out = (unsigned long long)__double_as_longlong(acc);
+        // =========================== phase A: newest tile ===========================
+        if (validA) {
+            if (p.nstaged) mbar_wait(&s_full[slotA], (uint32_t)((it / S) & 1));
+            const uint32_t* stage = reinterpret_cast<const uint32_t*>(stage_mem + (size_t)slotA * stage_bytes);
+            const int64_t warp_row0 = (int64_t)tileA * kTileRows + warp * kWarpRows;
+            const int64_t thread_row0 = warp_row0 + lane * kVec;
+            const int tile_off = warp * kWarpRows + lane * kVec;   // this thread's first row within the tile
+
+            uint32_t mask = 0xFFFFu;
+            if (p.sel_bitmap) mask &= load_bits(p.sel_bitmap, warp_row0, lane);
+            if (p.nterms > 0) {
+                uint32_t acc = 0;
+                for (int k = 0; k < p.nterms; ++k) {               // warp-uniform term program
+                    const DevTerm& t = p.terms[k];
+                    acc |= (t.cmp_type == MBC_ATTR_STRING) ? eval_term_str(t, warp_row0, lane)
+                                                           : eval_term32(t, thread_row0, stage, tile_off);
+                    if (t.end_conj) { mask &= acc; acc = 0; }      // OR inside, AND across (PredEval.java:164-176)
                 }
             }
-            s_agg[a][tid] = out;
-        }
-
-        // ---- optional selection bitmap (BitSet-compatible, bit p = word p/32 bit p%32) ------
-        if (p.out_bitmap) {
+            if (p.deleted) mask &= ~load_bits(p.deleted, warp_row0, lane);   // TupleScan.java:85
+            if (warp_row0 + kWarpRows > p.nrows) {                 // rows past the end of the table
 #pragma unroll
-            for (int u = 0; u < kUnits; ++u) {
-                uint32_t w = ((mask >> (u * 4)) & 0xFu) << ((lane & 7) * 4);
-                w |= __shfl_xor_sync(0xFFFFFFFFu, w, 1);
-                w |= __shfl_xor_sync(0xFFFFFFFFu, w, 2);
-                w |= __shfl_xor_sync(0xFFFFFFFFu, w, 4);
-                if ((lane & 7) == 0) p.out_bitmap[(warp_row0 >> 5) + u * (kUnitRows / 32) + (lane >> 3)] = w;
+                for (int u = 0; u < kUnits; ++u)
+#pragma unroll
+                    for (int j = 0; j < kVec; ++j)
+                        if (thread_row0 + u * kUnitRows + j >= p.nrows) mask &= ~(1u << (u * 4 + j));
             }
-        }
-        __syncthreads();
-
-        // ---- 4. CTA scan of the warp totals + look-back (warp 0); tile partials (other warps) ----
-        if (warp == 0) {
-            uint32_t v = lane < kWarpsPerCta ? s_warp_tot[lane] : 0u;
-            uint32_t inc = v;
+            // ranks: one packed warp scan of the four unit counters (each total <= 128 fits 8 bits)
+            const uint32_t packed = __popc(mask & 0xFu) | (__popc(mask & 0xF0u) << 8) | (__popc(mask & 0xF00u) << 16) |
+                                    (__popc(mask & 0xF000u) << 24);
+            uint32_t incl = packed;
 #pragma unroll
-            for (int o = 1; o < kWarpsPerCta; o <<= 1) {
-                uint32_t n = __shfl_up_sync(0xFFFFFFFFu, inc, o);
-                if (lane >= o) inc += n;
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t n = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+                if (lane >= o) incl += n;
             }
-            if (lane < kWarpsPerCta) s_warp_base[lane] = inc - v;
-            const long long tile_total = (long long)__shfl_sync(0xFFFFFFFFu, inc, kWarpsPerCta - 1);
-            long long init = 0;
-            if (tile == 0) init = *p.count;
-            const long long prefix = lookback(p.status, tile, tile_total, init, lane);
-            if (lane == 0) {
-                s_tile_base = prefix;
-                if (tile == p.ntiles - 1) *p.count = prefix + tile_total;
-            }
-        } else {
-            for (int a = warp - 1; a < p.nagg; a += kWarpsPerCta - 1) {
-                const DevAgg& g = p.aggs[a];
-                unsigned long long res;
-                if (g.kind == MBC_AGG_COUNT || (g.type == MBC_ATTR_INTEGER)) {
-                    long long acc = (g.kind == MBC_AGG_COUNT || g.kind == MBC_AGG_SUM) ? 0ll
-                                    : g.kind == MBC_AGG_MIN ? (long long)INT32_MAX : (long long)INT32_MIN;
-                    for (int i = lane; i < kScanThreads; i += 32) {
-                        long long x = (long long)s_agg[a][i];
-                        acc = (g.kind == MBC_AGG_COUNT || g.kind == MBC_AGG_SUM) ? acc + x
-                              : g.kind == MBC_AGG_MIN ? min(acc, x) : max(acc, x);
-                    }
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) {
-                        long long x = __shfl_xor_sync(0xFFFFFFFFu, acc, o);
-                        acc = (g.kind == MBC_AGG_COUNT || g.kind == MBC_AGG_SUM) ? acc + x
-                              : g.kind == MBC_AGG_MIN ? min(acc, x) : max(acc, x);
-                    }
-                    res = (unsigned long long)acc;
-                } else {
-                    double acc = g.kind == MBC_AGG_SUM ? 0.0 : g.kind == MBC_AGG_MIN ? (double)INFINITY : (double)-INFINITY;
-                    for (int i = lane; i < kScanThreads; i += 32) {
-                        double x = __longlong_as_double((long long)s_agg[a][i]);
-                        acc = g.kind == MBC_AGG_SUM ? acc + x : g.kind == MBC_AGG_MIN ? fmin(acc, x) : fmax(acc, x);
-                    }
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) {
-                        double x = __shfl_xor_sync(0xFFFFFFFFu, acc, o);
-                        acc = g.kind == MBC_AGG_SUM ? acc + x : g.kind == MBC_AGG_MIN ? fmin(acc, x) : fmax(acc, x);
-                    }
-                    res = (unsigned long long)__double_as_longlong(acc);
-                }
-                if (lane == 0) p.partials[(size_t)a * p.total_tiles + p.tile_base + tile] = res;
-            }
-        }
-        __syncthreads();
-
-        // ---- 5. ordered write of positions and projected values ------------------------------
-        if (mask) {
-            const long long base = s_tile_base + s_warp_base[warp];
-            long long slot[kUnits];
-#pragma unroll
-            for (int u = 0; u < kUnits; ++u) slot[u] = base + unit_off[u] + ((excl >> (8 * u)) & 0xFFu);
-
-            if (p.out_pos) {
+            const uint32_t tot = __shfl_sync(0xFFFFFFFFu, incl, 31);
+            const uint32_t excl = incl - packed;
+            uint32_t unit_off[kUnits];
+            unit_off[0] = 0;
+            unit_off[1] = tot & 0xFFu;
+            unit_off[2] = unit_off[1] + ((tot >> 8) & 0xFFu);
+            unit_off[3] = unit_off[2] + ((tot >> 16) & 0xFFu);
+            if (lane == 0) s_wtot[bufA][warp] = unit_off[3] + (tot >> 24);
+            if (mask) {
+                uint16_t* list = s_list[bufA][warp];
 #pragma unroll
                 for (int u = 0; u < kUnits; ++u) {
                     uint32_t nib = (mask >> (u * 4)) & 0xFu;
-                    long long s = slot[u];
+                    uint32_t r = unit_off[u] + ((excl >> (8 * u)) & 0xFFu);
 #pragma unroll
                     for (int j = 0; j < kVec; ++j)
-                        if ((nib >> j) & 1u) p.out_pos[s++] = p.pos_base + thread_row0 + u * kUnitRows + j;
+                        if ((nib >> j) & 1u) list[r++] = (uint16_t)(u * kUnitRows + lane * kVec + j);
                 }
             }
-            for (int c = 0; c < p.nproj; ++c) {                    // iterator/Projection.java:103-144
-                const DevProj& pr = p.proj[c];
-                if (pr.stride == 4) {
-                    const uint32_t* src = reinterpret_cast<const uint32_t*>(pr.src) + thread_row0;
-                    uint32_t* dst = reinterpret_cast<uint32_t*>(pr.dst);
+            if (p.out_bitmap) {                                    // BitSet-compatible: bit p = word p/32, bit p%32
 #pragma unroll
-                    for (int u = 0; u < kUnits; ++u) {
-                        uint32_t nib = (mask >> (u * 4)) & 0xFu;
-                        if (nib) {
-                            uint4 q = ldg128(src + u * kUnitRows);
-                            uint32_t v[4] = {q.x, q.y, q.z, q.w};
-                            long long s = slot[u];
-#pragma unroll
-                            for (int j = 0; j < kVec; ++j)
-                                if ((nib >> j) & 1u) dst[s++] = v[j];
-                        }
-                    }
-                } else if ((pr.stride & 15) == 0) {
-                    const int chunks = pr.stride >> 4;
-#pragma unroll
-                    for (int u = 0; u < kUnits; ++u) {
-                        uint32_t nib = (mask >> (u * 4)) & 0xFu;
-                        long long s = slot[u];
-#pragma unroll
-                        for (int j = 0; j < kVec; ++j) {
-                            if ((nib >> j) & 1u) {
-                                const uint4* src = reinterpret_cast<const uint4*>(
-                                    reinterpret_cast<const char*>(pr.src) + (thread_row0 + u * kUnitRows + j) * pr.stride);
-                                uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<char*>(pr.dst) + s * pr.stride);
-                                for (int k = 0; k < chunks; ++k) dst[k] = __ldg(src + k);
-                                ++s;
-                            }
-                        }
-                    }
-                } else {
-                    const int words = pr.stride >> 2;
-#pragma unroll
-                    for (int u = 0; u < kUnits; ++u) {
-                        uint32_t nib = (mask >> (u * 4)) & 0xFu;
-                        long long s = slot[u];
-#pragma unroll
-                        for (int j = 0; j < kVec; ++j) {
-                            if ((nib >> j) & 1u) {
-                                const uint32_t* src = reinterpret_cast<const uint32_t*>(
-                                    reinterpret_cast<const char*>(pr.src) + (thread_row0 + u * kUnitRows + j) * pr.stride);
-                                uint32_t* dst = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(pr.dst) + s * pr.stride);
-                                for (int k = 0; k < words; ++k) dst[k] = __ldg(src + k);
-                                ++s;
-                            }
-                        }
-                    }
+                for (int u = 0; u < kUnits; ++u) {
+                    uint32_t w = ((mask >> (u * 4)) & 0xFu) << ((lane & 7) * 4);
+                    w |= __shfl_xor_sync(0xFFFFFFFFu, w, 1);
+                    w |= __shfl_xor_sync(0xFFFFFFFFu, w, 2);
+                    w |= __shfl_xor_sync(0xFFFFFFFFu, w, 4);
+                    if ((lane & 7) == 0) p.out_bitmap[(warp_row0 >> 5) + u * (kUnitRows / 32) + (lane >> 3)] = w;
                 }
             }
         }
+        __syncthreads();                                           // S1
+
+        // ============ warp 0: publish tile A's aggregate, then resolve tile B's prefix ============
+        if (warp == 0) {
+            if (validA) {
+                uint32_t v = lane < kWarpsPerCta ? s_wtot[bufA][lane] : 0u;
+                uint32_t inc = v;
+#pragma unroll
+                for (int o = 1; o < kWarpsPerCta; o <<= 1) {
+                    uint32_t n = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+                    if (lane >= o) inc += n;
+                }
+                if (lane < kWarpsPerCta) s_wbase[bufA][lane] = inc - v;
+                const long long tile_total = (long long)__shfl_sync(0xFFFFFFFFu, inc, kWarpsPerCta - 1);
+                if (lane == 0) {
+                    s_ttotal[bufA] = tile_total;
+                    if (tileA > 0) p.status[tileA] = kFlagAgg | (unsigned long long)tile_total;
+                }
+            }
+            if (validB) {
+                const long long total = s_ttotal[bufB];
+                long long init = 0;
+                if (tileB == 0) init = *p.count;
+                const long long prefix = lookback(p.status, tileB, total, init, lane);
+                if (lane == 0) {
+                    s_tbase = prefix;
+                    if (tileB == p.ntiles - 1) *p.count = prefix + total;
+                }
+            }
+        } else if (tid == kProducer && validB) {
+            newtile = (int)atomicAdd(p.ticket, 1u);                // next tile for the slot tile B is about to free
+            s_tileq[slotB] = newtile;
+        }
+        __syncthreads();                                           // S2
+
+        // =========================== phase B: previous tile, one lane per survivor ===========================
+        if (validB) {
+            const uint32_t* stage = reinterpret_cast<const uint32_t*>(stage_mem + (size_t)slotB * stage_bytes);
+            const int n = (int)s_wtot[bufB][warp];
+            const long long base = s_tbase + s_wbase[bufB][warp];
+            const int64_t warp_row0 = (int64_t)tileB * kTileRows + warp * kWarpRows;
+            const uint16_t* list = s_list[bufB][warp];
+            unsigned long long acc[kMaxAgg];
+#pragma unroll
+            for (int a = 0; a < kMaxAgg; ++a) {
+                if (a < p.nagg) {
+                    const DevAgg& g = p.aggs[a];
+                    const bool integral = g.kind == MBC_AGG_COUNT || g.type == MBC_ATTR_INTEGER;
+                    if (g.kind == MBC_AGG_MIN) acc[a] = integral ? (unsigned long long)(long long)INT32_MAX : (unsigned long long)__double_as_longlong((double)INFINITY);
+                    else if (g.kind == MBC_AGG_MAX) acc[a] = integral ? (unsigned long long)(long long)INT32_MIN : (unsigned long long)__double_as_longlong((double)-INFINITY);
+                    else acc[a] = integral ? 0ull : (unsigned long long)__double_as_longlong(0.0);
+                }
+            }
+            for (int k = lane; k < n; k += 32) {
+                const int r = list[k];
+                const int64_t row = warp_row0 + r;
+                const long long slot = base + k;
+                if (p.out_pos) p.out_pos[slot] = p.pos_base + row;
+                for (int c = 0; c < p.nproj; ++c) {                // iterator/Projection.java:103-144
+                    const DevProj& pr = p.proj[c];
+                    if (pr.stride == 4) {
+                        uint32_t v = pr.staged >= 0 ? stage[pr.staged * kTileRows + warp * kWarpRows + r]
+                                                    : __ldg(reinterpret_cast<const uint32_t*>(pr.src) + row);
+                        reinterpret_cast<uint32_t*>(pr.dst)[slot] = v;
+                    } else if ((pr.stride & 15) == 0) {
+                        const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(pr.src) + row * pr.stride);
+                        uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<char*>(pr.dst) + slot * pr.stride);
+                        for (int q = 0; q < (pr.stride >> 4); ++q) dst[q] = __ldg(src + q);
+                    } else {
+                        const uint32_t* src = reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(pr.src) + row * pr.stride);
+                        uint32_t* dst = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(pr.dst) + slot * pr.stride);
+                        for (int q = 0; q < (pr.stride >> 2); ++q) dst[q] = __ldg(src + q);
+                    }
+                }
+#pragma unroll
+                for (int a = 0; a < kMaxAgg; ++a) {
+                    if (a < p.nagg) {
+                        const DevAgg& g = p.aggs[a];
+                        if (g.kind == MBC_AGG_COUNT) { acc[a] += 1ull; continue; }
+                        const uint32_t bits = g.staged >= 0 ? stage[g.staged * kTileRows + warp * kWarpRows + r]
+                                                            : __ldg(reinterpret_cast<const uint32_t*>(g.src) + row);
+                        if (g.type == MBC_ATTR_INTEGER) {
+                            const long long x = (long long)(int32_t)bits, cur = (long long)acc[a];
+                            acc[a] = (unsigned long long)(g.kind == MBC_AGG_SUM ? cur + x : g.kind == MBC_AGG_MIN ? min(cur, x) : max(cur, x));
+                        } else {
+                            const double x = (double)__uint_as_float(bits), cur = __longlong_as_double((long long)acc[a]);
+                            const double nv = g.kind == MBC_AGG_SUM ? cur + x : g.kind == MBC_AGG_MIN ? fmin(cur, x) : fmax(cur, x);
+                            acc[a] = (unsigned long long)__double_as_longlong(nv);
+                        }
+                    }
+                }
+            }
+            // per-warp partial of every aggregate (fixed lane order -> reproducible)
+#pragma unroll
+            for (int a = 0; a < kMaxAgg; ++a) {
+                if (a < p.nagg) {
+                    const DevAgg& g = p.aggs[a];
+                    const bool integral = g.kind == MBC_AGG_COUNT || g.type == MBC_ATTR_INTEGER;
+                    const bool additive = g.kind == MBC_AGG_COUNT || g.kind == MBC_AGG_SUM;
+                    unsigned long long v = acc[a];
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        unsigned long long y = __shfl_xor_sync(0xFFFFFFFFu, v, o);
+                        if (integral) {
+                            long long x1 = (long long)v, x2 = (long long)y;
+                            v = (unsigned long long)(additive ? x1 + x2 : g.kind == MBC_AGG_MIN ? min(x1, x2) : max(x1, x2));
+                        } else {
+                            double x1 = __longlong_as_double((long long)v), x2 = __longlong_as_double((long long)y);
+                            v = (unsigned long long)__double_as_longlong(additive ? x1 + x2 : g.kind == MBC_AGG_MIN ? fmin(x1, x2) : fmax(x1, x2));
+                        }
+                    }
+                    if (lane == 0) s_aggw[a][warp] = v;
+                }
+            }
+        }
+        __syncthreads();                                           // S3: tile B's slot and lists are free
+
+        if (validB) {
+            if (tid < p.nagg) {                                    // tile partial = warps in order
+                const DevAgg& g = p.aggs[tid];
+                const bool integral = g.kind == MBC_AGG_COUNT || g.type == MBC_ATTR_INTEGER;
+                const bool additive = g.kind == MBC_AGG_COUNT || g.kind == MBC_AGG_SUM;
+                unsigned long long v = s_aggw[tid][0];
+                for (int w = 1; w < kWarpsPerCta; ++w) {
+                    unsigned long long y = s_aggw[tid][w];
+                    if (integral) {
+                        long long x1 = (long long)v, x2 = (long long)y;
+                        v = (unsigned long long)(additive ? x1 + x2 : g.kind == MBC_AGG_MIN ? min(x1, x2) : max(x1, x2));
+                    } else {
+                        double x1 = __longlong_as_double((long long)v), x2 = __longlong_as_double((long long)y);
+                        v = (unsigned long long)__double_as_longlong(additive ? x1 + x2 : g.kind == MBC_AGG_MIN ? fmin(x1, x2) : fmax(x1, x2));
+                    }
+                }
+                p.partials[(size_t)tid * p.total_tiles + p.tile_base + tileB] = v;
+            }
+            if (tid == kProducer && newtile < p.ntiles) issue_tile(slotB, newtile);
+        }
+        tileB = tileA;
+        slotB = slotA;
+        bufB = bufA;
     }
 }
 

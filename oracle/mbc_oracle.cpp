@@ -434,6 +434,23 @@ int64_t orc_bitmap_join(int32_t n_ocols, const OCol* ocols, int64_t n_outer, con
                 // the reference stores `innerCol op' outerValue` with op' = getOppositeOperator(op) (:453);
                 // ColumnIndexScan.getBitSet then ORs the bitmaps of the indexed values v with v op' literal,
                 // i.e. exactly the inner values with  outerValue op v.
+                if (t.op == OP_EQ) {
+                    // EQ selects exactly the literal's own bitmap (ColumnIndexScan.java:660-667): look it up
+                    std::string key;
+                    if (ix.type == ATTR_STRING) {
+                        int len = ((otup[od.off[t.lhs.col]] << 8) | otup[od.off[t.lhs.col] + 1]) & 0xFFFF;
+                        key.assign((const char*)otup.data() + od.off[t.lhs.col] + 2, len);
+                    } else {
+                        uint8_t b[4];
+                        put_int(b, 0, get_int(otup.data(), od.off[t.lhs.col]) ^ 0x80000000u);
+                        key.assign((const char*)b, 4);
+                    }
+                    auto it = ix.by_value.find(key);
+                    if (it != ix.by_value.end())
+                        for (int64_t p : it->second)
+                            if (!bit(inner_deleted, p)) conj_bits[p >> 6] |= 1ull << (p & 63);
+                    continue;
+                }
                 for (auto& kv : ix.by_value) {
                     int c;                                           // sign of compare(outer value, v)
                     if (ix.type == ATTR_STRING) {
