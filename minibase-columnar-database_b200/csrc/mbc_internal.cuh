@@ -16,8 +16,11 @@ namespace mbc {
 // u*128 + l*4 + {0..3}, i.e. exactly one 128-bit load of a 4-byte column.  A 256-thread CTA
 // (8 warps) owns a 4096-row tile.  Every column allocation is padded to a whole tile so the
 // vector loads of the last tile stay in bounds; rows >= nrows are masked off.
-constexpr int kScanThreads   = 256;
-constexpr int kWarpsPerCta   = kScanThreads / 32;
+#ifndef MBC_WORKER_WARPS
+#define MBC_WORKER_WARPS 8
+#endif
+constexpr int kWarpsPerCta   = MBC_WORKER_WARPS;          // worker warps of a scan CTA (+1 scan warp)
+constexpr int kScanThreads   = kWarpsPerCta * 32;
 constexpr int kVec           = 4;
 constexpr int kUnits         = 4;
 constexpr int kRowsPerThread = kVec * kUnits;              // 16

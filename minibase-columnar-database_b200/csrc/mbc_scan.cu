@@ -1,6 +1,7 @@
 // mbc_scan.cu -- host side of K2/K5 (kernels in mbc_scan_kernels.cuh): builds the term program,
 // owns the result buffers, launches the fused scan, and implements the two public entry points
 // mbc_scan (table resident in HBM) and mbc_scan_host (host-resident columns streamed through HBM).
+#include <cstdio>
 #include <cstring>
 #include <algorithm>
 
@@ -104,6 +105,18 @@ static int32_t plan_staging(mbc_ctx* ctx, ScanParams* p, size_t* smem_bytes, int
         p->aggs[a].staged = -1;
         for (int s = 0; s < p->nstaged; ++s) if (p->aggs[a].col >= 0 && p->staged_cols[s] == p->aggs[a].col) p->aggs[a].staged = s;
     }
+    // columns phase B reads from HBM (prefetched into L2 one iteration ahead)
+    p->ngather = 0;
+    auto add_gather = [&](int col, int stride) {
+        for (int g = 0; g < p->ngather; ++g) if (p->gather[g].col == col) return;
+        if (p->ngather == kMaxGather) return;
+        p->gather[p->ngather].col = col;
+        p->gather[p->ngather].stride = stride;
+        p->gather[p->ngather].ptr = nullptr;
+        p->ngather++;
+    };
+    for (int c = 0; c < p->nproj; ++c) if (p->proj[c].staged < 0) add_gather(p->proj[c].col, p->proj[c].stride);
+    for (int a = 0; a < p->nagg; ++a) if (p->aggs[a].col >= 0 && p->aggs[a].staged < 0) add_gather(p->aggs[a].col, 4);
     p->nstages = p->nstaged <= 2 ? 3 : 2;
     *smem_bytes = (size_t)p->nstages * p->nstaged * kStageColBytes;
     static size_t configured = 0;
@@ -112,9 +125,9 @@ static int32_t plan_staging(mbc_ctx* ctx, ScanParams* p, size_t* smem_bytes, int
         configured = 200 * 1024;
     }
     int blocks_per_sm = 1;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, scan_kernel, kScanThreads, *smem_bytes) != cudaSuccess || blocks_per_sm < 1)
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, scan_kernel, kScanCtaThreads, *smem_bytes) != cudaSuccess || blocks_per_sm < 1)
         blocks_per_sm = 1;
-    blocks_per_sm = std::min(blocks_per_sm, 4);
+    blocks_per_sm = std::min(blocks_per_sm, 8);
     *grid = std::max(1, std::min(p->ntiles, ctx->sm_count * blocks_per_sm));
     return MBC_OK;
 }
@@ -334,6 +347,7 @@ static void bind_table(ScanJob* job, const mbc_table* t) {
     }
     for (int c = 0; c < p.nproj; ++c) p.proj[c].src = t->cols[p.proj[c].col].d;
     for (int s = 0; s < p.nstaged; ++s) p.staged_src[s] = t->cols[p.staged_cols[s]].d;
+    for (int g = 0; g < p.ngather; ++g) p.gather[g].ptr = t->cols[p.gather[g].col].d;
     for (int a = 0; a < p.nagg; ++a)
         if (p.aggs[a].col >= 0) p.aggs[a].src = t->cols[p.aggs[a].col].d;
     p.deleted = t->has_deleted ? t->d_deleted : nullptr;
@@ -354,7 +368,27 @@ static int32_t launch_job(ScanJob* job, int tile_base, bool first) {
         MBC_CUDA(cudaMemsetAsync(p.ticket, 0, 4, ctx->stream));
         MBC_CUDA(cudaMemsetAsync(p.status, 0, (size_t)p.ntiles * 8, ctx->stream));
     }
-    scan_kernel<<<job->grid_per_tiles(p.ntiles), kScanThreads, job->smem_bytes, ctx->stream>>>(p);
+#ifdef MBC_SCAN_PROFILE
+    static long long* d_prof = nullptr;
+    if (!d_prof) cudaMalloc(&d_prof, 24 * 8);
+    cudaMemsetAsync(d_prof, 0, 24 * 8, ctx->stream);
+    p.prof = d_prof;
+#endif
+    scan_kernel<<<job->grid_per_tiles(p.ntiles), kScanCtaThreads, job->smem_bytes, ctx->stream>>>(p);
+#ifdef MBC_SCAN_PROFILE
+    {
+        long long h[24];
+        cudaMemcpyAsync(h, d_prof, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream);
+        cudaStreamSynchronize(ctx->stream);
+        const int g = job->grid_per_tiles(p.ntiles);
+        const char* names[8] = {"tma_wait", "phaseA", "S1_wait", "list/publish", "phaseB", "S2_wait", "lookback", "other"};
+        for (int who = 0; who < 3; ++who) {
+            fprintf(stderr, "[scan prof] %s: ", who == 0 ? "scan warp " : who == 1 ? "worker w0 " : "worker w1 ");
+            for (int k = 0; k < 8; ++k) fprintf(stderr, "%s=%.0fk ", names[k], (double)h[who * 8 + k] / g / 1e3);
+            fprintf(stderr, "(cycles per CTA, %d CTAs, %d tiles)\n", g, p.ntiles);
+        }
+    }
+#endif
     ctx->launches++;
     MBC_CUDA(cudaGetLastError());
     return MBC_OK;

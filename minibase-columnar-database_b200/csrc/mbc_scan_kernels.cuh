@@ -72,6 +72,13 @@ struct DevAgg {
     int32_t staged;      // staged predicate column, or -1
 };
 
+struct DevGather {              // a column phase B gathers from HBM (not staged): prefetched to L2 in phase A
+    const void* ptr;
+    int32_t stride;
+    int32_t col;
+};
+
+constexpr int kMaxGather = 8;
 constexpr int kMaxStaged = 4;                    // 4-byte predicate columns staged through shared memory
 constexpr int kStageColBytes = kTileRows * 4;    // one column of one tile: 16 KB
 
@@ -88,6 +95,8 @@ struct ScanParams {
     int32_t nstages;              // depth of the tile ring (2..kMaxStages)
     const void* staged_src[kMaxStaged];
     int32_t staged_cols[kMaxStaged];   // host bookkeeping: table column of every staged slot
+    int32_t ngather, pad1;
+    DevGather gather[kMaxGather];
     const uint32_t* sel_bitmap;   // optional precomputed selection
     const uint32_t* deleted;      // optional markedDeleted bitmap
     int64_t* out_pos;
@@ -95,6 +104,7 @@ struct ScanParams {
     unsigned long long* status;   // one look-back word per tile
     unsigned int* ticket;
     long long* count;             // in: running output offset, out: offset after this launch
+    long long* prof;              // optional phase timers (MBC_SCAN_PROFILE builds)
     unsigned long long* partials; // [nagg][total_tiles]
     DevTerm terms[kMaxTerms];
     DevProj proj[kMaxProj];
@@ -168,27 +178,48 @@ __device__ __forceinline__ void load_operand32(const DevOperand& o, int64_t thre
     }
 }
 
+// 16 rows of one relation: bit i = rel(a[i], b[i])
+#define MBC_CMP16(T, CONV, REL)                                                           \
+    {                                                                                      \
+        uint32_t m = 0;                                                                    \
+        _Pragma("unroll") for (int i = 0; i < kRowsPerThread; ++i) {                       \
+            T x = CONV(a[i]), y = CONV(b[i]);                                              \
+            m |= (uint32_t)(x REL y) << i;                                                 \
+        }                                                                                  \
+        return m;                                                                          \
+    }
+
+__device__ __forceinline__ int32_t as_i32(uint32_t v) { return (int32_t)v; }
+
 // TupleUtils.java:48-57 (int) and :59-68 (float): 16 rows at once.  Bit u*4+j = row u*128+lane*4+j.
+// The operator switch is outside the row loop: one compare + one bit insert per row.
 __device__ __forceinline__ uint32_t eval_term32(const DevTerm& t, int64_t thread_row0, const uint32_t* stage, int tile_off) {
     uint32_t a[kRowsPerThread], b[kRowsPerThread];
     load_operand32(t.lhs, thread_row0, stage, tile_off, a);
     load_operand32(t.rhs, thread_row0, stage, tile_off, b);
-    uint32_t lt = 0, eq = 0;
     if (t.cmp_type == MBC_ATTR_INTEGER) {
-#pragma unroll
-        for (int i = 0; i < kRowsPerThread; ++i) {
-            lt |= (uint32_t)((int32_t)a[i] < (int32_t)b[i]) << i;
-            eq |= (uint32_t)(a[i] == b[i]) << i;
+        switch (t.op) {
+            case MBC_OP_EQ: MBC_CMP16(int32_t, as_i32, ==)
+            case MBC_OP_LT: MBC_CMP16(int32_t, as_i32, <)
+            case MBC_OP_GT: MBC_CMP16(int32_t, as_i32, >)
+            case MBC_OP_NE: MBC_CMP16(int32_t, as_i32, !=)
+            case MBC_OP_LE: MBC_CMP16(int32_t, as_i32, <=)
+            case MBC_OP_GE: MBC_CMP16(int32_t, as_i32, >=)
+            case MBC_OP_NOT: MBC_CMP16(int32_t, as_i32, !=)     // PredEval.java:158-160: aopNOT behaves as NE
+            default: return 0u;                                  // aopNOP / opRANGE never match
         }
     } else {
-#pragma unroll
-        for (int i = 0; i < kRowsPerThread; ++i) {
-            float x = __uint_as_float(a[i]), y = __uint_as_float(b[i]);
-            lt |= (uint32_t)(x < y) << i;
-            eq |= (uint32_t)(x == y) << i;
+        switch (t.op) {                                          // NaN-free by contract (TupleUtils.java:59-70)
+            case MBC_OP_EQ: MBC_CMP16(float, __uint_as_float, ==)
+            case MBC_OP_LT: MBC_CMP16(float, __uint_as_float, <)
+            case MBC_OP_GT: MBC_CMP16(float, __uint_as_float, >)
+            case MBC_OP_NE: MBC_CMP16(float, __uint_as_float, !=)
+            case MBC_OP_LE: MBC_CMP16(float, __uint_as_float, <=)
+            case MBC_OP_GE: MBC_CMP16(float, __uint_as_float, >=)
+            case MBC_OP_NOT: MBC_CMP16(float, __uint_as_float, !=)
+            default: return 0u;
         }
     }
-    return mask_op(t.op, lt, eq);
 }
 
 // one string operand word w of row `row`: column word (zero beyond the stride) or literal word
@@ -299,6 +330,8 @@ __device__ __forceinline__ long long lookback(volatile unsigned long long* statu
 
 // ---- TMA bulk copy + mbarrier (sm_90+/sm_100a) -----------------------------------------------------
 
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -331,36 +364,116 @@ __device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gmem_sr
 
 // ---- the kernel ------------------------------------------------------------------------------
 //
-// Persistent CTAs; each keeps a ring of kStages tile slots.  For every claimed tile the producer thread
-// issues one TMA bulk copy per staged predicate column (16 KB each) into the slot; the copies of the next
-// tiles are in flight while the current tile is evaluated, so HBM latency is hidden by the ring, not by
-// occupancy.  Every loop iteration runs phase A of the newest tile (mask, ranks, survivor list, publish the
-// tile aggregate for the look-back) and phase B of the previous tile (resolve its prefix, then write
-// positions / projected values / aggregate partials with one lane per SURVIVOR, so the cost of phase B is
-// proportional to the selectivity and the stores are coalesced).  Publishing a tile one iteration before
-// its own prefix is needed keeps the look-back chain off the critical path.
+// Persistent CTAs: kWarpsPerCta worker warps (512 rows each of a tile) + one scan warp.  Each CTA keeps a
+// ring of tile slots; for every claimed tile one worker thread issues one TMA bulk copy per staged
+// predicate column, so the copies of the next tiles are in flight while the current tile is evaluated:
+// HBM latency is hidden by the ring depth, not by occupancy.  One loop iteration `it` handles the newest
+// tile A and the previous tile B:
+//     workers   : phase A of tile A (mask from shared memory, packed warp scan -> warp totals)
+//   -- barrier 0 (all warps) --
+//     scan warp : tile total of A, publish its aggregate, run the wide decoupled look-back, leave A's global
+//                 output offset in shared memory.  It has a whole iteration for this: nobody waits for it
+//                 before barrier 0 of iteration it+1.
+//     workers   : write A's survivors (row-in-tile, by tile rank) into a shared list and prefetch the HBM
+//                 sectors phase B will gather; then phase B of tile B with ONE THREAD PER SURVIVOR: position,
+//                 projected values (staged columns from shared memory, the others gathered from HBM in
+//                 batches) and aggregate partials.  Warps without survivors skip; stores are coalesced.
+//   -- barrier 1 (workers only) --   tile B's slot is free: worker 0 claims the next tile and refills it.
 
 constexpr int kMaxStages = 4;
 
-__global__ void __launch_bounds__(kScanThreads, 2) scan_kernel(const __grid_constant__ ScanParams p) {
+// Optional phase timers (-DMBC_SCAN_PROFILE): per-phase clock64 sums of one worker warp / the scan warp,
+// accumulated into p.prof[8] by lane 0.  Off in the product build.
+#ifdef MBC_SCAN_PROFILE
+#define MBC_T0() long long _t0 = clock64()
+#define MBC_TICK(slot) do { long long _t1 = clock64(); _prof[slot] += _t1 - _t0; _t0 = _t1; } while (0)
+#else
+#define MBC_T0() do {} while (0)
+#define MBC_TICK(slot) do {} while (0)
+#endif
+constexpr int kScanCtaThreads = kScanThreads + 32;                 // worker warps + the scan warp
+constexpr int kGatherBatch = 4;
+constexpr int kScanMinCtas = kWarpsPerCta >= 8 ? 2 : kWarpsPerCta >= 4 ? 3 : 6;
+constexpr int kLookPerLane = 8;                                    // look-back window = 256 tiles per round
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// Decoupled look-back with a 256-tile window per round: with ~300 tiles in flight on a B200 the nearest
+// tile that already knows its inclusive prefix is usually more than 32 tiles back.
+__device__ __forceinline__ long long lookback_wide(volatile unsigned long long* status, int tile, long long total, long long init,
+                                                    int lane) {
+    if (tile == 0) {
+        if (lane == 0) status[0] = kFlagIncl | (unsigned long long)(init + total);
+        return init;
+    }
+    long long prefix = 0;
+    int hi = tile - 1 - lane * kLookPerLane;                      // nearest predecessor this lane inspects
+    while (true) {
+        unsigned long long s[kLookPerLane];
+#pragma unroll
+        for (int j = 0; j < kLookPerLane; ++j) s[j] = (hi - j) >= 0 ? status[hi - j] : (2ull << 62);   // before tile 0: inclusive 0
+        bool found = false, invalid = false;
+        long long sum = 0;
+#pragma unroll
+        for (int j = 0; j < kLookPerLane; ++j) {
+            if (!found && !invalid) {
+                const unsigned long long f = s[j] >> 62;
+                if (f == 0) invalid = true;
+                else { sum += (long long)(s[j] & kValMask); found = (f == 2); }
+            }
+        }
+        const uint32_t fmask = __ballot_sync(0xFFFFFFFFu, found);
+        const uint32_t imask = __ballot_sync(0xFFFFFFFFu, invalid);
+        const int first = fmask ? __ffs(fmask) - 1 : 31;          // nearest lane that reached an inclusive prefix
+        const uint32_t relevant = first >= 31 ? 0xFFFFFFFFu : ((1u << (first + 1)) - 1u);
+        if (imask & relevant) continue;                            // a needed predecessor has not published yet: reload
+        prefix += warp_sum_i64(lane <= first ? sum : 0ll);
+        if (fmask) break;
+        hi -= 32 * kLookPerLane;
+    }
+    if (lane == 0) status[tile] = kFlagIncl | (unsigned long long)(prefix + total);
+    return prefix;
+}
+
+template <typename T>
+__device__ __forceinline__ T agg_combine(int kind, T a, T b) {
+    return (kind == MBC_AGG_COUNT || kind == MBC_AGG_SUM) ? a + b : kind == MBC_AGG_MIN ? (a < b ? a : b) : (a > b ? a : b);
+}
+
+__device__ __forceinline__ unsigned long long agg_identity(const DevAgg& g) {
+    const bool integral = g.kind == MBC_AGG_COUNT || g.type == MBC_ATTR_INTEGER;
+    if (g.kind == MBC_AGG_MIN) return integral ? (unsigned long long)(long long)INT32_MAX : (unsigned long long)__double_as_longlong((double)INFINITY);
+    if (g.kind == MBC_AGG_MAX) return integral ? (unsigned long long)(long long)INT32_MIN : (unsigned long long)__double_as_longlong((double)-INFINITY);
+    return integral ? 0ull : (unsigned long long)__double_as_longlong(0.0);
+}
+
+__device__ __forceinline__ unsigned long long agg_merge(const DevAgg& g, unsigned long long a, unsigned long long b) {
+    if (g.kind == MBC_AGG_COUNT || g.type == MBC_ATTR_INTEGER)
+        return (unsigned long long)agg_combine<long long>(g.kind, (long long)a, (long long)b);
+    return (unsigned long long)__double_as_longlong(agg_combine<double>(g.kind, __longlong_as_double((long long)a), __longlong_as_double((long long)b)));
+}
+
+__global__ void __launch_bounds__(kScanCtaThreads, kScanMinCtas) scan_kernel(const __grid_constant__ ScanParams p) {
     extern __shared__ __align__(128) uint8_t stage_mem[];          // [nstages][nstaged][kTileRows] uint32
     __shared__ __align__(8) uint64_t s_full[kMaxStages];
     __shared__ int s_tileq[kMaxStages];
-    __shared__ uint16_t s_list[2][kWarpsPerCta][kWarpRows];        // survivor rows (within the warp's 512), by rank
+    __shared__ uint16_t s_list[2][kTileRows];                      // survivor rows within the tile, by tile rank
     __shared__ uint32_t s_wtot[2][kWarpsPerCta];
-    __shared__ uint32_t s_wbase[2][kWarpsPerCta];
     __shared__ long long s_ttotal[2];
     __shared__ long long s_tbase;
     __shared__ unsigned long long s_aggw[kMaxAgg][kWarpsPerCta];
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
-    const int warp = tid >> 5;
+    const bool scan_warp = tid < 32;
+    const int wwarp = (tid >> 5) - 1;                              // worker warp 0..7 (-1 for the scan warp)
+    const int wtid = tid - 32;                                     // worker thread 0..255
     const int S = p.nstages;
     const uint32_t stage_bytes = (uint32_t)p.nstaged * kStageColBytes;
-    constexpr int kProducer = 32;                                  // first lane of warp 1 (warp 0 runs the look-back)
 
-    auto issue_tile = [&](int slot, int tile) {                    // producer thread only
+    auto issue_tile = [&](int slot, int tile) {                    // one elected thread
         if (p.nstaged == 0) return;
         mbar_arrive_expect_tx(&s_full[slot], stage_bytes);
         for (int c = 0; c < p.nstaged; ++c)
@@ -369,12 +482,9 @@ __global__ void __launch_bounds__(kScanThreads, 2) scan_kernel(const __grid_cons
                          &s_full[slot]);
     };
 
-    if (tid == kProducer) {
+    if (tid == 0) {
         for (int s = 0; s < S; ++s) mbar_init(&s_full[s], 1);
         mbar_fence_init();
-    }
-    __syncthreads();
-    if (tid == kProducer) {
         for (int s = 0; s < S; ++s) {
             int t = (int)atomicAdd(p.ticket, 1u);
             s_tileq[s] = t;
@@ -383,22 +493,46 @@ __global__ void __launch_bounds__(kScanThreads, 2) scan_kernel(const __grid_cons
     }
     __syncthreads();
 
+#ifdef MBC_SCAN_PROFILE
+    long long _prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#endif
+    MBC_T0();
     int tileB = INT32_MAX, slotB = 0, bufB = 0, newtile = INT32_MAX;
+    int slotA = 0;
+    uint32_t parityA = 0;                                          // flips every time the ring wraps
     for (int it = 0;; ++it) {
-        const int slotA = it % S, bufA = it & 1;
+        const int bufA = it & 1;
         const int tileA = s_tileq[slotA];
         const bool validA = tileA < p.ntiles, validB = tileB < p.ntiles;
         if (!validA && !validB) break;
 
-        // =========================== phase A: newest tile ===========================
-        if (validA) {
-            if (p.nstaged) mbar_wait(&s_full[slotA], (uint32_t)((it / S) & 1));
+        uint32_t mask = 0, excl = 0, unit_off1 = 0, unit_off2 = 0, unit_off3 = 0;
+        if (scan_warp) {
+            // ---- look-back of the previous tile, overlapped with the workers' phase A ----
+            if (validB) {
+                const long long total = s_ttotal[bufB];
+                long long init = 0;
+                if (tileB == 0) init = *p.count;
+                MBC_TICK(7);
+                const long long prefix = lookback_wide(p.status, tileB, total, init, lane);
+                MBC_TICK(6);
+                if (lane == 0) {
+                    s_tbase = prefix;
+                    if (tileB == p.ntiles - 1) *p.count = prefix + total;
+                    newtile = (int)atomicAdd(p.ticket, 1u);        // next tile for the slot tile B is about to free
+                }
+            }
+        } else if (validA) {
+            // =========================== phase A: newest tile ===========================
+            MBC_TICK(7);
+            if (p.nstaged) mbar_wait(&s_full[slotA], parityA);
+            MBC_TICK(0);
             const uint32_t* stage = reinterpret_cast<const uint32_t*>(stage_mem + (size_t)slotA * stage_bytes);
-            const int64_t warp_row0 = (int64_t)tileA * kTileRows + warp * kWarpRows;
+            const int64_t warp_row0 = (int64_t)tileA * kTileRows + wwarp * kWarpRows;
             const int64_t thread_row0 = warp_row0 + lane * kVec;
-            const int tile_off = warp * kWarpRows + lane * kVec;   // this thread's first row within the tile
+            const int tile_off = wwarp * kWarpRows + lane * kVec;  // this thread's first row within the tile
 
-            uint32_t mask = 0xFFFFu;
+            mask = 0xFFFFu;
             if (p.sel_bitmap) mask &= load_bits(p.sel_bitmap, warp_row0, lane);
             if (p.nterms > 0) {
                 uint32_t acc = 0;
@@ -427,24 +561,11 @@ __global__ void __launch_bounds__(kScanThreads, 2) scan_kernel(const __grid_cons
                 if (lane >= o) incl += n;
             }
             const uint32_t tot = __shfl_sync(0xFFFFFFFFu, incl, 31);
-            const uint32_t excl = incl - packed;
-            uint32_t unit_off[kUnits];
-            unit_off[0] = 0;
-            unit_off[1] = tot & 0xFFu;
-            unit_off[2] = unit_off[1] + ((tot >> 8) & 0xFFu);
-            unit_off[3] = unit_off[2] + ((tot >> 16) & 0xFFu);
-            if (lane == 0) s_wtot[bufA][warp] = unit_off[3] + (tot >> 24);
-            if (mask) {
-                uint16_t* list = s_list[bufA][warp];
-#pragma unroll
-                for (int u = 0; u < kUnits; ++u) {
-                    uint32_t nib = (mask >> (u * 4)) & 0xFu;
-                    uint32_t r = unit_off[u] + ((excl >> (8 * u)) & 0xFFu);
-#pragma unroll
-                    for (int j = 0; j < kVec; ++j)
-                        if ((nib >> j) & 1u) list[r++] = (uint16_t)(u * kUnitRows + lane * kVec + j);
-                }
-            }
+            excl = incl - packed;
+            unit_off1 = tot & 0xFFu;
+            unit_off2 = unit_off1 + ((tot >> 8) & 0xFFu);
+            unit_off3 = unit_off2 + ((tot >> 16) & 0xFFu);
+            if (lane == 0) s_wtot[bufA][wwarp] = unit_off3 + (tot >> 24);
             if (p.out_bitmap) {                                    // BitSet-compatible: bit p = word p/32, bit p%32
 #pragma unroll
                 for (int u = 0; u < kUnits; ++u) {
@@ -456,147 +577,240 @@ __global__ void __launch_bounds__(kScanThreads, 2) scan_kernel(const __grid_cons
                 }
             }
         }
-        __syncthreads();                                           // S1
+        MBC_TICK(1);
+        __syncthreads();                                           // S1: warp totals of A, prefix of B
+        MBC_TICK(2);
 
-        // ============ warp 0: publish tile A's aggregate, then resolve tile B's prefix ============
-        if (warp == 0) {
-            if (validA) {
+        if (scan_warp) {
+            if (lane == 0 && validB) s_tileq[slotB] = newtile;
+            if (validA) {                                          // publish the newest tile's aggregate
                 uint32_t v = lane < kWarpsPerCta ? s_wtot[bufA][lane] : 0u;
-                uint32_t inc = v;
 #pragma unroll
-                for (int o = 1; o < kWarpsPerCta; o <<= 1) {
-                    uint32_t n = __shfl_up_sync(0xFFFFFFFFu, inc, o);
-                    if (lane >= o) inc += n;
-                }
-                if (lane < kWarpsPerCta) s_wbase[bufA][lane] = inc - v;
-                const long long tile_total = (long long)__shfl_sync(0xFFFFFFFFu, inc, kWarpsPerCta - 1);
+                for (int o = 4; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
                 if (lane == 0) {
-                    s_ttotal[bufA] = tile_total;
-                    if (tileA > 0) p.status[tileA] = kFlagAgg | (unsigned long long)tile_total;
+                    s_ttotal[bufA] = (long long)v;
+                    if (tileA > 0) p.status[tileA] = kFlagAgg | (unsigned long long)v;
                 }
             }
+        } else {
+            if (validA) {
+                // tile rank of this warp's first survivor = totals of the warps before it
+                const uint32_t mine = s_wtot[bufA][wwarp];
+                uint32_t wbase = (lane < wwarp) ? s_wtot[bufA][lane & (kWarpsPerCta - 1)] : 0u;
+                wbase += __shfl_xor_sync(0xFFFFFFFFu, wbase, 1);
+                wbase += __shfl_xor_sync(0xFFFFFFFFu, wbase, 2);
+                wbase += __shfl_xor_sync(0xFFFFFFFFu, wbase, 4);
+                wbase = __shfl_sync(0xFFFFFFFFu, wbase, 0);
+                if (mask) {
+                    uint16_t* list = s_list[bufA] + wbase;
+                    const uint32_t uoff[kUnits] = {0u, unit_off1, unit_off2, unit_off3};
+                    const int64_t row0 = (int64_t)tileA * kTileRows + wwarp * kWarpRows + lane * kVec;
+                    const bool sparse = mine <= kWarpRows / 4;         // dense tiles stream anyway: no prefetch
+#pragma unroll
+                    for (int u = 0; u < kUnits; ++u) {
+                        uint32_t nib = (mask >> (u * 4)) & 0xFu;
+                        if (nib) {
+                            uint32_t r = uoff[u] + ((excl >> (8 * u)) & 0xFFu);
+#pragma unroll
+                            for (int j = 0; j < kVec; ++j)
+                                if ((nib >> j) & 1u) list[r++] = (uint16_t)(wwarp * kWarpRows + u * kUnitRows + lane * kVec + j);
+                            // phase B gathers these rows one iteration from now: pull their sectors into L2 today
+                            if (sparse) {
+                                for (int g = 0; g < p.ngather; ++g) {
+                                    const char* base = reinterpret_cast<const char*>(p.gather[g].ptr) + (row0 + u * kUnitRows) * p.gather[g].stride;
+                                    if (p.gather[g].stride <= 8) {
+                                        prefetch_l2(base);                               // 4 rows share one sector
+                                    } else {
+#pragma unroll
+                                        for (int j = 0; j < kVec; ++j)
+                                            if ((nib >> j) & 1u) prefetch_l2(base + j * p.gather[g].stride);
+                                    }
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            MBC_TICK(3);
+            // =========================== phase B: previous tile, one thread per survivor ===========================
             if (validB) {
-                const long long total = s_ttotal[bufB];
-                long long init = 0;
-                if (tileB == 0) init = *p.count;
-                const long long prefix = lookback(p.status, tileB, total, init, lane);
-                if (lane == 0) {
-                    s_tbase = prefix;
-                    if (tileB == p.ntiles - 1) *p.count = prefix + total;
-                }
-            }
-        } else if (tid == kProducer && validB) {
-            newtile = (int)atomicAdd(p.ticket, 1u);                // next tile for the slot tile B is about to free
-            s_tileq[slotB] = newtile;
-        }
-        __syncthreads();                                           // S2
-
-        // =========================== phase B: previous tile, one lane per survivor ===========================
-        if (validB) {
-            const uint32_t* stage = reinterpret_cast<const uint32_t*>(stage_mem + (size_t)slotB * stage_bytes);
-            const int n = (int)s_wtot[bufB][warp];
-            const long long base = s_tbase + s_wbase[bufB][warp];
-            const int64_t warp_row0 = (int64_t)tileB * kTileRows + warp * kWarpRows;
-            const uint16_t* list = s_list[bufB][warp];
-            unsigned long long acc[kMaxAgg];
+                const int T = (int)s_ttotal[bufB];
+                if (T > 0 && T <= kScanThreads) {
+                    // sparse tile: one work item (positions / one projected column / one aggregate) per warp, so the
+                    // dependent load->store chains of the columns run side by side instead of back to back
+                    const uint32_t* stage = reinterpret_cast<const uint32_t*>(stage_mem + (size_t)slotB * stage_bytes);
+                    const long long base = s_tbase;
+                    const int64_t tile_row0 = (int64_t)tileB * kTileRows;
+                    const uint16_t* list = s_list[bufB];
+                    const int nitems = 1 + p.nproj + p.nagg;
+                    for (int item = wwarp; item < nitems; item += kWarpsPerCta) {
+                        if (item == 0) {
+                            if (p.out_pos)
+                                for (int k = lane; k < T; k += 32) p.out_pos[base + k] = p.pos_base + tile_row0 + list[k];
+                        } else if (item <= p.nproj) {
+                            const DevProj& pr = p.proj[item - 1];
+                            if (pr.stride == 4) {
+                                uint32_t* dst = reinterpret_cast<uint32_t*>(pr.dst) + base;
+                                const uint32_t* src = pr.staged >= 0 ? stage + pr.staged * kTileRows
+                                                                     : reinterpret_cast<const uint32_t*>(pr.src) + tile_row0;
+                                for (int k = lane; k < T; k += 32) dst[k] = src[list[k]];
+                            } else if (pr.stride == 16) {
+                                const uint4* src = reinterpret_cast<const uint4*>(pr.src) + tile_row0;
+                                uint4* dst = reinterpret_cast<uint4*>(pr.dst) + base;
+                                for (int k = lane; k < T; k += 32) dst[k] = __ldg(src + list[k]);
+                            } else {
+                                const int words = pr.stride >> 2;
+                                for (int k = lane; k < T; k += 32) {
+                                    const uint32_t* src = reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(pr.src) +
+                                                                                            (tile_row0 + list[k]) * pr.stride);
+                                    uint32_t* dst = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(pr.dst) + (base + k) * pr.stride);
+                                    for (int q = 0; q < words; ++q) dst[q] = __ldg(src + q);
+                                }
+                            }
+                        } else {
+                            const int a = item - 1 - p.nproj;
+                            const DevAgg& g = p.aggs[a];
+                            unsigned long long v;
+                            if (g.kind == MBC_AGG_COUNT) {
+                                v = (unsigned long long)T;
+                            } else {
+                                const uint32_t* src = g.staged >= 0 ? stage + g.staged * kTileRows
+                                                                    : reinterpret_cast<const uint32_t*>(g.src) + tile_row0;
+                                if (g.type == MBC_ATTR_INTEGER) {
+                                    long long acc = (long long)agg_identity(g);
+                                    for (int k = lane; k < T; k += 32) acc = agg_combine<long long>(g.kind, acc, (long long)(int32_t)src[list[k]]);
 #pragma unroll
-            for (int a = 0; a < kMaxAgg; ++a) {
-                if (a < p.nagg) {
-                    const DevAgg& g = p.aggs[a];
-                    const bool integral = g.kind == MBC_AGG_COUNT || g.type == MBC_ATTR_INTEGER;
-                    if (g.kind == MBC_AGG_MIN) acc[a] = integral ? (unsigned long long)(long long)INT32_MAX : (unsigned long long)__double_as_longlong((double)INFINITY);
-                    else if (g.kind == MBC_AGG_MAX) acc[a] = integral ? (unsigned long long)(long long)INT32_MIN : (unsigned long long)__double_as_longlong((double)-INFINITY);
-                    else acc[a] = integral ? 0ull : (unsigned long long)__double_as_longlong(0.0);
-                }
-            }
-            for (int k = lane; k < n; k += 32) {
-                const int r = list[k];
-                const int64_t row = warp_row0 + r;
-                const long long slot = base + k;
-                if (p.out_pos) p.out_pos[slot] = p.pos_base + row;
-                for (int c = 0; c < p.nproj; ++c) {                // iterator/Projection.java:103-144
-                    const DevProj& pr = p.proj[c];
-                    if (pr.stride == 4) {
-                        uint32_t v = pr.staged >= 0 ? stage[pr.staged * kTileRows + warp * kWarpRows + r]
-                                                    : __ldg(reinterpret_cast<const uint32_t*>(pr.src) + row);
-                        reinterpret_cast<uint32_t*>(pr.dst)[slot] = v;
-                    } else if ((pr.stride & 15) == 0) {
-                        const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(pr.src) + row * pr.stride);
-                        uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<char*>(pr.dst) + slot * pr.stride);
-                        for (int q = 0; q < (pr.stride >> 4); ++q) dst[q] = __ldg(src + q);
-                    } else {
-                        const uint32_t* src = reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(pr.src) + row * pr.stride);
-                        uint32_t* dst = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(pr.dst) + slot * pr.stride);
-                        for (int q = 0; q < (pr.stride >> 2); ++q) dst[q] = __ldg(src + q);
+                                    for (int o = 16; o > 0; o >>= 1) acc = agg_combine<long long>(g.kind, acc, __shfl_xor_sync(0xFFFFFFFFu, acc, o));
+                                    v = (unsigned long long)acc;
+                                } else {
+                                    // same association as the dense path: lane partials in survivor order, then the butterfly
+                                    double acc = __longlong_as_double((long long)agg_identity(g));
+                                    for (int k = lane; k < T; k += 32) acc = agg_combine<double>(g.kind, acc, (double)__uint_as_float(src[list[k]]));
+#pragma unroll
+                                    for (int o = 16; o > 0; o >>= 1) acc = agg_combine<double>(g.kind, acc, __shfl_xor_sync(0xFFFFFFFFu, acc, o));
+                                    v = (unsigned long long)__double_as_longlong(acc);
+                                }
+                            }
+                            if (lane == 0) p.partials[(size_t)a * p.total_tiles + p.tile_base + tileB] = v;
+                        }
                     }
-                }
+                } else
+                if (wwarp * 32 < T) {                              // warp-uniform: warps without survivors skip
+                    const uint32_t* stage = reinterpret_cast<const uint32_t*>(stage_mem + (size_t)slotB * stage_bytes);
+                    const long long base = s_tbase;
+                    const int64_t tile_row0 = (int64_t)tileB * kTileRows;
+                    const uint16_t* list = s_list[bufB];
+                    if (p.out_pos) {
+                        for (int k = wtid; k < T; k += kScanThreads) p.out_pos[base + k] = p.pos_base + tile_row0 + list[k];
+                    }
+                    for (int c = 0; c < p.nproj; ++c) {            // iterator/Projection.java:103-144
+                        const DevProj& pr = p.proj[c];
+                        if (pr.stride == 4) {
+                            uint32_t* dst = reinterpret_cast<uint32_t*>(pr.dst) + base;
+                            if (pr.staged >= 0) {
+                                const uint32_t* src = stage + pr.staged * kTileRows;
+                                for (int k = wtid; k < T; k += kScanThreads) dst[k] = src[list[k]];
+                            } else {
+                                const uint32_t* src = reinterpret_cast<const uint32_t*>(pr.src) + tile_row0;
+                                for (int k0 = wtid; k0 < T; k0 += kScanThreads * kGatherBatch) {
+                                    uint32_t v[kGatherBatch];
 #pragma unroll
-                for (int a = 0; a < kMaxAgg; ++a) {
-                    if (a < p.nagg) {
+                                    for (int b = 0; b < kGatherBatch; ++b) {
+                                        int k = k0 + b * kScanThreads;
+                                        if (k < T) v[b] = __ldg(src + list[k]);
+                                    }
+#pragma unroll
+                                    for (int b = 0; b < kGatherBatch; ++b) {
+                                        int k = k0 + b * kScanThreads;
+                                        if (k < T) dst[k] = v[b];
+                                    }
+                                }
+                            }
+                        } else if (pr.stride == 16) {
+                            const uint4* src = reinterpret_cast<const uint4*>(pr.src) + tile_row0;
+                            uint4* dst = reinterpret_cast<uint4*>(pr.dst) + base;
+                            for (int k0 = wtid; k0 < T; k0 += kScanThreads * kGatherBatch) {
+                                uint4 v[kGatherBatch];
+#pragma unroll
+                                for (int b = 0; b < kGatherBatch; ++b) {
+                                    int k = k0 + b * kScanThreads;
+                                    if (k < T) v[b] = __ldg(src + list[k]);
+                                }
+#pragma unroll
+                                for (int b = 0; b < kGatherBatch; ++b) {
+                                    int k = k0 + b * kScanThreads;
+                                    if (k < T) dst[k] = v[b];
+                                }
+                            }
+                        } else {
+                            const int words = pr.stride >> 2;
+                            for (int k = wtid; k < T; k += kScanThreads) {
+                                const uint32_t* src = reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(pr.src) +
+                                                                                        (tile_row0 + list[k]) * pr.stride);
+                                uint32_t* dst = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(pr.dst) + (base + k) * pr.stride);
+                                for (int q = 0; q < words; ++q) dst[q] = __ldg(src + q);
+                            }
+                        }
+                    }
+                    // aggregates: per-thread fold over its survivors, then one butterfly per participating warp
+                    for (int a = 0; a < p.nagg; ++a) {
                         const DevAgg& g = p.aggs[a];
-                        if (g.kind == MBC_AGG_COUNT) { acc[a] += 1ull; continue; }
-                        const uint32_t bits = g.staged >= 0 ? stage[g.staged * kTileRows + warp * kWarpRows + r]
-                                                            : __ldg(reinterpret_cast<const uint32_t*>(g.src) + row);
+                        if (g.kind == MBC_AGG_COUNT) continue;     // the tile total is the count
+                        const uint32_t* src = g.staged >= 0 ? stage + g.staged * kTileRows
+                                                            : reinterpret_cast<const uint32_t*>(g.src) + tile_row0;
+                        unsigned long long v;
                         if (g.type == MBC_ATTR_INTEGER) {
-                            const long long x = (long long)(int32_t)bits, cur = (long long)acc[a];
-                            acc[a] = (unsigned long long)(g.kind == MBC_AGG_SUM ? cur + x : g.kind == MBC_AGG_MIN ? min(cur, x) : max(cur, x));
-                        } else {
-                            const double x = (double)__uint_as_float(bits), cur = __longlong_as_double((long long)acc[a]);
-                            const double nv = g.kind == MBC_AGG_SUM ? cur + x : g.kind == MBC_AGG_MIN ? fmin(cur, x) : fmax(cur, x);
-                            acc[a] = (unsigned long long)__double_as_longlong(nv);
-                        }
-                    }
-                }
-            }
-            // per-warp partial of every aggregate (fixed lane order -> reproducible)
+                            long long acc = (long long)agg_identity(g);
+                            for (int k = wtid; k < T; k += kScanThreads)
+                                acc = agg_combine<long long>(g.kind, acc, (long long)(int32_t)src[list[k]]);
 #pragma unroll
-            for (int a = 0; a < kMaxAgg; ++a) {
-                if (a < p.nagg) {
-                    const DevAgg& g = p.aggs[a];
-                    const bool integral = g.kind == MBC_AGG_COUNT || g.type == MBC_ATTR_INTEGER;
-                    const bool additive = g.kind == MBC_AGG_COUNT || g.kind == MBC_AGG_SUM;
-                    unsigned long long v = acc[a];
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) {
-                        unsigned long long y = __shfl_xor_sync(0xFFFFFFFFu, v, o);
-                        if (integral) {
-                            long long x1 = (long long)v, x2 = (long long)y;
-                            v = (unsigned long long)(additive ? x1 + x2 : g.kind == MBC_AGG_MIN ? min(x1, x2) : max(x1, x2));
+                            for (int o = 16; o > 0; o >>= 1) acc = agg_combine<long long>(g.kind, acc, __shfl_xor_sync(0xFFFFFFFFu, acc, o));
+                            v = (unsigned long long)acc;
                         } else {
-                            double x1 = __longlong_as_double((long long)v), x2 = __longlong_as_double((long long)y);
-                            v = (unsigned long long)__double_as_longlong(additive ? x1 + x2 : g.kind == MBC_AGG_MIN ? fmin(x1, x2) : fmax(x1, x2));
+                            double acc = __longlong_as_double((long long)agg_identity(g));
+                            for (int k = wtid; k < T; k += kScanThreads)
+                                acc = agg_combine<double>(g.kind, acc, (double)__uint_as_float(src[list[k]]));
+#pragma unroll
+                            for (int o = 16; o > 0; o >>= 1) acc = agg_combine<double>(g.kind, acc, __shfl_xor_sync(0xFFFFFFFFu, acc, o));
+                            v = (unsigned long long)__double_as_longlong(acc);
                         }
+                        if (lane == 0) s_aggw[a][wwarp] = v;
                     }
-                    if (lane == 0) s_aggw[a][warp] = v;
                 }
             }
         }
-        __syncthreads();                                           // S3: tile B's slot and lists are free
+        MBC_TICK(4);
+        __syncthreads();                                           // S2: tile B's slot and list are free
+        MBC_TICK(5);
 
         if (validB) {
-            if (tid < p.nagg) {                                    // tile partial = warps in order
-                const DevAgg& g = p.aggs[tid];
-                const bool integral = g.kind == MBC_AGG_COUNT || g.type == MBC_ATTR_INTEGER;
-                const bool additive = g.kind == MBC_AGG_COUNT || g.kind == MBC_AGG_SUM;
-                unsigned long long v = s_aggw[tid][0];
-                for (int w = 1; w < kWarpsPerCta; ++w) {
-                    unsigned long long y = s_aggw[tid][w];
-                    if (integral) {
-                        long long x1 = (long long)v, x2 = (long long)y;
-                        v = (unsigned long long)(additive ? x1 + x2 : g.kind == MBC_AGG_MIN ? min(x1, x2) : max(x1, x2));
-                    } else {
-                        double x1 = __longlong_as_double((long long)v), x2 = __longlong_as_double((long long)y);
-                        v = (unsigned long long)__double_as_longlong(additive ? x1 + x2 : g.kind == MBC_AGG_MIN ? fmin(x1, x2) : fmax(x1, x2));
-                    }
+            if (tid == 0 && newtile < p.ntiles) issue_tile(slotB, newtile);
+            if (!scan_warp && wtid < p.nagg && !((int)s_ttotal[bufB] > 0 && (int)s_ttotal[bufB] <= kScanThreads)) {
+                // dense (or empty) tile: tile partial = participating warps in order
+                const DevAgg& g = p.aggs[wtid];
+                const int T = (int)s_ttotal[bufB];
+                unsigned long long v;
+                if (g.kind == MBC_AGG_COUNT) {
+                    v = (unsigned long long)T;
+                } else {
+                    v = agg_identity(g);
+                    const int nw = min(kWarpsPerCta, (T + 31) / 32);
+                    for (int w = 0; w < nw; ++w) v = agg_merge(g, v, s_aggw[wtid][w]);
                 }
-                p.partials[(size_t)tid * p.total_tiles + p.tile_base + tileB] = v;
+                p.partials[(size_t)wtid * p.total_tiles + p.tile_base + tileB] = v;
             }
-            if (tid == kProducer && newtile < p.ntiles) issue_tile(slotB, newtile);
         }
         tileB = tileA;
         slotB = slotA;
         bufB = bufA;
+        if (++slotA == S) { slotA = 0; parityA ^= 1u; }
     }
+#ifdef MBC_SCAN_PROFILE
+    if (p.prof && lane == 0 && (tid == 0 || tid == 32 || tid == 64)) {
+        const int who = tid >> 5;                                  // 0 scan warp, 1 first worker warp, 2 second worker warp
+        for (int k = 0; k < 8; ++k) atomicAdd((unsigned long long*)&p.prof[who * 8 + k], (unsigned long long)_prof[k]);
+    }
+#endif
 }
 
 // Reduce the per-tile partials of one aggregate in tile order (fixed tree => reproducible sums).
