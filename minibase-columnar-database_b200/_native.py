@@ -11,7 +11,7 @@ import os
 import re
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libmbcol.so")
+LIB_PATH = os.environ.get("MBC_LIB_PATH") or os.path.join(_HERE, "csrc", "libmbcol.so")   # override: tuning variants only
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "mbcol.h")
 
 # ---- constants (mirrors of the #defines in mbcol.h) ------------------------------------------

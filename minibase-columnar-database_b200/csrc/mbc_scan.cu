@@ -80,8 +80,8 @@ int32_t build_terms(const mbc_table* t, const mbc_term* terms, int32_t nterms, D
     return MBC_OK;
 }
 
-// Choose which 4-byte predicate columns are staged through the TMA ring, the ring depth, the dynamic
-// shared memory size and the persistent grid.
+// Choose which 4-byte predicate columns are staged through the TMA ring of the filter pass, the ring
+// depth, the dynamic shared memory size and the persistent grid.
 static int32_t plan_staging(mbc_ctx* ctx, ScanParams* p, size_t* smem_bytes, int* grid) {
     p->nstaged = 0;
     auto stage_of = [&](int col) -> int {
@@ -96,39 +96,22 @@ static int32_t plan_staging(mbc_ctx* ctx, ScanParams* p, size_t* smem_bytes, int
         if (t.lhs.kind == 1) t.lhs.staged = stage_of(t.lhs.col);
         if (t.rhs.kind == 1) t.rhs.staged = stage_of(t.rhs.col);
     }
-    for (int c = 0; c < p->nproj; ++c) {
-        p->proj[c].staged = -1;
-        if (p->proj[c].stride == 4)
-            for (int s = 0; s < p->nstaged; ++s) if (p->staged_cols[s] == p->proj[c].col) p->proj[c].staged = s;
-    }
-    for (int a = 0; a < p->nagg; ++a) {
-        p->aggs[a].staged = -1;
-        for (int s = 0; s < p->nstaged; ++s) if (p->aggs[a].col >= 0 && p->staged_cols[s] == p->aggs[a].col) p->aggs[a].staged = s;
-    }
-    // columns phase B reads from HBM (prefetched into L2 one iteration ahead)
+    for (int c = 0; c < p->nproj; ++c) p->proj[c].staged = -1;
+    for (int a = 0; a < p->nagg; ++a) p->aggs[a].staged = -1;
     p->ngather = 0;
-    auto add_gather = [&](int col, int stride) {
-        for (int g = 0; g < p->ngather; ++g) if (p->gather[g].col == col) return;
-        if (p->ngather == kMaxGather) return;
-        p->gather[p->ngather].col = col;
-        p->gather[p->ngather].stride = stride;
-        p->gather[p->ngather].ptr = nullptr;
-        p->ngather++;
-    };
-    for (int c = 0; c < p->nproj; ++c) if (p->proj[c].staged < 0) add_gather(p->proj[c].col, p->proj[c].stride);
-    for (int a = 0; a < p->nagg; ++a) if (p->aggs[a].col >= 0 && p->aggs[a].staged < 0) add_gather(p->aggs[a].col, 4);
-    p->nstages = p->nstaged <= 2 ? 3 : 2;
+    // ring depth: as deep as ~100 KB of shared memory allows (two CTAs per SM), at least 2
+    p->nstages = p->nstaged == 0 ? 2 : std::max(2, std::min(kMaxStages, (int)(100 * 1024 / (p->nstaged * kStageColBytes))));
     *smem_bytes = (size_t)p->nstages * p->nstaged * kStageColBytes;
-    static size_t configured = 0;
-    if (*smem_bytes > configured) {
-        MBC_CUDA(cudaFuncSetAttribute(scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kMaxStages * kMaxStaged * kStageColBytes > 200 * 1024 ? 200 * 1024 : kMaxStages * kMaxStaged * kStageColBytes)));
-        configured = 200 * 1024;
+    static bool configured = false;
+    if (!configured) {
+        MBC_CUDA(cudaFuncSetAttribute(filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        configured = true;
     }
     int blocks_per_sm = 1;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, scan_kernel, kScanCtaThreads, *smem_bytes) != cudaSuccess || blocks_per_sm < 1)
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, filter_kernel, kScanThreads, *smem_bytes) != cudaSuccess || blocks_per_sm < 1)
         blocks_per_sm = 1;
     blocks_per_sm = std::min(blocks_per_sm, 8);
-    *grid = std::max(1, std::min(p->ntiles, ctx->sm_count * blocks_per_sm));
+    *grid = std::max(1, ctx->sm_count * blocks_per_sm);
     return MBC_OK;
 }
 
@@ -253,26 +236,28 @@ void decode_aggs(mbc_result* r, const DevAgg* dev, int nagg, const unsigned long
     }
 }
 
-// Workspace layout: [ticket:u32 @0][count:i64 @16][status: max_launch_tiles u64 @64][partials: nagg*total_tiles u64][agg out: 8 u64]
+// Workspace layout: [count:i64 @0][tile_counts: launch_tiles u32][tile_out: launch_tiles u64]
+//                   [partials: nagg*total_tiles u64][agg out: 8 u64]
 struct Workspace {
-    unsigned int* ticket;
     long long* count;
-    unsigned long long* status;
+    uint32_t* tile_counts;
+    unsigned long long* tile_out;
     unsigned long long* partials;
     unsigned long long* agg_out;
 };
 
 static int32_t carve_workspace(mbc_ctx* ctx, int64_t launch_tiles, int64_t total_tiles, int nagg, Workspace* w) {
-    size_t status_bytes = (size_t)launch_tiles * 8;
+    size_t counts_bytes = (size_t)round_up(launch_tiles * 4, 64);
+    size_t out_bytes = (size_t)launch_tiles * 8;
     size_t partial_bytes = (size_t)std::max(nagg, 1) * total_tiles * 8;
-    size_t total = 64 + status_bytes + partial_bytes + kMaxAgg * 8 + 64;
+    size_t total = 64 + counts_bytes + out_bytes + partial_bytes + kMaxAgg * 8 + 64;
     MBC_TRY(ensure_workspace(ctx, total));
     char* b = (char*)ctx->ws;
-    w->ticket = (unsigned int*)b;
-    w->count = (long long*)(b + 16);
-    w->status = (unsigned long long*)(b + 64);
-    w->partials = (unsigned long long*)(b + 64 + status_bytes);
-    w->agg_out = (unsigned long long*)(b + 64 + status_bytes + partial_bytes);
+    w->count = (long long*)b;
+    w->tile_counts = (uint32_t*)(b + 64);
+    w->tile_out = (unsigned long long*)(b + 64 + counts_bytes);
+    w->partials = (unsigned long long*)(b + 64 + counts_bytes + out_bytes);
+    w->agg_out = (unsigned long long*)(b + 64 + counts_bytes + out_bytes + partial_bytes);
     return MBC_OK;
 }
 
@@ -329,8 +314,8 @@ static int32_t prepare_job(const mbc_table* schema, const ScanRequest& rq, int64
     MBC_TRY(carve_workspace(ctx, launch_tiles, total_tiles, p.nagg, &job->w));
     job->total_tiles = total_tiles;
     p.total_tiles = (int)total_tiles;
-    p.status = job->w.status;
-    p.ticket = job->w.ticket;
+    p.tile_counts = job->w.tile_counts;
+    p.tile_out = job->w.tile_out;
     p.count = job->w.count;
     p.partials = job->w.partials;
     p.out_pos = r->d_pos;
@@ -347,7 +332,6 @@ static void bind_table(ScanJob* job, const mbc_table* t) {
     }
     for (int c = 0; c < p.nproj; ++c) p.proj[c].src = t->cols[p.proj[c].col].d;
     for (int s = 0; s < p.nstaged; ++s) p.staged_src[s] = t->cols[p.staged_cols[s]].d;
-    for (int g = 0; g < p.ngather; ++g) p.gather[g].ptr = t->cols[p.gather[g].col].d;
     for (int a = 0; a < p.nagg; ++a)
         if (p.aggs[a].col >= 0) p.aggs[a].src = t->cols[p.aggs[a].col].d;
     p.deleted = t->has_deleted ? t->d_deleted : nullptr;
@@ -356,40 +340,20 @@ static void bind_table(ScanJob* job, const mbc_table* t) {
     p.ntiles = (int)((t->nrows + kTileRows - 1) / kTileRows);
 }
 
-// one launch over the bound table; its tiles occupy [tile_base, tile_base + ntiles) of the partials
+// the three launches over the bound table; its tiles occupy [tile_base, tile_base + ntiles) of the partials
 static int32_t launch_job(ScanJob* job, int tile_base, bool first) {
     mbc_ctx* ctx = job->r->ctx;
     ScanParams& p = job->p;
     p.tile_base = tile_base;
+    if (first) MBC_CUDA(cudaMemsetAsync(p.count, 0, 8, ctx->stream));   // later launches append at the running offset
     if (p.ntiles == 0) return MBC_OK;
-    // ticket + status words are per launch; the running output offset survives between launches
-    if (first) MBC_CUDA(cudaMemsetAsync(ctx->ws, 0, 64 + (size_t)p.ntiles * 8, ctx->stream));
-    else {
-        MBC_CUDA(cudaMemsetAsync(p.ticket, 0, 4, ctx->stream));
-        MBC_CUDA(cudaMemsetAsync(p.status, 0, (size_t)p.ntiles * 8, ctx->stream));
+    filter_kernel<<<job->grid_per_tiles(p.ntiles), kScanThreads, job->smem_bytes, ctx->stream>>>(p);
+    tile_offsets_kernel<<<1, 1024, 0, ctx->stream>>>(p.tile_counts, p.ntiles, p.tile_out, p.count);
+    ctx->launches += 2;
+    if (p.out_pos || p.nproj > 0 || p.nagg > 0) {
+        write_kernel<<<p.ntiles, kScanThreads, 0, ctx->stream>>>(p);
+        ctx->launches++;
     }
-#ifdef MBC_SCAN_PROFILE
-    static long long* d_prof = nullptr;
-    if (!d_prof) cudaMalloc(&d_prof, 24 * 8);
-    cudaMemsetAsync(d_prof, 0, 24 * 8, ctx->stream);
-    p.prof = d_prof;
-#endif
-    scan_kernel<<<job->grid_per_tiles(p.ntiles), kScanCtaThreads, job->smem_bytes, ctx->stream>>>(p);
-#ifdef MBC_SCAN_PROFILE
-    {
-        long long h[24];
-        cudaMemcpyAsync(h, d_prof, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream);
-        cudaStreamSynchronize(ctx->stream);
-        const int g = job->grid_per_tiles(p.ntiles);
-        const char* names[8] = {"tma_wait", "phaseA", "S1_wait", "list/publish", "phaseB", "S2_wait", "lookback", "other"};
-        for (int who = 0; who < 3; ++who) {
-            fprintf(stderr, "[scan prof] %s: ", who == 0 ? "scan warp " : who == 1 ? "worker w0 " : "worker w1 ");
-            for (int k = 0; k < 8; ++k) fprintf(stderr, "%s=%.0fk ", names[k], (double)h[who * 8 + k] / g / 1e3);
-            fprintf(stderr, "(cycles per CTA, %d CTAs, %d tiles)\n", g, p.ntiles);
-        }
-    }
-#endif
-    ctx->launches++;
     MBC_CUDA(cudaGetLastError());
     return MBC_OK;
 }
@@ -398,7 +362,7 @@ static int32_t finish_job(ScanJob* job, int64_t tiles_done) {
     mbc_ctx* ctx = job->r->ctx;
     ScanParams& p = job->p;
     mbc_result* r = job->r;
-    if (tiles_done == 0) MBC_CUDA(cudaMemsetAsync(ctx->ws, 0, 64, ctx->stream));
+    if (tiles_done == 0) MBC_CUDA(cudaMemsetAsync(p.count, 0, 8, ctx->stream));
     if (p.nagg > 0) {
         AggList list;
         memcpy(list.g, p.aggs, sizeof(list.g));
@@ -432,11 +396,10 @@ int32_t run_scan(const ScanRequest& rq, mbc_result** out) {
         mbc_result* r = job.r;
         r->nrows = t->nrows;
         job.p.sel_bitmap = rq.d_sel_bitmap;
-        if (rq.want & MBC_WANT_BITMAP) {
-            s = dev_alloc(ctx, (void**)&r->d_bitmap, (size_t)t->words_pad * 4, true);
-            r->bitmap_words32 = t->words_pad;
-            job.p.out_bitmap = r->d_bitmap;
-        }
+        // the filter pass always leaves the selection as a bitmap; it is the result's bitmap when asked for
+        s = dev_alloc(ctx, (void**)&r->d_bitmap, (size_t)t->words_pad * 4, true);
+        r->bitmap_words32 = t->words_pad;
+        job.p.out_bitmap = r->d_bitmap;
     }
     if (s == MBC_OK) {
         bind_table(&job, t);
@@ -486,6 +449,10 @@ static int32_t run_scan_host(mbc_ctx* ctx, int32_t ncols, const mbc_coldesc* col
     s = prepare_job(stage[0], rq, nrows, tiles_per_chunk, tiles_per_chunk * nchunks, &job);
     if (s != MBC_OK) { if (job.r) mbc_result_free(job.r); cleanup(); return s; }
     job.r->nrows = nrows;
+    // per-chunk selection bitmap of the filter pass (scratch: the chunks reuse it in stream order)
+    s = dev_alloc(ctx, (void**)&job.r->d_bitmap, (size_t)stage[0]->words_pad * 4, true);
+    if (s != MBC_OK) { mbc_result_free(job.r); cleanup(); return s; }
+    job.p.out_bitmap = job.r->d_bitmap;
 
     // which columns does the query touch?
     std::vector<char> used(ncols, 0);

@@ -16,10 +16,11 @@
 //     the result bits are transposed into the 4-rows-per-lane layout with warp ballots;
 //   * the CNF is a small term program in the kernel parameters; the operator/type switch runs once
 //     per term per 16 rows, the compares themselves are straight-line;
-//   * survivors are counted with one packed warp scan (four 8-bit unit counters in one register),
-//     a CTA scan over 8 warp totals, and a decoupled look-back over per-tile status words, so the
-//     output is written in ascending position order in a single pass (the reference emits rows in
-//     position order; bit-exact position lists need order, not atomics);
+//   * the filter pass emits the selection bitmap (warp-shuffle assembled words) and one count per tile;
+//     a one-block scan turns the counts into output offsets; the write pass ranks the survivors of a
+//     tile with one packed warp scan (four 8-bit unit counters in one register) and a CTA scan, so
+//     the output is written in ascending position order (the reference emits rows in position order;
+//     bit-exact position lists need order, not atomics) and no CTA ever waits for another;
 //   * survivors are written with one lane per SURVIVOR (a per-warp rank->row list in shared memory):
 //     projection columns that are not predicate columns are only gathered for qualifying rows (late
 //     materialisation: at low selectivity most sectors are never read), stores are coalesced, and the
@@ -101,8 +102,8 @@ struct ScanParams {
     const uint32_t* deleted;      // optional markedDeleted bitmap
     int64_t* out_pos;
     uint32_t* out_bitmap;
-    unsigned long long* status;   // one look-back word per tile
-    unsigned int* ticket;
+    uint32_t* tile_counts;        // qualifying rows per tile (pass 1 -> pass 2)
+    unsigned long long* tile_out; // global output offset of every tile (tile_offsets_kernel)
     long long* count;             // in: running output offset, out: offset after this launch
     long long* prof;              // optional phase timers (MBC_SCAN_PROFILE builds)
     unsigned long long* partials; // [nagg][total_tiles]
@@ -295,39 +296,6 @@ __device__ __forceinline__ long long warp_sum_i64(long long v) {
     return v;
 }
 
-constexpr unsigned long long kFlagAgg  = 1ull << 62;
-constexpr unsigned long long kFlagIncl = 2ull << 62;
-constexpr unsigned long long kValMask  = (1ull << 62) - 1;
-
-// Decoupled look-back (single-pass chained scan) executed by warp 0.  Tiles are handed out through
-// an atomic ticket, so every predecessor of a running tile is itself running or finished.
-__device__ __forceinline__ long long lookback(volatile unsigned long long* status, int tile, long long total,
-                                               long long init, int lane) {
-    if (tile == 0) {
-        if (lane == 0) status[0] = kFlagIncl | (unsigned long long)(init + total);
-        return init;
-    }
-    if (lane == 0) status[tile] = kFlagAgg | (unsigned long long)total;
-    long long prefix = 0;
-    int idx = tile - 1 - lane;
-    while (true) {
-        unsigned long long s = kFlagIncl;          // tiles before tile 0: inclusive, value 0
-        if (idx >= 0) {
-            do { s = status[idx]; } while ((s >> 62) == 0);
-        }
-        uint32_t incl = __ballot_sync(0xFFFFFFFFu, (s >> 62) == 2);
-        if (incl) {
-            int first = __ffs(incl) - 1;           // nearest tile with an inclusive prefix
-            prefix += warp_sum_i64(lane <= first ? (long long)(s & kValMask) : 0ll);
-            break;
-        }
-        prefix += warp_sum_i64((long long)(s & kValMask));
-        idx -= 32;
-    }
-    if (lane == 0) status[tile] = kFlagIncl | (unsigned long long)(prefix + total);
-    return prefix;
-}
-
 // ---- TMA bulk copy + mbarrier (sm_90+/sm_100a) -----------------------------------------------------
 
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
@@ -362,80 +330,22 @@ __device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gmem_sr
                  : "memory");
 }
 
-// ---- the kernel ------------------------------------------------------------------------------
+// ---- the kernels --------------------------------------------------------------------------------
 //
-// Persistent CTAs: kWarpsPerCta worker warps (512 rows each of a tile) + one scan warp.  Each CTA keeps a
-// ring of tile slots; for every claimed tile one worker thread issues one TMA bulk copy per staged
-// predicate column, so the copies of the next tiles are in flight while the current tile is evaluated:
-// HBM latency is hidden by the ring depth, not by occupancy.  One loop iteration `it` handles the newest
-// tile A and the previous tile B:
-//     workers   : phase A of tile A (mask from shared memory, packed warp scan -> warp totals)
-//   -- barrier 0 (all warps) --
-//     scan warp : tile total of A, publish its aggregate, run the wide decoupled look-back, leave A's global
-//                 output offset in shared memory.  It has a whole iteration for this: nobody waits for it
-//                 before barrier 0 of iteration it+1.
-//     workers   : write A's survivors (row-in-tile, by tile rank) into a shared list and prefetch the HBM
-//                 sectors phase B will gather; then phase B of tile B with ONE THREAD PER SURVIVOR: position,
-//                 projected values (staged columns from shared memory, the others gathered from HBM in
-//                 batches) and aggregate partials.  Warps without survivors skip; stores are coalesced.
-//   -- barrier 1 (workers only) --   tile B's slot is free: worker 0 claims the next tile and refills it.
+// The scan is two streaming passes with no dependency between CTAs (a single-pass version with a
+// decoupled look-back was built first and measured: with ~300 persistent CTAs in flight on a B200 the
+// look-back chain became a grid-wide barrier per wave of tiles and capped the low-selectivity case at
+// ~1 TB/s; see DESIGN.md "What was tried").
+//
+//   filter_kernel   persistent CTAs, static tile assignment, ring of TMA-staged predicate columns:
+//                   evaluates the CNF, emits the selection bitmap (BitSet order) and one count per tile.
+//   tile_offsets_kernel  one block: exclusive scan of the tile counts -> global output offset of
+//                   every tile (added to the running count, which is how chunked scans append).
+//   write_kernel    one CTA per tile: ranks from the bitmap, rank->row list in shared memory, then
+//                   one thread per SURVIVOR writes position / projected values and folds aggregates.
 
 constexpr int kMaxStages = 4;
-
-// Optional phase timers (-DMBC_SCAN_PROFILE): per-phase clock64 sums of one worker warp / the scan warp,
-// accumulated into p.prof[8] by lane 0.  Off in the product build.
-#ifdef MBC_SCAN_PROFILE
-#define MBC_T0() long long _t0 = clock64()
-#define MBC_TICK(slot) do { long long _t1 = clock64(); _prof[slot] += _t1 - _t0; _t0 = _t1; } while (0)
-#else
-#define MBC_T0() do {} while (0)
-#define MBC_TICK(slot) do {} while (0)
-#endif
-constexpr int kScanCtaThreads = kScanThreads + 32;                 // worker warps + the scan warp
 constexpr int kGatherBatch = 4;
-constexpr int kScanMinCtas = kWarpsPerCta >= 8 ? 2 : kWarpsPerCta >= 4 ? 3 : 6;
-constexpr int kLookPerLane = 8;                                    // look-back window = 256 tiles per round
-
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
-
-// Decoupled look-back with a 256-tile window per round: with ~300 tiles in flight on a B200 the nearest
-// tile that already knows its inclusive prefix is usually more than 32 tiles back.
-__device__ __forceinline__ long long lookback_wide(volatile unsigned long long* status, int tile, long long total, long long init,
-                                                    int lane) {
-    if (tile == 0) {
-        if (lane == 0) status[0] = kFlagIncl | (unsigned long long)(init + total);
-        return init;
-    }
-    long long prefix = 0;
-    int hi = tile - 1 - lane * kLookPerLane;                      // nearest predecessor this lane inspects
-    while (true) {
-        unsigned long long s[kLookPerLane];
-#pragma unroll
-        for (int j = 0; j < kLookPerLane; ++j) s[j] = (hi - j) >= 0 ? status[hi - j] : (2ull << 62);   // before tile 0: inclusive 0
-        bool found = false, invalid = false;
-        long long sum = 0;
-#pragma unroll
-        for (int j = 0; j < kLookPerLane; ++j) {
-            if (!found && !invalid) {
-                const unsigned long long f = s[j] >> 62;
-                if (f == 0) invalid = true;
-                else { sum += (long long)(s[j] & kValMask); found = (f == 2); }
-            }
-        }
-        const uint32_t fmask = __ballot_sync(0xFFFFFFFFu, found);
-        const uint32_t imask = __ballot_sync(0xFFFFFFFFu, invalid);
-        const int first = fmask ? __ffs(fmask) - 1 : 31;          // nearest lane that reached an inclusive prefix
-        const uint32_t relevant = first >= 31 ? 0xFFFFFFFFu : ((1u << (first + 1)) - 1u);
-        if (imask & relevant) continue;                            // a needed predecessor has not published yet: reload
-        prefix += warp_sum_i64(lane <= first ? sum : 0ll);
-        if (fmask) break;
-        hi -= 32 * kLookPerLane;
-    }
-    if (lane == 0) status[tile] = kFlagIncl | (unsigned long long)(prefix + total);
-    return prefix;
-}
 
 template <typename T>
 __device__ __forceinline__ T agg_combine(int kind, T a, T b) {
@@ -455,26 +365,19 @@ __device__ __forceinline__ unsigned long long agg_merge(const DevAgg& g, unsigne
     return (unsigned long long)__double_as_longlong(agg_combine<double>(g.kind, __longlong_as_double((long long)a), __longlong_as_double((long long)b)));
 }
 
-__global__ void __launch_bounds__(kScanCtaThreads, kScanMinCtas) scan_kernel(const __grid_constant__ ScanParams p) {
+// ---- pass 1: CNF -> selection bitmap + tile counts ------------------------------------------------------
+__global__ void __launch_bounds__(kScanThreads, 2) filter_kernel(const __grid_constant__ ScanParams p) {
     extern __shared__ __align__(128) uint8_t stage_mem[];          // [nstages][nstaged][kTileRows] uint32
     __shared__ __align__(8) uint64_t s_full[kMaxStages];
-    __shared__ int s_tileq[kMaxStages];
-    __shared__ uint16_t s_list[2][kTileRows];                      // survivor rows within the tile, by tile rank
-    __shared__ uint32_t s_wtot[2][kWarpsPerCta];
-    __shared__ long long s_ttotal[2];
-    __shared__ long long s_tbase;
-    __shared__ unsigned long long s_aggw[kMaxAgg][kWarpsPerCta];
+    __shared__ uint32_t s_wcnt[kWarpsPerCta];
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
-    const bool scan_warp = tid < 32;
-    const int wwarp = (tid >> 5) - 1;                              // worker warp 0..7 (-1 for the scan warp)
-    const int wtid = tid - 32;                                     // worker thread 0..255
+    const int warp = tid >> 5;
     const int S = p.nstages;
     const uint32_t stage_bytes = (uint32_t)p.nstaged * kStageColBytes;
 
     auto issue_tile = [&](int slot, int tile) {                    // one elected thread
-        if (p.nstaged == 0) return;
         mbar_arrive_expect_tx(&s_full[slot], stage_bytes);
         for (int c = 0; c < p.nstaged; ++c)
             tma_bulk_g2s(stage_mem + (size_t)slot * stage_bytes + (size_t)c * kStageColBytes,
@@ -482,335 +385,289 @@ __global__ void __launch_bounds__(kScanCtaThreads, kScanMinCtas) scan_kernel(con
                          &s_full[slot]);
     };
 
-    if (tid == 0) {
+    if (tid == 0 && p.nstaged) {
         for (int s = 0; s < S; ++s) mbar_init(&s_full[s], 1);
         mbar_fence_init();
         for (int s = 0; s < S; ++s) {
-            int t = (int)atomicAdd(p.ticket, 1u);
-            s_tileq[s] = t;
-            if (t < p.ntiles) issue_tile(s, t);
+            const long long t = (long long)blockIdx.x + (long long)s * gridDim.x;
+            if (t < p.ntiles) issue_tile(s, (int)t);
         }
     }
     __syncthreads();
 
-#ifdef MBC_SCAN_PROFILE
-    long long _prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-#endif
-    MBC_T0();
-    int tileB = INT32_MAX, slotB = 0, bufB = 0, newtile = INT32_MAX;
-    int slotA = 0;
-    uint32_t parityA = 0;                                          // flips every time the ring wraps
-    for (int it = 0;; ++it) {
-        const int bufA = it & 1;
-        const int tileA = s_tileq[slotA];
-        const bool validA = tileA < p.ntiles, validB = tileB < p.ntiles;
-        if (!validA && !validB) break;
+    int slot = 0;
+    uint32_t parity = 0;
+    for (long long tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+        if (p.nstaged) mbar_wait(&s_full[slot], parity);
+        const uint32_t* stage = reinterpret_cast<const uint32_t*>(stage_mem + (size_t)slot * stage_bytes);
+        const int64_t warp_row0 = (int64_t)tile * kTileRows + warp * kWarpRows;
+        const int64_t thread_row0 = warp_row0 + lane * kVec;
+        const int tile_off = warp * kWarpRows + lane * kVec;       // this thread's first row within the tile
 
-        uint32_t mask = 0, excl = 0, unit_off1 = 0, unit_off2 = 0, unit_off3 = 0;
-        if (scan_warp) {
-            // ---- look-back of the previous tile, overlapped with the workers' phase A ----
-            if (validB) {
-                const long long total = s_ttotal[bufB];
-                long long init = 0;
-                if (tileB == 0) init = *p.count;
-                MBC_TICK(7);
-                const long long prefix = lookback_wide(p.status, tileB, total, init, lane);
-                MBC_TICK(6);
-                if (lane == 0) {
-                    s_tbase = prefix;
-                    if (tileB == p.ntiles - 1) *p.count = prefix + total;
-                    newtile = (int)atomicAdd(p.ticket, 1u);        // next tile for the slot tile B is about to free
-                }
-            }
-        } else if (validA) {
-            // =========================== phase A: newest tile ===========================
-            MBC_TICK(7);
-            if (p.nstaged) mbar_wait(&s_full[slotA], parityA);
-            MBC_TICK(0);
-            const uint32_t* stage = reinterpret_cast<const uint32_t*>(stage_mem + (size_t)slotA * stage_bytes);
-            const int64_t warp_row0 = (int64_t)tileA * kTileRows + wwarp * kWarpRows;
-            const int64_t thread_row0 = warp_row0 + lane * kVec;
-            const int tile_off = wwarp * kWarpRows + lane * kVec;  // this thread's first row within the tile
-
-            mask = 0xFFFFu;
-            if (p.sel_bitmap) mask &= load_bits(p.sel_bitmap, warp_row0, lane);
-            if (p.nterms > 0) {
-                uint32_t acc = 0;
-                for (int k = 0; k < p.nterms; ++k) {               // warp-uniform term program
-                    const DevTerm& t = p.terms[k];
-                    acc |= (t.cmp_type == MBC_ATTR_STRING) ? eval_term_str(t, warp_row0, lane)
-                                                           : eval_term32(t, thread_row0, stage, tile_off);
-                    if (t.end_conj) { mask &= acc; acc = 0; }      // OR inside, AND across (PredEval.java:164-176)
-                }
-            }
-            if (p.deleted) mask &= ~load_bits(p.deleted, warp_row0, lane);   // TupleScan.java:85
-            if (warp_row0 + kWarpRows > p.nrows) {                 // rows past the end of the table
-#pragma unroll
-                for (int u = 0; u < kUnits; ++u)
-#pragma unroll
-                    for (int j = 0; j < kVec; ++j)
-                        if (thread_row0 + u * kUnitRows + j >= p.nrows) mask &= ~(1u << (u * 4 + j));
-            }
-            // ranks: one packed warp scan of the four unit counters (each total <= 128 fits 8 bits)
-            const uint32_t packed = __popc(mask & 0xFu) | (__popc(mask & 0xF0u) << 8) | (__popc(mask & 0xF00u) << 16) |
-                                    (__popc(mask & 0xF000u) << 24);
-            uint32_t incl = packed;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                uint32_t n = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-                if (lane >= o) incl += n;
-            }
-            const uint32_t tot = __shfl_sync(0xFFFFFFFFu, incl, 31);
-            excl = incl - packed;
-            unit_off1 = tot & 0xFFu;
-            unit_off2 = unit_off1 + ((tot >> 8) & 0xFFu);
-            unit_off3 = unit_off2 + ((tot >> 16) & 0xFFu);
-            if (lane == 0) s_wtot[bufA][wwarp] = unit_off3 + (tot >> 24);
-            if (p.out_bitmap) {                                    // BitSet-compatible: bit p = word p/32, bit p%32
-#pragma unroll
-                for (int u = 0; u < kUnits; ++u) {
-                    uint32_t w = ((mask >> (u * 4)) & 0xFu) << ((lane & 7) * 4);
-                    w |= __shfl_xor_sync(0xFFFFFFFFu, w, 1);
-                    w |= __shfl_xor_sync(0xFFFFFFFFu, w, 2);
-                    w |= __shfl_xor_sync(0xFFFFFFFFu, w, 4);
-                    if ((lane & 7) == 0) p.out_bitmap[(warp_row0 >> 5) + u * (kUnitRows / 32) + (lane >> 3)] = w;
-                }
+        uint32_t mask = 0xFFFFu;
+        if (p.sel_bitmap) mask &= load_bits(p.sel_bitmap, warp_row0, lane);
+        if (p.nterms > 0) {
+            uint32_t acc = 0;
+            for (int k = 0; k < p.nterms; ++k) {                   // warp-uniform term program
+                const DevTerm& t = p.terms[k];
+                acc |= (t.cmp_type == MBC_ATTR_STRING) ? eval_term_str(t, warp_row0, lane)
+                                                       : eval_term32(t, thread_row0, stage, tile_off);
+                if (t.end_conj) { mask &= acc; acc = 0; }          // OR inside, AND across (PredEval.java:164-176)
             }
         }
-        MBC_TICK(1);
-        __syncthreads();                                           // S1: warp totals of A, prefix of B
-        MBC_TICK(2);
+        if (p.deleted) mask &= ~load_bits(p.deleted, warp_row0, lane);   // TupleScan.java:85
+        if (warp_row0 + kWarpRows > p.nrows) {                     // rows past the end of the table
+#pragma unroll
+            for (int u = 0; u < kUnits; ++u)
+#pragma unroll
+                for (int j = 0; j < kVec; ++j)
+                    if (thread_row0 + u * kUnitRows + j >= p.nrows) mask &= ~(1u << (u * 4 + j));
+        }
+        // selection bitmap, java.util.BitSet order: bit p = word p/32, bit p%32
+#pragma unroll
+        for (int u = 0; u < kUnits; ++u) {
+            uint32_t w = ((mask >> (u * 4)) & 0xFu) << ((lane & 7) * 4);
+            w |= __shfl_xor_sync(0xFFFFFFFFu, w, 1);
+            w |= __shfl_xor_sync(0xFFFFFFFFu, w, 2);
+            w |= __shfl_xor_sync(0xFFFFFFFFu, w, 4);
+            if ((lane & 7) == 0) p.out_bitmap[(warp_row0 >> 5) + u * (kUnitRows / 32) + (lane >> 3)] = w;
+        }
+        const uint32_t wcnt = __reduce_add_sync(0xFFFFFFFFu, (uint32_t)__popc(mask));
+        if (lane == 0) s_wcnt[warp] = wcnt;
+        __syncthreads();                                           // every warp is done with the slot
+        if (tid == 0) {
+            uint32_t c = 0;
+#pragma unroll
+            for (int w = 0; w < kWarpsPerCta; ++w) c += s_wcnt[w];
+            p.tile_counts[tile] = c;
+            const long long next = tile + (long long)S * gridDim.x;
+            if (p.nstaged && next < p.ntiles) issue_tile(slot, (int)next);
+        }
+        if (++slot == S) { slot = 0; parity ^= 1u; }
+        // s_wcnt is rewritten only after the next iteration's work, which ends in the barrier above
+    }
+}
 
-        if (scan_warp) {
-            if (lane == 0 && validB) s_tileq[slotB] = newtile;
-            if (validA) {                                          // publish the newest tile's aggregate
-                uint32_t v = lane < kWarpsPerCta ? s_wtot[bufA][lane] : 0u;
+// ---- pass 1.5: tile counts -> tile output offsets -----------------------------------------------------------
+__global__ void __launch_bounds__(1024) tile_offsets_kernel(const uint32_t* counts, int ntiles, unsigned long long* tile_base,
+                                                            long long* running /* in: offset so far, out: + total */) {
+    __shared__ unsigned long long sh[1024];
+    const int per = (ntiles + 1023) / 1024;
+    const int lo = min(ntiles, (int)threadIdx.x * per), hi = min(ntiles, lo + per);
+    unsigned long long s = 0;
+    for (int i = lo; i < hi; ++i) s += counts[i];
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+        unsigned long long t = threadIdx.x >= o ? sh[threadIdx.x - o] : 0;
+        __syncthreads();
+        sh[threadIdx.x] += t;
+        __syncthreads();
+    }
+    const unsigned long long start = (unsigned long long)*running;
+    unsigned long long run = start + sh[threadIdx.x] - s;
+    for (int i = lo; i < hi; ++i) {
+        tile_base[i] = run;
+        run += counts[i];
+    }
+    __syncthreads();
+    if (threadIdx.x == 1023) *running = (long long)(start + sh[1023]);
+}
+
+// ---- pass 2: ordered write of the survivors ----------------------------------------------------------------------
+__global__ void __launch_bounds__(kScanThreads, 4) write_kernel(const __grid_constant__ ScanParams p) {
+    __shared__ uint16_t s_list[kTileRows];                         // survivor rows within the tile, by tile rank
+    __shared__ uint32_t s_wtot[kWarpsPerCta];
+    __shared__ unsigned long long s_aggw[kMaxAgg][kWarpsPerCta];
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    const int tile = blockIdx.x;
+    const int T = (int)p.tile_counts[tile];
+    if (T == 0) {                                                  // block-uniform: nothing qualifies in this tile
+        if (tid < p.nagg) p.partials[(size_t)tid * p.total_tiles + p.tile_base + tile] = agg_identity(p.aggs[tid]);
+        return;
+    }
+    const long long base = (long long)p.tile_out[tile];
+    const int64_t tile_row0 = (int64_t)tile * kTileRows;
+
+    // ranks from the bitmap: same 16-rows-per-thread layout as the filter pass
+    {
+        const int64_t warp_row0 = tile_row0 + warp * kWarpRows;
+        const uint32_t mask = load_bits(p.out_bitmap, warp_row0, lane);
+        const uint32_t packed = __popc(mask & 0xFu) | (__popc(mask & 0xF0u) << 8) | (__popc(mask & 0xF00u) << 16) |
+                                (__popc(mask & 0xF000u) << 24);
+        uint32_t incl = packed;
 #pragma unroll
-                for (int o = 4; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
-                if (lane == 0) {
-                    s_ttotal[bufA] = (long long)v;
-                    if (tileA > 0) p.status[tileA] = kFlagAgg | (unsigned long long)v;
-                }
-            }
-        } else {
-            if (validA) {
-                // tile rank of this warp's first survivor = totals of the warps before it
-                const uint32_t mine = s_wtot[bufA][wwarp];
-                uint32_t wbase = (lane < wwarp) ? s_wtot[bufA][lane & (kWarpsPerCta - 1)] : 0u;
-                wbase += __shfl_xor_sync(0xFFFFFFFFu, wbase, 1);
-                wbase += __shfl_xor_sync(0xFFFFFFFFu, wbase, 2);
-                wbase += __shfl_xor_sync(0xFFFFFFFFu, wbase, 4);
-                wbase = __shfl_sync(0xFFFFFFFFu, wbase, 0);
-                if (mask) {
-                    uint16_t* list = s_list[bufA] + wbase;
-                    const uint32_t uoff[kUnits] = {0u, unit_off1, unit_off2, unit_off3};
-                    const int64_t row0 = (int64_t)tileA * kTileRows + wwarp * kWarpRows + lane * kVec;
-                    const bool sparse = mine <= kWarpRows / 4;         // dense tiles stream anyway: no prefetch
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t n = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if (lane >= o) incl += n;
+        }
+        const uint32_t tot = __shfl_sync(0xFFFFFFFFu, incl, 31);  // per-unit totals, each <= 128
+        const uint32_t excl = incl - packed;
+        uint32_t uoff[kUnits];
+        uoff[0] = 0;
+        uoff[1] = tot & 0xFFu;
+        uoff[2] = uoff[1] + ((tot >> 8) & 0xFFu);
+        uoff[3] = uoff[2] + ((tot >> 16) & 0xFFu);
+        if (lane == 0) s_wtot[warp] = uoff[3] + (tot >> 24);
+        __syncthreads();
+        uint32_t wbase = (lane < warp) ? s_wtot[lane & (kWarpsPerCta - 1)] : 0u;
+        wbase += __shfl_xor_sync(0xFFFFFFFFu, wbase, 1);
+        wbase += __shfl_xor_sync(0xFFFFFFFFu, wbase, 2);
+        wbase += __shfl_xor_sync(0xFFFFFFFFu, wbase, 4);
+        wbase = __shfl_sync(0xFFFFFFFFu, wbase, 0);
+        if (mask) {
+            uint16_t* list = s_list + wbase;
 #pragma unroll
-                    for (int u = 0; u < kUnits; ++u) {
-                        uint32_t nib = (mask >> (u * 4)) & 0xFu;
-                        if (nib) {
-                            uint32_t r = uoff[u] + ((excl >> (8 * u)) & 0xFFu);
+            for (int u = 0; u < kUnits; ++u) {
+                uint32_t nib = (mask >> (u * 4)) & 0xFu;
+                uint32_t r = uoff[u] + ((excl >> (8 * u)) & 0xFFu);
 #pragma unroll
-                            for (int j = 0; j < kVec; ++j)
-                                if ((nib >> j) & 1u) list[r++] = (uint16_t)(wwarp * kWarpRows + u * kUnitRows + lane * kVec + j);
-                            // phase B gathers these rows one iteration from now: pull their sectors into L2 today
-                            if (sparse) {
-                                for (int g = 0; g < p.ngather; ++g) {
-                                    const char* base = reinterpret_cast<const char*>(p.gather[g].ptr) + (row0 + u * kUnitRows) * p.gather[g].stride;
-                                    if (p.gather[g].stride <= 8) {
-                                        prefetch_l2(base);                               // 4 rows share one sector
-                                    } else {
-#pragma unroll
-                                        for (int j = 0; j < kVec; ++j)
-                                            if ((nib >> j) & 1u) prefetch_l2(base + j * p.gather[g].stride);
-                                    }
-                                }
-                            }
-                        }
-                    }
-                }
-            }
-            MBC_TICK(3);
-            // =========================== phase B: previous tile, one thread per survivor ===========================
-            if (validB) {
-                const int T = (int)s_ttotal[bufB];
-                if (T > 0 && T <= kScanThreads) {
-                    // sparse tile: one work item (positions / one projected column / one aggregate) per warp, so the
-                    // dependent load->store chains of the columns run side by side instead of back to back
-                    const uint32_t* stage = reinterpret_cast<const uint32_t*>(stage_mem + (size_t)slotB * stage_bytes);
-                    const long long base = s_tbase;
-                    const int64_t tile_row0 = (int64_t)tileB * kTileRows;
-                    const uint16_t* list = s_list[bufB];
-                    const int nitems = 1 + p.nproj + p.nagg;
-                    for (int item = wwarp; item < nitems; item += kWarpsPerCta) {
-                        if (item == 0) {
-                            if (p.out_pos)
-                                for (int k = lane; k < T; k += 32) p.out_pos[base + k] = p.pos_base + tile_row0 + list[k];
-                        } else if (item <= p.nproj) {
-                            const DevProj& pr = p.proj[item - 1];
-                            if (pr.stride == 4) {
-                                uint32_t* dst = reinterpret_cast<uint32_t*>(pr.dst) + base;
-                                const uint32_t* src = pr.staged >= 0 ? stage + pr.staged * kTileRows
-                                                                     : reinterpret_cast<const uint32_t*>(pr.src) + tile_row0;
-                                for (int k = lane; k < T; k += 32) dst[k] = src[list[k]];
-                            } else if (pr.stride == 16) {
-                                const uint4* src = reinterpret_cast<const uint4*>(pr.src) + tile_row0;
-                                uint4* dst = reinterpret_cast<uint4*>(pr.dst) + base;
-                                for (int k = lane; k < T; k += 32) dst[k] = __ldg(src + list[k]);
-                            } else {
-                                const int words = pr.stride >> 2;
-                                for (int k = lane; k < T; k += 32) {
-                                    const uint32_t* src = reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(pr.src) +
-                                                                                            (tile_row0 + list[k]) * pr.stride);
-                                    uint32_t* dst = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(pr.dst) + (base + k) * pr.stride);
-                                    for (int q = 0; q < words; ++q) dst[q] = __ldg(src + q);
-                                }
-                            }
-                        } else {
-                            const int a = item - 1 - p.nproj;
-                            const DevAgg& g = p.aggs[a];
-                            unsigned long long v;
-                            if (g.kind == MBC_AGG_COUNT) {
-                                v = (unsigned long long)T;
-                            } else {
-                                const uint32_t* src = g.staged >= 0 ? stage + g.staged * kTileRows
-                                                                    : reinterpret_cast<const uint32_t*>(g.src) + tile_row0;
-                                if (g.type == MBC_ATTR_INTEGER) {
-                                    long long acc = (long long)agg_identity(g);
-                                    for (int k = lane; k < T; k += 32) acc = agg_combine<long long>(g.kind, acc, (long long)(int32_t)src[list[k]]);
-#pragma unroll
-                                    for (int o = 16; o > 0; o >>= 1) acc = agg_combine<long long>(g.kind, acc, __shfl_xor_sync(0xFFFFFFFFu, acc, o));
-                                    v = (unsigned long long)acc;
-                                } else {
-                                    // same association as the dense path: lane partials in survivor order, then the butterfly
-                                    double acc = __longlong_as_double((long long)agg_identity(g));
-                                    for (int k = lane; k < T; k += 32) acc = agg_combine<double>(g.kind, acc, (double)__uint_as_float(src[list[k]]));
-#pragma unroll
-                                    for (int o = 16; o > 0; o >>= 1) acc = agg_combine<double>(g.kind, acc, __shfl_xor_sync(0xFFFFFFFFu, acc, o));
-                                    v = (unsigned long long)__double_as_longlong(acc);
-                                }
-                            }
-                            if (lane == 0) p.partials[(size_t)a * p.total_tiles + p.tile_base + tileB] = v;
-                        }
-                    }
-                } else
-                if (wwarp * 32 < T) {                              // warp-uniform: warps without survivors skip
-                    const uint32_t* stage = reinterpret_cast<const uint32_t*>(stage_mem + (size_t)slotB * stage_bytes);
-                    const long long base = s_tbase;
-                    const int64_t tile_row0 = (int64_t)tileB * kTileRows;
-                    const uint16_t* list = s_list[bufB];
-                    if (p.out_pos) {
-                        for (int k = wtid; k < T; k += kScanThreads) p.out_pos[base + k] = p.pos_base + tile_row0 + list[k];
-                    }
-                    for (int c = 0; c < p.nproj; ++c) {            // iterator/Projection.java:103-144
-                        const DevProj& pr = p.proj[c];
-                        if (pr.stride == 4) {
-                            uint32_t* dst = reinterpret_cast<uint32_t*>(pr.dst) + base;
-                            if (pr.staged >= 0) {
-                                const uint32_t* src = stage + pr.staged * kTileRows;
-                                for (int k = wtid; k < T; k += kScanThreads) dst[k] = src[list[k]];
-                            } else {
-                                const uint32_t* src = reinterpret_cast<const uint32_t*>(pr.src) + tile_row0;
-                                for (int k0 = wtid; k0 < T; k0 += kScanThreads * kGatherBatch) {
-                                    uint32_t v[kGatherBatch];
-#pragma unroll
-                                    for (int b = 0; b < kGatherBatch; ++b) {
-                                        int k = k0 + b * kScanThreads;
-                                        if (k < T) v[b] = __ldg(src + list[k]);
-                                    }
-#pragma unroll
-                                    for (int b = 0; b < kGatherBatch; ++b) {
-                                        int k = k0 + b * kScanThreads;
-                                        if (k < T) dst[k] = v[b];
-                                    }
-                                }
-                            }
-                        } else if (pr.stride == 16) {
-                            const uint4* src = reinterpret_cast<const uint4*>(pr.src) + tile_row0;
-                            uint4* dst = reinterpret_cast<uint4*>(pr.dst) + base;
-                            for (int k0 = wtid; k0 < T; k0 += kScanThreads * kGatherBatch) {
-                                uint4 v[kGatherBatch];
-#pragma unroll
-                                for (int b = 0; b < kGatherBatch; ++b) {
-                                    int k = k0 + b * kScanThreads;
-                                    if (k < T) v[b] = __ldg(src + list[k]);
-                                }
-#pragma unroll
-                                for (int b = 0; b < kGatherBatch; ++b) {
-                                    int k = k0 + b * kScanThreads;
-                                    if (k < T) dst[k] = v[b];
-                                }
-                            }
-                        } else {
-                            const int words = pr.stride >> 2;
-                            for (int k = wtid; k < T; k += kScanThreads) {
-                                const uint32_t* src = reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(pr.src) +
-                                                                                        (tile_row0 + list[k]) * pr.stride);
-                                uint32_t* dst = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(pr.dst) + (base + k) * pr.stride);
-                                for (int q = 0; q < words; ++q) dst[q] = __ldg(src + q);
-                            }
-                        }
-                    }
-                    // aggregates: per-thread fold over its survivors, then one butterfly per participating warp
-                    for (int a = 0; a < p.nagg; ++a) {
-                        const DevAgg& g = p.aggs[a];
-                        if (g.kind == MBC_AGG_COUNT) continue;     // the tile total is the count
-                        const uint32_t* src = g.staged >= 0 ? stage + g.staged * kTileRows
-                                                            : reinterpret_cast<const uint32_t*>(g.src) + tile_row0;
-                        unsigned long long v;
-                        if (g.type == MBC_ATTR_INTEGER) {
-                            long long acc = (long long)agg_identity(g);
-                            for (int k = wtid; k < T; k += kScanThreads)
-                                acc = agg_combine<long long>(g.kind, acc, (long long)(int32_t)src[list[k]]);
-#pragma unroll
-                            for (int o = 16; o > 0; o >>= 1) acc = agg_combine<long long>(g.kind, acc, __shfl_xor_sync(0xFFFFFFFFu, acc, o));
-                            v = (unsigned long long)acc;
-                        } else {
-                            double acc = __longlong_as_double((long long)agg_identity(g));
-                            for (int k = wtid; k < T; k += kScanThreads)
-                                acc = agg_combine<double>(g.kind, acc, (double)__uint_as_float(src[list[k]]));
-#pragma unroll
-                            for (int o = 16; o > 0; o >>= 1) acc = agg_combine<double>(g.kind, acc, __shfl_xor_sync(0xFFFFFFFFu, acc, o));
-                            v = (unsigned long long)__double_as_longlong(acc);
-                        }
-                        if (lane == 0) s_aggw[a][wwarp] = v;
-                    }
-                }
+                for (int j = 0; j < kVec; ++j)
+                    if ((nib >> j) & 1u) list[r++] = (uint16_t)(warp * kWarpRows + u * kUnitRows + lane * kVec + j);
             }
         }
-        MBC_TICK(4);
-        __syncthreads();                                           // S2: tile B's slot and list are free
-        MBC_TICK(5);
+        __syncthreads();
+    }
 
-        if (validB) {
-            if (tid == 0 && newtile < p.ntiles) issue_tile(slotB, newtile);
-            if (!scan_warp && wtid < p.nagg && !((int)s_ttotal[bufB] > 0 && (int)s_ttotal[bufB] <= kScanThreads)) {
-                // dense (or empty) tile: tile partial = participating warps in order
-                const DevAgg& g = p.aggs[wtid];
-                const int T = (int)s_ttotal[bufB];
+    const uint16_t* list = s_list;
+    if (T <= kScanThreads) {
+        // sparse tile: one work item (positions / one projected column / one aggregate) per warp, so the
+        // dependent load->store chains of the columns run side by side
+        const int nitems = 1 + p.nproj + p.nagg;
+        for (int item = warp; item < nitems; item += kWarpsPerCta) {
+            if (item == 0) {
+                if (p.out_pos)
+                    for (int k = lane; k < T; k += 32) p.out_pos[base + k] = p.pos_base + tile_row0 + list[k];
+            } else if (item <= p.nproj) {                          // iterator/Projection.java:103-144
+                const DevProj& pr = p.proj[item - 1];
+                if (pr.stride == 4) {
+                    const uint32_t* src = reinterpret_cast<const uint32_t*>(pr.src) + tile_row0;
+                    uint32_t* dst = reinterpret_cast<uint32_t*>(pr.dst) + base;
+                    for (int k = lane; k < T; k += 32) dst[k] = __ldg(src + list[k]);
+                } else if (pr.stride == 16) {
+                    const uint4* src = reinterpret_cast<const uint4*>(pr.src) + tile_row0;
+                    uint4* dst = reinterpret_cast<uint4*>(pr.dst) + base;
+                    for (int k = lane; k < T; k += 32) dst[k] = __ldg(src + list[k]);
+                } else {
+                    const int words = pr.stride >> 2;
+                    for (int k = lane; k < T; k += 32) {
+                        const uint32_t* src = reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(pr.src) +
+                                                                                (tile_row0 + list[k]) * pr.stride);
+                        uint32_t* dst = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(pr.dst) + (base + k) * pr.stride);
+                        for (int q = 0; q < words; ++q) dst[q] = __ldg(src + q);
+                    }
+                }
+            } else {
+                const int a = item - 1 - p.nproj;
+                const DevAgg& g = p.aggs[a];
                 unsigned long long v;
                 if (g.kind == MBC_AGG_COUNT) {
                     v = (unsigned long long)T;
                 } else {
-                    v = agg_identity(g);
-                    const int nw = min(kWarpsPerCta, (T + 31) / 32);
-                    for (int w = 0; w < nw; ++w) v = agg_merge(g, v, s_aggw[wtid][w]);
+                    const uint32_t* src = reinterpret_cast<const uint32_t*>(g.src) + tile_row0;
+                    if (g.type == MBC_ATTR_INTEGER) {
+                        long long acc = (long long)agg_identity(g);
+                        for (int k = lane; k < T; k += 32) acc = agg_combine<long long>(g.kind, acc, (long long)(int32_t)__ldg(src + list[k]));
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) acc = agg_combine<long long>(g.kind, acc, __shfl_xor_sync(0xFFFFFFFFu, acc, o));
+                        v = (unsigned long long)acc;
+                    } else {
+                        double acc = __longlong_as_double((long long)agg_identity(g));
+                        for (int k = lane; k < T; k += 32) acc = agg_combine<double>(g.kind, acc, (double)__uint_as_float(__ldg(src + list[k])));
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) acc = agg_combine<double>(g.kind, acc, __shfl_xor_sync(0xFFFFFFFFu, acc, o));
+                        v = (unsigned long long)__double_as_longlong(acc);
+                    }
                 }
-                p.partials[(size_t)wtid * p.total_tiles + p.tile_base + tileB] = v;
+                if (lane == 0) p.partials[(size_t)a * p.total_tiles + p.tile_base + tile] = v;
             }
         }
-        tileB = tileA;
-        slotB = slotA;
-        bufB = bufA;
-        if (++slotA == S) { slotA = 0; parityA ^= 1u; }
+        return;
     }
-#ifdef MBC_SCAN_PROFILE
-    if (p.prof && lane == 0 && (tid == 0 || tid == 32 || tid == 64)) {
-        const int who = tid >> 5;                                  // 0 scan warp, 1 first worker warp, 2 second worker warp
-        for (int k = 0; k < 8; ++k) atomicAdd((unsigned long long*)&p.prof[who * 8 + k], (unsigned long long)_prof[k]);
+
+    // dense tile: one thread per survivor, gathers issued in batches before the dependent stores
+    if (p.out_pos) {
+        for (int k = tid; k < T; k += kScanThreads) p.out_pos[base + k] = p.pos_base + tile_row0 + list[k];
     }
-#endif
+    for (int c = 0; c < p.nproj; ++c) {
+        const DevProj& pr = p.proj[c];
+        if (pr.stride == 4) {
+            const uint32_t* src = reinterpret_cast<const uint32_t*>(pr.src) + tile_row0;
+            uint32_t* dst = reinterpret_cast<uint32_t*>(pr.dst) + base;
+            for (int k0 = tid; k0 < T; k0 += kScanThreads * kGatherBatch) {
+                uint32_t v[kGatherBatch];
+#pragma unroll
+                for (int b = 0; b < kGatherBatch; ++b) {
+                    int k = k0 + b * kScanThreads;
+                    if (k < T) v[b] = __ldg(src + list[k]);
+                }
+#pragma unroll
+                for (int b = 0; b < kGatherBatch; ++b) {
+                    int k = k0 + b * kScanThreads;
+                    if (k < T) dst[k] = v[b];
+                }
+            }
+        } else if (pr.stride == 16) {
+            const uint4* src = reinterpret_cast<const uint4*>(pr.src) + tile_row0;
+            uint4* dst = reinterpret_cast<uint4*>(pr.dst) + base;
+            for (int k0 = tid; k0 < T; k0 += kScanThreads * kGatherBatch) {
+                uint4 v[kGatherBatch];
+#pragma unroll
+                for (int b = 0; b < kGatherBatch; ++b) {
+                    int k = k0 + b * kScanThreads;
+                    if (k < T) v[b] = __ldg(src + list[k]);
+                }
+#pragma unroll
+                for (int b = 0; b < kGatherBatch; ++b) {
+                    int k = k0 + b * kScanThreads;
+                    if (k < T) dst[k] = v[b];
+                }
+            }
+        } else {
+            const int words = pr.stride >> 2;
+            for (int k = tid; k < T; k += kScanThreads) {
+                const uint32_t* src = reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(pr.src) + (tile_row0 + list[k]) * pr.stride);
+                uint32_t* dst = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(pr.dst) + (base + k) * pr.stride);
+                for (int q = 0; q < words; ++q) dst[q] = __ldg(src + q);
+            }
+        }
+    }
+    // aggregates: per-thread fold over its survivors, one butterfly per warp, warps combined in order
+    for (int a = 0; a < p.nagg; ++a) {
+        const DevAgg& g = p.aggs[a];
+        if (g.kind == MBC_AGG_COUNT) continue;                     // the tile count is the count
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(g.src) + tile_row0;
+        unsigned long long v;
+        if (g.type == MBC_ATTR_INTEGER) {
+            long long acc = (long long)agg_identity(g);
+            for (int k = tid; k < T; k += kScanThreads) acc = agg_combine<long long>(g.kind, acc, (long long)(int32_t)__ldg(src + list[k]));
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc = agg_combine<long long>(g.kind, acc, __shfl_xor_sync(0xFFFFFFFFu, acc, o));
+            v = (unsigned long long)acc;
+        } else {
+            double acc = __longlong_as_double((long long)agg_identity(g));
+            for (int k = tid; k < T; k += kScanThreads) acc = agg_combine<double>(g.kind, acc, (double)__uint_as_float(__ldg(src + list[k])));
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc = agg_combine<double>(g.kind, acc, __shfl_xor_sync(0xFFFFFFFFu, acc, o));
+            v = (unsigned long long)__double_as_longlong(acc);
+        }
+        if (lane == 0) s_aggw[a][warp] = v;
+    }
+    __syncthreads();
+    if (tid < p.nagg) {
+        const DevAgg& g = p.aggs[tid];
+        unsigned long long v;
+        if (g.kind == MBC_AGG_COUNT) {
+            v = (unsigned long long)T;
+        } else {
+            v = s_aggw[tid][0];
+            for (int w = 1; w < kWarpsPerCta; ++w) v = agg_merge(g, v, s_aggw[tid][w]);
+        }
+        p.partials[(size_t)tid * p.total_tiles + p.tile_base + tile] = v;
+    }
 }
 
 // Reduce the per-tile partials of one aggregate in tile order (fixed tree => reproducible sums).
