@@ -103,6 +103,7 @@ struct ScanParams {
     int64_t* out_pos;
     uint32_t* out_bitmap;
     uint32_t* tile_counts;        // qualifying rows per tile (pass 1 -> pass 2)
+    uint32_t* warp_counts;        // [tile][kWarpsPerCta] qualifying rows per 512-row warp chunk
     unsigned long long* tile_out; // global output offset of every tile (tile_offsets_kernel)
     long long* count;             // in: running output offset, out: offset after this launch
     long long* prof;              // optional phase timers (MBC_SCAN_PROFILE builds)
@@ -440,6 +441,8 @@ __global__ void __launch_bounds__(kScanThreads, 2) filter_kernel(const __grid_co
 #pragma unroll
             for (int w = 0; w < kWarpsPerCta; ++w) c += s_wcnt[w];
             p.tile_counts[tile] = c;
+#pragma unroll
+            for (int w = 0; w < kWarpsPerCta; ++w) p.warp_counts[(size_t)tile * kWarpsPerCta + w] = s_wcnt[w];
             const long long next = tile + (long long)S * gridDim.x;
             if (p.nstaged && next < p.ntiles) issue_tile(slot, (int)next);
         }
@@ -449,33 +452,59 @@ __global__ void __launch_bounds__(kScanThreads, 2) filter_kernel(const __grid_co
 }
 
 // ---- pass 1.5: tile counts -> tile output offsets -----------------------------------------------------------
+// One block; 4096 counts per round (coalesced 128-bit loads, warp-shuffle scans), carry between rounds.
 __global__ void __launch_bounds__(1024) tile_offsets_kernel(const uint32_t* counts, int ntiles, unsigned long long* tile_base,
                                                             long long* running /* in: offset so far, out: + total */) {
-    __shared__ unsigned long long sh[1024];
-    const int per = (ntiles + 1023) / 1024;
-    const int lo = min(ntiles, (int)threadIdx.x * per), hi = min(ntiles, lo + per);
-    unsigned long long s = 0;
-    for (int i = lo; i < hi; ++i) s += counts[i];
-    sh[threadIdx.x] = s;
+    __shared__ unsigned long long s_warp[32];
+    __shared__ unsigned long long s_carry;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_carry = (unsigned long long)*running;
     __syncthreads();
-    for (int o = 1; o < 1024; o <<= 1) {
-        unsigned long long t = threadIdx.x >= o ? sh[threadIdx.x - o] : 0;
+    for (int base = 0; base < ntiles; base += 4096) {
+        const int i0 = base + tid * 4;
+        uint32_t c[4] = {0, 0, 0, 0};
+        if (i0 + 3 < ntiles) {
+            uint4 q = *reinterpret_cast<const uint4*>(counts + i0);   // counts is 64-byte aligned, i0 a multiple of 4
+            c[0] = q.x; c[1] = q.y; c[2] = q.z; c[3] = q.w;
+        } else {
+            for (int j = 0; j < 4; ++j) if (i0 + j < ntiles) c[j] = counts[i0 + j];
+        }
+        const unsigned long long mine = (unsigned long long)c[0] + c[1] + c[2] + c[3];
+        unsigned long long incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned long long n = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if (lane >= o) incl += n;
+        }
+        if (lane == 31) s_warp[warp] = incl;
         __syncthreads();
-        sh[threadIdx.x] += t;
+        unsigned long long wsum = s_warp[lane];                    // every warp scans the 32 warp totals itself
+        unsigned long long winc = wsum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned long long n = __shfl_up_sync(0xFFFFFFFFu, winc, o);
+            if (lane >= o) winc += n;
+        }
+        const unsigned long long warp_excl = __shfl_sync(0xFFFFFFFFu, winc - wsum, warp);
+        const unsigned long long total = __shfl_sync(0xFFFFFFFFu, winc, 31);
+        unsigned long long run = s_carry + warp_excl + incl - mine;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (i0 + j < ntiles) tile_base[i0 + j] = run;
+            run += c[j];
+        }
+        __syncthreads();
+        if (tid == 0) s_carry += total;
         __syncthreads();
     }
-    const unsigned long long start = (unsigned long long)*running;
-    unsigned long long run = start + sh[threadIdx.x] - s;
-    for (int i = lo; i < hi; ++i) {
-        tile_base[i] = run;
-        run += counts[i];
-    }
-    __syncthreads();
-    if (threadIdx.x == 1023) *running = (long long)(start + sh[1023]);
+    if (tid == 0) *running = (long long)s_carry;
 }
 
 // ---- pass 2: ordered write of the survivors ----------------------------------------------------------------------
-__global__ void __launch_bounds__(kScanThreads, 4) write_kernel(const __grid_constant__ ScanParams p) {
+#ifndef MBC_WRITE_MIN_CTAS
+#define MBC_WRITE_MIN_CTAS 4
+#endif
+__global__ void __launch_bounds__(kScanThreads, MBC_WRITE_MIN_CTAS) write_kernel(const __grid_constant__ ScanParams p) {
     __shared__ uint16_t s_list[kTileRows];                         // survivor rows within the tile, by tile rank
     __shared__ uint32_t s_wtot[kWarpsPerCta];
     __shared__ unsigned long long s_aggw[kMaxAgg][kWarpsPerCta];
@@ -670,57 +699,34 @@ __global__ void __launch_bounds__(kScanThreads, 4) write_kernel(const __grid_con
     }
 }
 
-// Reduce the per-tile partials of one aggregate in tile order (fixed tree => reproducible sums).
+// Reduce the per-tile partials of one aggregate (fixed association => reproducible sums): thread i folds
+// entries i, i+1024, ... then a fixed tree combines the 1024 lanes.
 struct AggList {
     DevAgg g[kMaxAgg];
 };
 
-__global__ void __launch_bounds__(256) agg_finish_kernel(const unsigned long long* partials, int total_tiles,
-                                                         int ntiles, const __grid_constant__ AggList list,
-                                                         unsigned long long* out) {
+__global__ void __launch_bounds__(1024) agg_finish_kernel(const unsigned long long* partials, int total_tiles,
+                                                          int ntiles, const __grid_constant__ AggList list,
+                                                          unsigned long long* out) {
     const DevAgg g = list.g[blockIdx.x];
     const unsigned long long* src = partials + (size_t)blockIdx.x * total_tiles;
-    __shared__ unsigned long long sh[256];
-    const bool additive = g.kind == MBC_AGG_COUNT || g.kind == MBC_AGG_SUM;
-    const bool integral = g.kind == MBC_AGG_COUNT || g.type == MBC_ATTR_INTEGER;
-    // each thread folds a contiguous slice, then a fixed-shape tree combines the 256 slices
-    int per = (ntiles + 255) / 256;
-    int lo = min(ntiles, (int)threadIdx.x * per), hi = min(ntiles, lo + per);
-    if (integral) {
-        long long acc = additive ? 0ll : g.kind == MBC_AGG_MIN ? (long long)INT32_MAX : (long long)INT32_MIN;
-        for (int i = lo; i < hi; ++i) {
-            long long x = (long long)src[i];
-            acc = additive ? acc + x : g.kind == MBC_AGG_MIN ? min(acc, x) : max(acc, x);
-        }
-        sh[threadIdx.x] = (unsigned long long)acc;
-    } else {
-        double acc = additive ? 0.0 : g.kind == MBC_AGG_MIN ? (double)INFINITY : (double)-INFINITY;
-        for (int i = lo; i < hi; ++i) {
-            double x = __longlong_as_double((long long)src[i]);
-            acc = additive ? acc + x : g.kind == MBC_AGG_MIN ? fmin(acc, x) : fmax(acc, x);
-        }
-        sh[threadIdx.x] = (unsigned long long)__double_as_longlong(acc);
+    __shared__ unsigned long long sh[1024];
+    unsigned long long acc = agg_identity(g);
+    int i = threadIdx.x;
+    for (; i + 3 * 1024 < ntiles; i += 4 * 1024) {                 // four independent loads in flight
+        unsigned long long x0 = src[i], x1 = src[i + 1024], x2 = src[i + 2048], x3 = src[i + 3072];
+        acc = agg_merge(g, agg_merge(g, agg_merge(g, agg_merge(g, acc, x0), x1), x2), x3);
     }
+    for (; i < ntiles; i += 1024) acc = agg_merge(g, acc, src[i]);
+    sh[threadIdx.x] = acc;
     __syncthreads();
-    for (int s = 128; s > 0; s >>= 1) {
-        if ((int)threadIdx.x < s) {
-            if (integral) {
-                long long a = (long long)sh[threadIdx.x], b = (long long)sh[threadIdx.x + s];
-                sh[threadIdx.x] = (unsigned long long)(additive ? a + b : g.kind == MBC_AGG_MIN ? min(a, b) : max(a, b));
-            } else {
-                double a = __longlong_as_double((long long)sh[threadIdx.x]);
-                double b = __longlong_as_double((long long)sh[threadIdx.x + s]);
-                double r = additive ? a + b : g.kind == MBC_AGG_MIN ? fmin(a, b) : fmax(a, b);
-                sh[threadIdx.x] = (unsigned long long)__double_as_longlong(r);
-            }
-        }
+    for (int s = 512; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) sh[threadIdx.x] = agg_merge(g, sh[threadIdx.x], sh[threadIdx.x + s]);
         __syncthreads();
     }
     if (threadIdx.x == 0) out[blockIdx.x] = sh[0];
 }
 
-// SoA projected columns -> reference Tuple bytes (heap/Tuple.java:369-440 header,
-// global/Convert.java:163-275 big-endian fields, strings as [len:2][bytes][zero pad]).
 struct TupleField {
     const void* src;
     int32_t type, width, stride, offset;
