@@ -1,0 +1,220 @@
+"""Mirror of the driver classes that sit directly on the scan path (minijava/src/input/): they marshal the
+command-line arguments, build CondExpr[] / FldSpec[] and drive the operators.  Same argument order and the
+same printed rows as the reference; every method also returns the rows so tests can assert on them."""
+from __future__ import annotations
+
+from typing import Optional, Sequence
+
+from . import _native as N
+from .columnar import Columnarfile
+from .engine import Term, bitmap_join
+from .global_ import AttrOperator, AttrType, IndexType, SystemDefs
+from .index import ColumnarIndexScan
+from .iterator import ColumnarFileScan, CondExpr, FldSpec, RelSpec
+
+
+def _emit(lines: list, text: str, echo: bool) -> None:
+    lines.append(text)
+    if echo:
+        print(text)
+
+
+def _footer(lines: list, count: int, echo: bool) -> None:
+    for t in ("", "*" * 72, f"Total Results Count By Query: {count}", "*" * 72, ""):
+        _emit(lines, t, echo)
+
+
+def build_cnf_condexpr(constraintStr: str, cf: Columnarfile, outer: bool = True):
+    """BitMapQuery.buildCNFQueryCondExpr (:347-420) / MultiIndexQuery's 4-field form.
+    `{(A,=,x)|(B,<,y,BM)}^{(C,!=,6)}` -> (CondExpr[] with trailing None, indexTypes, fldNums, indNames)."""
+    exprs, index_types, fld_nums, ind_names = [], [], [], []
+    for conj in constraintStr.split("^"):
+        if not (conj.startswith("{") and conj.endswith("}")):
+            raise Exception("Invalid query format")
+        head = tail = None
+        for dis in conj[1:-1].split("|"):
+            if not (dis.startswith("(") and dis.endswith(")")):
+                raise Exception("Invalid query format")
+            parts = [p.strip() for p in dis[1:-1].strip().split(",")]
+            if len(parts) not in (3, 4):
+                raise Exception("Invalid VALUECONSTRAINT elements")
+            col = cf.colNameToIndex(parts[0])
+            t = CondExpr()
+            t.op = AttrOperator.findOperator(parts[1])
+            t.type1 = AttrType(AttrType.attrSymbol)
+            t.operand1.symbol = FldSpec(RelSpec(RelSpec.outer if outer else RelSpec.innerRel), col + 1)
+            if cf.getAttributeTypes()[col].attrType == AttrType.attrInteger:
+                t.type2 = AttrType(AttrType.attrInteger)
+                t.operand2.integer = int(parts[2])
+            else:
+                t.type2 = AttrType(AttrType.attrString)
+                t.operand2.string = parts[2]
+            access = parts[3] if len(parts) == 4 else "BM"
+            t.indexType = IndexType(IndexType.Bitmap if access.upper() in ("BM", "BITMAP") else IndexType.B_Index)
+            index_types.append(t.indexType)
+            ind_names.append(" ")
+            fld_nums.append(col + 1)
+            if head is None:
+                head = tail = t
+            else:
+                tail.next = t
+                tail = t
+        exprs.append(head)
+    exprs.append(None)
+    return exprs, index_types, fld_nums, ind_names
+
+
+def _fmt(tuple_, types: Sequence[int]) -> str:
+    vals = []
+    for i, t in enumerate(types):
+        vals.append(str(tuple_.getIntFld(i + 1)) if t == AttrType.attrInteger else
+                    repr(tuple_.getFloFld(i + 1)) if t == AttrType.attrReal else tuple_.getStrFld(i + 1))
+    return ", ".join(vals)
+
+
+class Index:
+    """input/Index.java:16-66: `index DB CF COL bitmap`"""
+
+    def createIndex(self, args: Sequence[str]) -> None:
+        _, cfname, colname, kind = args[:4]
+        if kind.lower() != "bitmap":
+            raise Exception("Only bitmap indexes are built on the GPU; B-tree indexes stay in Java")
+        cf = Columnarfile(cfname)
+        cf.createBitMapIndex(cf.colNameToIndex(colname))
+
+
+class Query:
+    """input/Query.java:35-155,248-297: `query DB CF [targets] {col,op,val} NUMBUF FILESCAN|COLUMNSCAN|BITMAP`"""
+
+    def execute(self, args: Sequence[str], echo: bool = True) -> list[str]:
+        if len(args) < 6:
+            raise Exception("Invalid number of attributes.")
+        cfname, targets, constraint, access = args[1], args[2], args[3], args[5]
+        if not (targets.startswith("[") and targets.endswith("]")):
+            raise Exception("[TARGETCOLUMNNAMES] format invalid.")
+        if not (constraint.startswith("{") and constraint.endswith("}")):
+            raise Exception("VALUECONSTRAINT format invalid.")
+        if access.upper() not in ("FILESCAN", "COLUMNSCAN", "BTREE", "BITMAP"):
+            raise Exception("access type invalid.")
+        if access.upper() == "BTREE":
+            raise Exception("BTREE access stays in Java (out of scope for the GPU path)")
+        cf = Columnarfile(cfname)
+        names = [t.strip() for t in targets[1:-1].split(",")]
+        cols = [cf.colNameToIndex(n) for n in names]
+        proj = [FldSpec(RelSpec(RelSpec.outer), c + 1) for c in cols]
+        out_types = [cf.getAttributeTypes()[c].attrType for c in cols]
+        parts = constraint[1:-1].strip().split(",")
+        if len(parts) != 3:
+            raise Exception("Invalid VALUECONSTRAINT elements")
+        exprs, itypes, fnums, inames = build_cnf_condexpr("{(" + ",".join(parts) + ")}", cf)
+        lines: list[str] = []
+        _emit(lines, ", ".join(names), echo)
+        count = 0
+        if access.upper() == "BITMAP":                            # Query.executeBitmapScan (:248-297)
+            if not cf.bitmapIndexExists(cols[0] if False else cf.colNameToIndex(parts[0].strip())):
+                raise Exception("Bitmap index does not exist on column " + parts[0])
+            it = ColumnarIndexScan(cf, fnums, itypes, inames, cf.getAttributeTypes(), cf.getStringSizes(), cf.getFieldCount(),
+                                   len(cols), cols, proj, exprs, False)
+        else:                                                     # executeFileScan (:121-155); COLUMNSCAN gives the same rows
+            it = ColumnarFileScan(cfname, cf.getAttributeTypes(), cf.getStringSizes(), cf.getFieldCount(), len(cols), proj, exprs)
+        while True:
+            t = it.get_next()
+            if t is None:
+                break
+            _emit(lines, _fmt(t, out_types), echo)
+            count += 1
+        it.close()
+        _footer(lines, count, echo)
+        self.resultCount = count
+        return lines
+
+
+class MultiIndexQuery:
+    """input/MultiIndexQuery.java:99-136: `indexes_query DB CF [targets] CNF NUMBUF`"""
+
+    def execute(self, args: Sequence[str], echo: bool = True) -> list[str]:
+        cfname, targets, cnf = args[1], args[2], args[3]
+        cf = Columnarfile(cfname)
+        names = [t.strip() for t in targets[1:-1].split(",")]
+        cols = [cf.colNameToIndex(n) for n in names]
+        proj = [FldSpec(RelSpec(RelSpec.outer), c + 1) for c in cols]
+        exprs, itypes, fnums, inames = build_cnf_condexpr(cnf, cf)
+        it = ColumnarIndexScan(cf, fnums, itypes, inames, cf.getAttributeTypes(), cf.getStringSizes(), cf.getFieldCount(),
+                               len(cols), cols, proj, exprs, False)
+        out_types = [cf.getAttributeTypes()[c].attrType for c in cols]
+        lines: list[str] = []
+        _emit(lines, ", ".join(names), echo)
+        count = 0
+        while True:
+            t = it.get_next()
+            if t is None:
+                break
+            _emit(lines, _fmt(t, out_types), echo)
+            count += 1
+        it.close()
+        _footer(lines, count, echo)
+        self.resultCount = count
+        return lines
+
+
+class BitMapQuery:
+    """input/BitMapQuery.java:49-305: `bmj DB OUTER INNER OUTERCNF INNERCNF JOINCNF [targets] NUMBUF`.
+    The side filters run as bitmap CNF scans (getConstraintBitset :322-345), the join itself is K6."""
+
+    def execute(self, args: Sequence[str], echo: bool = True) -> list[str]:
+        if len(args) < 8:
+            raise Exception("Invalid number of attributes.")
+        outer_name, inner_name, ocnf, icnf, jcnf, targets = args[1], args[2], args[3], args[4], args[5], args[6]
+        outer, inner = Columnarfile(outer_name), Columnarfile(inner_name)
+        lines: list[str] = []
+        osel = self._constraint_bitset(outer, ocnf)
+        _emit(lines, "OuterConstraint Bitset After performing AND and ORs", echo)
+        _emit(lines, repr(osel.getOutputPositions()), echo)
+        isel = self._constraint_bitset(inner, icnf)
+        _emit(lines, "InnerConstraint Bitset After performing AND and ORs", echo)
+        _emit(lines, repr(isel.getOutputPositions()), echo)
+        if not (targets.startswith("[") and targets.endswith("]")):
+            raise Exception("[TARGETCOLUMNNAMES] format invalid.")
+        names = [t.strip() for t in targets[1:-1].split(",")]
+        proj, out_types = [], []
+        for n in names:                                            # createProjectionsAndTuples (:113-185)
+            rel, col = n.split(".")
+            if rel == outer_name:
+                proj.append((N.OPERAND_OUTER, outer.colNameToIndex(col)))
+                out_types.append(outer.getAttributeTypes()[proj[-1][1]].attrType)
+            else:
+                proj.append((N.OPERAND_INNER, inner.colNameToIndex(col)))
+                out_types.append(inner.getAttributeTypes()[proj[-1][1]].attrType)
+        join_terms = []
+        for ci, conj in enumerate(jcnf.split("^")):                # buildCNFJoinCondExprForFilling (:422-476)
+            if not (conj.startswith("{") and conj.endswith("}")):
+                raise Exception("Invalid query format")
+            for dis in conj[1:-1].split("|"):
+                parts = [p.strip() for p in dis[1:-1].strip().split(",")]
+                if len(parts) != 3:
+                    raise Exception("Invalid VALUECONSTRAINT elements")
+                oc, ic = outer.colNameToIndex(parts[0]), inner.colNameToIndex(parts[2])
+                if outer.getAttributeTypes()[oc].attrType != inner.getAttributeTypes()[ic].attrType:
+                    raise Exception("Invalid JOIN COLUMN ATTR TYPE NOT MATCH.")
+                if not inner.bitmapIndexExists(ic):                # the reference probes the inner column's bitmap index
+                    raise Exception("Bitmap index does not exist on column " + parts[2])
+                join_terms.append(Term(AttrOperator.findOperator(parts[1]).attrOperator, ("col", oc), ("icol", ic), ci))
+        res = bitmap_join(outer.table, inner.table, join_terms, proj,
+                          N.WANT_POSITIONS | N.WANT_COLUMNS | N.WANT_TUPLES | N.WANT_AGG | N.WANT_HOST, aggs=[(N.AGG_COUNT, 0)],
+                          outer_sel=osel._result, inner_sel=isel._result)
+        _emit(lines, ", ".join(names), echo)
+        from .heap import Tuple
+        for raw in res.tuples():
+            t = Tuple(bytes(raw))
+            t._adopt_header()
+            _emit(lines, _fmt(t, out_types), echo)
+        count = res.count
+        res.close(); osel.close(); isel.close()
+        _footer(lines, count, echo)
+        self.resultCount = count
+        return lines
+
+    @staticmethod
+    def _constraint_bitset(cf: Columnarfile, cnf: str) -> ColumnarIndexScan:
+        exprs, itypes, fnums, inames = build_cnf_condexpr(cnf, cf)
+        return ColumnarIndexScan(cf, fnums, itypes, inames, cf.getAttributeTypes(), cf.getStringSizes(), cf.getFieldCount(), exprs)

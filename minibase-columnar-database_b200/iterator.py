@@ -1,0 +1,276 @@
+"""Mirror of the reference's ``iterator`` package for the columnar scan path: the CondExpr/FldSpec
+predicate and projection structures and the ColumnarFileScan operator, same names and argument meaning
+as minijava/src/iterator/*.java.  The operator's work (TupleScan -> PredEval -> Projection per row in the
+reference) is one fused GPU scan through the C ABI; ``get_next()`` then slices the result.
+"""
+from __future__ import annotations
+
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _native as N
+from .engine import Term
+from .global_ import AttrOperator, AttrType, IndexType, SystemDefs, TID
+from .heap import Tuple
+
+
+# ---- exceptions (chainexception/ChainException.java: every checked exception carries `prev`) ----------
+class ChainException(Exception):
+    def __init__(self, prev: Optional[BaseException] = None, msg: str = ""):
+        super().__init__(msg)
+        self.prev = prev
+
+
+class FileScanException(ChainException):
+    pass
+
+
+class TupleUtilsException(ChainException):
+    pass
+
+
+class InvalidRelation(ChainException):
+    def __init__(self, msg: str = ""):
+        super().__init__(None, msg)
+
+
+class PredEvalException(ChainException):
+    pass
+
+
+class UnknowAttrType(ChainException):
+    pass
+
+
+class WrongPermat(ChainException):
+    def __init__(self, msg: str = ""):
+        super().__init__(None, msg)
+
+
+class IndexException(ChainException):
+    pass
+
+
+# ---- predicate / projection structures -----------------------------------------------------------------
+class RelSpec:
+    """iterator/RelSpec.java:3-16"""
+    outer, innerRel = 0, 1
+
+    def __init__(self, key: int):
+        self.key = key
+
+
+class FldSpec:
+    """iterator/FldSpec.java:4-17: (relation, 1-based field offset)"""
+
+    def __init__(self, relation: RelSpec, offset: int):
+        self.relation = relation
+        self.offset = offset
+
+
+class Operand:
+    """iterator/Operand.java:5-10"""
+
+    def __init__(self):
+        self.symbol: Optional[FldSpec] = None
+        self.string: Optional[str] = None
+        self.integer: int = 0
+        self.real: float = 0.0
+
+
+class CondExpr:
+    """iterator/CondExpr.java:12-57.  A CondExpr[] is a CNF: the array (None-terminated) is AND, the
+    ``next`` chain of one element is OR (iterator/PredEval.java:51-54,164-176)."""
+
+    def __init__(self):
+        self.op = AttrOperator(AttrOperator.aopNOP)
+        self.type1: Optional[AttrType] = None
+        self.type2: Optional[AttrType] = None
+        self.operand1 = Operand()
+        self.operand2 = Operand()
+        self.next: Optional["CondExpr"] = None
+        self.indexType = IndexType(IndexType.None_)
+
+
+def _operand_spec(t: AttrType, o: Operand) -> tuple:
+    if t.attrType == AttrType.attrSymbol:
+        kind = "col" if o.symbol.relation.key == RelSpec.outer else "icol"
+        return (kind, o.symbol.offset - 1)                     # symbol.offset is 1-based (PredEval.java:79-91)
+    if t.attrType == AttrType.attrInteger:
+        return ("int", o.integer)
+    if t.attrType == AttrType.attrReal:
+        return ("real", o.real)
+    if t.attrType == AttrType.attrString:
+        return ("str", o.string)
+    raise UnknowAttrType(None, "Don't know how to handle attrSymbol, attrNull")
+
+
+def flatten_condexpr(p: Optional[Sequence[Optional[CondExpr]]]) -> list[Term]:
+    """CondExpr[] -> flat term list for the C ABI (conjunct id = array index)."""
+    terms: list[Term] = []
+    if p is None:
+        return terms                                            # p == null: every row qualifies (PredEval.java:46-49)
+    for i, head in enumerate(p):
+        if head is None:
+            break                                               # the array is None-terminated
+        cur = head
+        while cur is not None:
+            terms.append(Term(cur.op.attrOperator, _operand_spec(cur.type1, cur.operand1),
+                              _operand_spec(cur.type2, cur.operand2), i))
+            cur = cur.next
+    return terms
+
+
+def setup_op_tuple(Jtuple: Tuple, res_attrs: list, in1: Sequence[AttrType], len_in1: int, t1_str_sizes: Sequence[int],
+                   proj_list: Sequence[FldSpec], nOutFlds: int) -> list[int]:
+    """iterator/TupleUtils.java:295-341: output tuple header of a single-relation projection."""
+    sizes = [0] * len_in1
+    c = 0
+    for i in range(len_in1):
+        if in1[i].attrType == AttrType.attrString:
+            sizes[i] = t1_str_sizes[c]
+            c += 1
+    for i in range(nOutFlds):
+        if proj_list[i].relation.key != RelSpec.outer:
+            raise InvalidRelation("Invalid relation -innerRel")
+        res_attrs[i] = AttrType(in1[proj_list[i].offset - 1].attrType)
+    res_str_sizes = [sizes[proj_list[i].offset - 1] for i in range(nOutFlds)
+                     if in1[proj_list[i].offset - 1].attrType == AttrType.attrString]
+    try:
+        Jtuple.setHdr(nOutFlds, res_attrs, res_str_sizes)
+    except Exception as e:
+        raise TupleUtilsException(e, "setHdr() failed")
+    return res_str_sizes
+
+
+class Iterator:
+    """iterator/Iterator.java:12-61"""
+
+    def __init__(self):
+        self.closeFlag = False
+
+    def get_next(self):
+        raise NotImplementedError
+
+    def close(self):
+        raise NotImplementedError
+
+
+class _ResultCursor:
+    """Slices an engine Result into reference Tuples, reusing ONE Jtuple like the Java iterators do."""
+
+    def __init__(self, result, out_types: Sequence[AttrType], jtuple: Tuple):
+        self.result = result
+        self.jtuple = jtuple
+        self.types = [t.attrType for t in out_types]
+        self.positions = result.positions()
+        self.cols = [result.column(i) for i in range(len(self.types))]
+        self.i = 0
+
+    def next_tuple(self) -> Optional[Tuple]:
+        if self.i >= len(self.positions):
+            return None
+        k = self.i
+        self.i += 1
+        for f, t in enumerate(self.types):                     # Projection.Project (:103-144)
+            if t == AttrType.attrInteger:
+                self.jtuple.setIntFld(f + 1, int(self.cols[f][k]))
+            elif t == AttrType.attrReal:
+                self.jtuple.setFloFld(f + 1, float(self.cols[f][k]))
+            else:
+                self.jtuple.setStrFld(f + 1, bytes(self.cols[f][k]).rstrip(b"\0").decode("utf-8"))
+        return self.jtuple
+
+    def next_position(self) -> Optional[int]:
+        if self.i >= len(self.positions):
+            return None
+        self.i += 1
+        return int(self.positions[self.i - 1])
+
+
+class ColumnarFileScan(Iterator):
+    """iterator/ColumnarFileScan.java:19-219.
+
+    ColumnarFileScan(file_name, in1, s1_sizes, len_in1, n_out_flds, proj_list, outFilter)   (:51)
+    ColumnarFileScan(file_name, in1, s1_sizes, len_in1, outFilter)                          (:102, tid-only / delete query)
+
+    The scan runs on the GPU when the first row is asked for; rows come back in ascending position order
+    exactly as TupleScan produces them, deleted rows skipped (columnar/TupleScan.java:85)."""
+
+    def __init__(self, file_name: str, in1: Sequence[AttrType], s1_sizes: Sequence[int], len_in1: int, *rest):
+        super().__init__()
+        from .columnar import Columnarfile
+        if len(rest) == 3:
+            n_out_flds, proj_list, outFilter = rest
+            self.deleteQuery = False
+        elif len(rest) == 1:
+            (outFilter,) = rest
+            n_out_flds, proj_list = 0, []
+            self.deleteQuery = True
+        else:
+            raise TypeError("ColumnarFileScan(file_name, in1, s1_sizes, len_in1, [n_out_flds, proj_list,] outFilter)")
+        self._in1, self.in1_len, self.s_sizes = list(in1), len_in1, list(s1_sizes)
+        self.OutputFilter = outFilter
+        self.perm_mat = list(proj_list)
+        self.nOutFlds = n_out_flds
+        self.Jtuple = Tuple()
+        self._out_types: list = [None] * n_out_flds
+        if not self.deleteQuery:
+            setup_op_tuple(self.Jtuple, self._out_types, self._in1, len_in1, self.s_sizes, self.perm_mat, n_out_flds)
+        try:
+            self.f = Columnarfile(file_name)                    # ColumnarFileScan.java:84-91
+        except Exception as e:
+            raise FileScanException(e, "Create new heapfile failed")
+        if self.f.numColumns != len_in1 or any(a.attrType != b.attrType for a, b in zip(self.f.attrTypes, self._in1)):
+            raise FileScanException(None, "openTupleScan() failed")
+        self._cursor: Optional[_ResultCursor] = None
+        self._result = None
+
+    def show(self):
+        return self.perm_mat
+
+    def _open(self) -> _ResultCursor:
+        if self._cursor is None:
+            try:
+                terms = flatten_condexpr(self.OutputFilter)
+                proj = [fs.offset - 1 for fs in self.perm_mat]
+                self._result = self.f.table.scan(terms, proj=proj, want=N.WANT_POSITIONS | N.WANT_COLUMNS | N.WANT_HOST)
+            except N.MbcError as e:
+                raise PredEvalException(e, "TupleUtilsException is caught by PredEval.java")
+            self._cursor = _ResultCursor(self._result, self._out_types, self.Jtuple)
+        return self._cursor
+
+    def get_next(self) -> Optional[Tuple]:
+        return self._open().next_tuple()
+
+    def get_next_tid(self) -> Optional[TID]:
+        pos = self._open().next_position()
+        return None if pos is None else TID(self.in1_len, pos)
+
+    def close(self) -> None:
+        if not self.closeFlag:
+            if self._result is not None:
+                self._result.close()
+            self._cursor = self._result = None
+            self.closeFlag = True
+
+    def restart(self) -> None:
+        if self._result is not None:
+            self._result.close()
+        self._cursor = self._result = None
+
+    def getTupleSize(self) -> int:
+        return self.Jtuple.size()
+
+    # ---- extensions the reference does not have: aggregates over the qualifying set ----
+    def aggregate(self, specs: Sequence[tuple]) -> list:
+        """specs = [(kind, col)], kind in {COUNT 0, SUM 1, MIN 2, MAX 3}, col 0-based.  Returns (value, valid)."""
+        res = self.f.table.scan(flatten_condexpr(self.OutputFilter), want=N.WANT_AGG, aggs=specs)
+        out = []
+        for a, (kind, col) in enumerate(specs):
+            i, f, v = res.agg(a)
+            integral = kind == N.AGG_COUNT or self.f.attrTypes[col].attrType == AttrType.attrInteger
+            out.append((i if integral else f, v))
+        res.close()
+        return out
