@@ -76,8 +76,19 @@ int32_t ensure_workspace(mbc_ctx* ctx, size_t bytes) {
     return MBC_OK;
 }
 
-void begin_timing(mbc_ctx* ctx) { cudaEventRecord(ctx->ev_begin, ctx->stream); }
+void begin_timing(mbc_ctx* ctx) {
+    if (!ctx->timing_split) ctx->extra_ms = 0.f;
+    ctx->timing_split = false;
+    cudaEventRecord(ctx->ev_begin, ctx->stream);
+}
 void end_timing(mbc_ctx* ctx) { cudaEventRecord(ctx->ev_end, ctx->stream); }
+void split_timing(mbc_ctx* ctx) {
+    cudaEventRecord(ctx->ev_end, ctx->stream);
+    float ms = 0.f;
+    if (cudaEventSynchronize(ctx->ev_end) == cudaSuccess && cudaEventElapsedTime(&ms, ctx->ev_begin, ctx->ev_end) == cudaSuccess)
+        ctx->extra_ms += ms;
+    ctx->timing_split = true;
+}
 
 }  // namespace mbc
 
@@ -154,7 +165,7 @@ float mbc_last_kernel_ms(const mbc_ctx* ctx) {
     float ms = 0.f;
     if (cudaEventSynchronize(ctx->ev_end) != cudaSuccess) return 0.f;
     if (cudaEventElapsedTime(&ms, ctx->ev_begin, ctx->ev_end) != cudaSuccess) return 0.f;
-    return ms;
+    return ms + ctx->extra_ms;
 }
 
 int32_t mbc_host_alloc(void** p, int64_t bytes) {

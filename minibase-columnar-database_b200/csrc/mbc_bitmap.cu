@@ -32,7 +32,50 @@ struct HashTab {
     unsigned long long* slots;
     uint32_t* slot_id;       // dense id per slot, filled by the host after sorting the values
     uint32_t mask;           // capacity - 1
+    // direct mode (int column whose value range is small): id = id_of[value - kmin], no hashing
+    const uint32_t* id_of;
+    long long kmin;
+    uint32_t range;
+    int32_t direct;
 };
+
+constexpr uint32_t kMaxDirectRange = 1u << 16;
+
+__global__ void __launch_bounds__(256) column_minmax_kernel(const int32_t* col, int64_t nrows, const uint32_t* deleted, long long* out) {
+    long long mn = INT64_MAX, mx = INT64_MIN;
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < nrows; r += (int64_t)gridDim.x * blockDim.x) {
+        if (deleted && ((deleted[r >> 5] >> (r & 31)) & 1u)) continue;
+        long long k = col[r];
+        mn = min(mn, k);
+        mx = max(mx, k);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        mn = min(mn, __shfl_xor_sync(0xFFFFFFFFu, mn, o));
+        mx = max(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, o));
+    }
+    if ((threadIdx.x & 31) == 0 && mn <= mx) {
+        atomicMin(out, mn);
+        atomicMax(out + 1, mx);
+    }
+}
+
+// presence bits of the values of a small-range int column: per-CTA bitmap in shared memory, OR-ed into global
+__global__ void __launch_bounds__(256) column_presence_kernel(const int32_t* col, int64_t nrows, const uint32_t* deleted, long long kmin,
+                                                              uint32_t range, uint32_t* presence) {
+    __shared__ uint32_t sh[kMaxDirectRange / 32];
+    const uint32_t words = (range + 31) / 32;
+    for (uint32_t i = threadIdx.x; i < words; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < nrows; r += (int64_t)gridDim.x * blockDim.x) {
+        if (deleted && ((deleted[r >> 5] >> (r & 31)) & 1u)) continue;
+        const uint32_t k = (uint32_t)((long long)col[r] - kmin);
+        const uint32_t bit = 1u << (k & 31);
+        if (!(sh[k >> 5] & bit)) atomicOr(&sh[k >> 5], bit);
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < words; i += blockDim.x)
+        if (sh[i]) atomicOr(&presence[i], sh[i]);
+}
 
 __device__ __forceinline__ uint32_t hash32(uint32_t x) {
     x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
@@ -117,7 +160,7 @@ struct BuildParams {
     unsigned int* ticket;
 };
 
-__global__ void __launch_bounds__(kBuildThreads, 1) bitmap_build_kernel(const __grid_constant__ BuildParams p) {
+__global__ void __launch_bounds__(kBuildThreads, 2) bitmap_build_kernel(const __grid_constant__ BuildParams p) {
     extern __shared__ uint4 sm4[];
     uint32_t* sm = reinterpret_cast<uint32_t*>(sm4);
     __shared__ long long s_chunk;
@@ -138,8 +181,12 @@ __global__ void __launch_bounds__(kBuildThreads, 1) bitmap_build_kernel(const __
             const int64_t row = row0 + r;
             int id = -1;
             if (row < p.nrows && !(p.deleted && ((p.deleted[row >> 5] >> (row & 31)) & 1u))) {
-                int s = probe<false>(p.h, p.col, p.stride, p.is_str != 0, row);
-                if (s >= 0) id = (int)p.h.slot_id[s] - p.v0;
+                if (p.h.direct) {
+                    id = (int)__ldg(p.h.id_of + (uint32_t)((long long)reinterpret_cast<const int32_t*>(p.col)[row] - p.h.kmin)) - p.v0;
+                } else {
+                    int s = probe<false>(p.h, p.col, p.stride, p.is_str != 0, row);
+                    if (s >= 0) id = (int)p.h.slot_id[s] - p.v0;
+                }
                 if (id < 0 || id >= p.nv) id = -1;
             }
             const uint32_t group = __match_any_sync(0xFFFFFFFFu, id);
@@ -149,10 +196,11 @@ __global__ void __launch_bounds__(kBuildThreads, 1) bitmap_build_kernel(const __
         __syncthreads();
 
         // stream the finished words out: wpc*4 contiguous bytes per value
-        const int quads_per_value = wpc >> 2;
+        const int qshift = 31 - __clz(wpc >> 2);               // quads per value is a power of two
+        const int qmask = (wpc >> 2) - 1;
         uint32_t* dst0 = p.bitmaps + (int64_t)p.v0 * p.words_pad + chunk * wpc;
         for (int i = threadIdx.x; i < total_words / 4; i += kBuildThreads) {
-            const int v = i / quads_per_value, q = i - v * quads_per_value;
+            const int v = i >> qshift, q = i & qmask;
             reinterpret_cast<uint4*>(dst0 + (int64_t)v * p.words_pad)[q] = sm4[i];
         }
         __syncthreads();
@@ -229,17 +277,61 @@ extern "C" int32_t mbc_bitmap_build(mbc_table* t, int32_t col) {
     MBC_TRY(dev_alloc(ctx, (void**)&d_overflow, 4, true));
     std::vector<unsigned long long> slots;
     uint32_t cap = 0;
-    begin_timing(ctx);
+    bool direct = false;
+    std::vector<uint32_t> id_of_host;
+    if (!is_str && t->nrows > 0) {
+        long long* d_mm = nullptr;
+        uint32_t* d_presence = nullptr;
+        MBC_TRY(dev_alloc(ctx, (void**)&d_mm, 16, false));
+        long long init[2] = {INT64_MAX, INT64_MIN}, mm[2];
+        MBC_CUDA(cudaMemcpyAsync(d_mm, init, 16, cudaMemcpyHostToDevice, ctx->stream));
+        begin_timing(ctx);
+        const int grid = (int)std::min<int64_t>((t->nrows + 255) / 256, (int64_t)ctx->sm_count * 8);
+        column_minmax_kernel<<<grid, 256, 0, ctx->stream>>>((const int32_t*)c.d, t->nrows, deleted, d_mm);
+        ctx->launches++;
+        split_timing(ctx);
+        MBC_CUDA(cudaMemcpyAsync(mm, d_mm, 16, cudaMemcpyDeviceToHost, ctx->stream));
+        MBC_CUDA(cudaStreamSynchronize(ctx->stream));
+        dev_free(ctx, d_mm);
+        if (mm[0] <= mm[1] && mm[1] - mm[0] < (long long)kMaxDirectRange) {
+            direct = true;
+            h.direct = 1;
+            h.kmin = mm[0];
+            h.range = (uint32_t)(mm[1] - mm[0] + 1);
+            const uint32_t words = (h.range + 31) / 32;
+            MBC_TRY(dev_alloc(ctx, (void**)&d_presence, (size_t)words * 4, true));
+            begin_timing(ctx);
+            column_presence_kernel<<<grid, 256, 0, ctx->stream>>>((const int32_t*)c.d, t->nrows, deleted, h.kmin, h.range, d_presence);
+            ctx->launches++;
+            split_timing(ctx);
+            std::vector<uint32_t> pres(words);
+            MBC_CUDA(cudaMemcpyAsync(pres.data(), d_presence, (size_t)words * 4, cudaMemcpyDeviceToHost, ctx->stream));
+            MBC_CUDA(cudaStreamSynchronize(ctx->stream));
+            dev_free(ctx, d_presence);
+            id_of_host.assign(h.range, 0xFFFFFFFFu);
+            bi.ivals.clear();
+            bi.svals.clear();
+            for (uint32_t k = 0; k < h.range; ++k)
+                if ((pres[k >> 5] >> (k & 31)) & 1u) {
+                    id_of_host[k] = (uint32_t)bi.ivals.size();
+                    bi.ivals.push_back((int32_t)(h.kmin + k));
+                }
+            bi.nvalues = (int64_t)bi.ivals.size();
+        }
+    }
     for (uint32_t try_cap : {1u << 12, 1u << 16, 1u << 20}) {
+        if (direct) break;
         cap = try_cap;
         MBC_TRY(dev_alloc(ctx, (void**)&h.slots, (size_t)cap * 8, true));
         h.mask = cap - 1;
         MBC_CUDA(cudaMemsetAsync(d_overflow, 0, 4, ctx->stream));
+        begin_timing(ctx);
         if (t->nrows > 0) {
             int grid = (int)std::min<int64_t>((t->nrows + 255) / 256, (int64_t)ctx->sm_count * 8);
             distinct_insert_kernel<<<grid, 256, 0, ctx->stream>>>(h, c.d, c.stride, is_str, t->nrows, deleted, d_overflow);
             ctx->launches++;
         }
+        split_timing(ctx);
         int overflow = 0;
         MBC_CUDA(cudaMemcpyAsync(&overflow, d_overflow, 4, cudaMemcpyDeviceToHost, ctx->stream));
         slots.resize(cap);
@@ -258,9 +350,15 @@ extern "C" int32_t mbc_bitmap_build(mbc_table* t, int32_t col) {
     dev_free(ctx, d_overflow);
 
     // 2. sort the values, give every slot its dense id
+    uint32_t* d_id_of = nullptr;
+    if (direct) {
+        MBC_TRY(dev_alloc(ctx, (void**)&d_id_of, (size_t)h.range * 4, false));
+        MBC_CUDA(cudaMemcpyAsync(d_id_of, id_of_host.data(), (size_t)h.range * 4, cudaMemcpyHostToDevice, ctx->stream));
+        h.id_of = d_id_of;
+    }
     std::vector<int> used_slots;
     for (uint32_t s = 0; s < cap; ++s) if (slots[s]) used_slots.push_back((int)s);
-    const int64_t D = (int64_t)used_slots.size();
+    const int64_t D = direct ? bi.nvalues : (int64_t)used_slots.size();
     std::vector<uint8_t> rep_bytes;                      // strings: representative rows
     if (is_str && D > 0) {
         rep_bytes.resize((size_t)D * c.stride);
@@ -271,7 +369,7 @@ extern "C" int32_t mbc_bitmap_build(mbc_table* t, int32_t col) {
         }
         MBC_CUDA(cudaStreamSynchronize(ctx->stream));
     }
-    std::vector<int> order(D);
+    std::vector<int> order(direct ? 0 : D);
     std::iota(order.begin(), order.end(), 0);
     if (is_str) {
         std::sort(order.begin(), order.end(), [&](int a, int b) {
@@ -283,9 +381,11 @@ extern "C" int32_t mbc_bitmap_build(mbc_table* t, int32_t col) {
         });
     }
     std::vector<uint32_t> slot_id(cap, 0xFFFFFFFFu);
-    bi.ivals.clear();
-    bi.svals.clear();
-    for (int64_t k = 0; k < D; ++k) {
+    if (!direct) {
+        bi.ivals.clear();
+        bi.svals.clear();
+    }
+    for (int64_t k = 0; k < (direct ? 0 : D); ++k) {
         int src = order[k];
         slot_id[used_slots[src]] = (uint32_t)k;
         if (is_str) bi.svals.insert(bi.svals.end(), rep_bytes.begin() + (size_t)src * c.stride,
@@ -293,8 +393,10 @@ extern "C" int32_t mbc_bitmap_build(mbc_table* t, int32_t col) {
         else bi.ivals.push_back((int32_t)(uint32_t)slots[used_slots[src]]);
     }
     bi.nvalues = D;
-    MBC_TRY(dev_alloc(ctx, (void**)&h.slot_id, (size_t)cap * 4, false));
-    MBC_CUDA(cudaMemcpyAsync(h.slot_id, slot_id.data(), (size_t)cap * 4, cudaMemcpyHostToDevice, ctx->stream));
+    if (!direct) {
+        MBC_TRY(dev_alloc(ctx, (void**)&h.slot_id, (size_t)cap * 4, false));
+        MBC_CUDA(cudaMemcpyAsync(h.slot_id, slot_id.data(), (size_t)cap * 4, cudaMemcpyHostToDevice, ctx->stream));
+    }
 
     // 3. build
     if (D > 0) {
@@ -305,7 +407,7 @@ extern "C" int32_t mbc_bitmap_build(mbc_table* t, int32_t col) {
         if (need > total_b) MBC_FAIL(MBC_ERR_UNSUPPORTED, "bitmap index needs %zu bytes (%lld values x %lld rows), device has %zu",
                                      need, (long long)D, (long long)t->nrows_pad, total_b);
         MBC_TRY(dev_alloc(ctx, (void**)&bi.d_words, need, false));
-        const size_t smem_budget = 200 * 1024;
+        const size_t smem_budget = 100 * 1024;                    // two CTAs per SM: one streams out while the other fills
         // rows per chunk: as many as fit for the values of one pass, power of two in [1024, 8192]
         int R = 8192;
         while (R > 1024 && (size_t)std::min<int64_t>(D, 4096) * (R / 8) > smem_budget) R >>= 1;
@@ -313,6 +415,8 @@ extern "C" int32_t mbc_bitmap_build(mbc_table* t, int32_t col) {
         unsigned int* d_ticket = nullptr;
         MBC_TRY(dev_alloc(ctx, (void**)&d_ticket, 4, true));
         MBC_CUDA(cudaFuncSetAttribute(bitmap_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_budget));
+        MBC_CUDA(cudaStreamSynchronize(ctx->stream));        // the allocation above is not kernel time
+        begin_timing(ctx);
         for (int64_t v0 = 0; v0 < D; v0 += max_nv) {
             BuildParams p{};
             p.h = h;
@@ -335,12 +439,16 @@ extern "C" int32_t mbc_bitmap_build(mbc_table* t, int32_t col) {
             ctx->launches++;
         }
         dev_free(ctx, d_ticket);
+        end_timing(ctx);
+    } else {
+        begin_timing(ctx);
+        end_timing(ctx);
     }
-    end_timing(ctx);
     MBC_CUDA(cudaGetLastError());
     MBC_CUDA(cudaStreamSynchronize(ctx->stream));
     dev_free(ctx, h.slots);
     dev_free(ctx, h.slot_id);
+    dev_free(ctx, d_id_of);
     bi.exists = true;
     return MBC_OK;
 }

@@ -96,6 +96,8 @@ struct mbc_ctx {
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
     int64_t launches = 0;
     float last_ms = 0.f;
+    bool timing_split = false;
+    float extra_ms = 0.f;                // device time of earlier timed segments of the same call
     // per-context scan workspace (tile status words, ticket, partials), grown on demand
     void*   ws = nullptr;
     size_t  ws_bytes = 0;
@@ -153,6 +155,7 @@ void    pinned_release(mbc_ctx* ctx, void* p, size_t bytes);
 int32_t ensure_workspace(mbc_ctx* ctx, size_t bytes);
 void    begin_timing(mbc_ctx* ctx);
 void    end_timing(mbc_ctx* ctx);
+void    split_timing(mbc_ctx* ctx);        // close a timed segment (sync), keep its time, the next begin_timing adds to it
 
 // ---- the select -> compact -> project -> aggregate engine (mbc_scan.cu) ---------------------
 struct ScanRequest {
