@@ -173,6 +173,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = "WARN"        # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
     ctx = mbcol.Context(local_rank)
     stream = torch.cuda.current_stream()
@@ -190,40 +191,23 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     counts = {}
 
     def gather_results(res, sel):
-        """NCCL: aggregates all-reduced, counts all-gathered, the 1% query's positions+values to rank 0."""
-        agg = torch.tensor([res.agg(0)[0], res.agg(1)[0], res.agg(3)[0], res.agg(4)[0]], dtype=torch.int64, device=dev)
-        fsum = torch.tensor([res.agg(2)[1]], dtype=torch.float64, device=dev)
-        sums = agg[:2].clone()
-        dist.all_reduce(sums)
-        dist.all_reduce(fsum)
-        mn, mx = agg[2:3].clone(), agg[3:4].clone()
-        dist.all_reduce(mn, op=dist.ReduceOp.MIN)
-        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-        cnt = torch.tensor([res.count], dtype=torch.int64, device=dev)
-        all_cnt = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
-        dist.all_gather(all_cnt, cnt)
-        if sel != SELECTIVITIES[0]:
-            return
-        all_cnt = [int(c.item()) for c in all_cnt]
+        """mbcol.sharding over NCCL: one all-gather of every rank's [aggregates..., count] block (each rank then folds
+        COUNT/SUM/MIN/MAX locally, which is the all-reduce), and the 1% query's positions + projected values
+        gathered on rank 0 in rank (= position) order."""
+        from mbcol import sharding
         ptrs = res.device_pointers()
+        mine = torch.as_tensor(_CudaArray(ptrs["aggs"], 9 * 8), device=dev).view(torch.int64)      # 8 raw aggregates + count
+        blocks = sharding.allgather_blocks(mine)                                                    # [world, 9] on every rank
+        folded = (blocks[:, 8].sum(), blocks[:, 1].sum(), blocks[:, 2].view(torch.float64).sum(), blocks[:, 3].min(), blocks[:, 4].max())
+        if sel != SELECTIVITIES[0]:
+            return folded
+        counts = [int(c) for c in blocks[:, 8].cpu()]
         bufs = [(ptrs["positions"], 8)] + [res.column_device(i) for i in range(4)]
-        ops, keep = [], []
+        gathered = []
         for ptr, stride in bufs:
-            mine = torch.as_tensor(_CudaArray(ptr, max(res.count, 1) * stride), device=dev)[:res.count * stride]
-            if rank == 0:
-                total = torch.empty(sum(all_cnt) * stride, dtype=torch.uint8, device=dev)
-                total[:all_cnt[0] * stride].copy_(mine)
-                off = all_cnt[0] * stride
-                for r in range(1, world):
-                    ops.append(dist.P2POp(dist.irecv, total[off:off + all_cnt[r] * stride], r))
-                    off += all_cnt[r] * stride
-                keep.append(total)
-            else:
-                ops.append(dist.P2POp(dist.isend, mine, 0))
-                keep.append(mine)
-        if ops:
-            for w in dist.batch_isend_irecv(ops):
-                w.wait()
+            local = torch.as_tensor(_CudaArray(ptr, max(res.count, 1) * stride), device=dev)[:res.count * stride]
+            gathered.append(sharding.gather_rows(local, counts, stride))
+        return folded
 
     def step(record=False):
         for s in SELECTIVITIES:
@@ -333,7 +317,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             "e2e": {"value": e2e_value, "unit": "rows/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "api": "mbc_scan_host (pinned host columns -> chunked H2D + fused scan -> D2H results)"},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "mbc::scan_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "mbc scan = filter_kernel + tile_offsets_kernel + write_kernel + agg_finish_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "frac_of_nominal_8000": achieved / 8000.0, "peak_source": peak_src,
                          "traffic": None, "algorithmic_bytes_per_launch": tot_bytes / 3,
                          "per_selectivity": per_sel},

@@ -1,0 +1,74 @@
+"""TID-range sharding of a scan across ranks: one process per GPU, rows split by contiguous
+position range, no data-path collective.  After the local scans, torch.distributed (NCCL on GPUs, gloo in the CPU
+tests) only moves results: every rank's [aggregates, count] block is all-gathered and folded locally (= the
+all-reduce of COUNT/SUM/MIN/MAX), and position / value lists are gathered on rank 0 at the exclusive-scan offsets
+of the counts -- rank order is position order, so the concatenation is already sorted."""
+from __future__ import annotations
+
+from typing import Optional, Sequence
+
+import torch
+import torch.distributed as dist
+
+TILE = 8192        # shard boundaries are multiples of the column padding (and of the 8000-bit bitmap page grain x tile)
+
+
+def shard_range(total_rows: int, world: int, rank: int) -> tuple[int, int]:
+    """[begin, end) of `rank`: equal tile-aligned slices, the last rank takes the ragged tail."""
+    per = (total_rows + world - 1) // world
+    per = (per + TILE - 1) // TILE * TILE
+    lo = min(total_rows, rank * per)
+    hi = min(total_rows, lo + per) if rank < world - 1 else total_rows
+    return lo, max(lo, hi)
+
+
+def fold_aggregates(blocks: torch.Tensor, kinds: Sequence[int], real: Sequence[bool]) -> list:
+    """blocks: [world, nagg+1] int64 raw 8-byte aggregate values (doubles as bits) + count in the last column.
+    Returns python values [(value, valid)] per aggregate and the total count."""
+    world = blocks.shape[0]
+    counts = blocks[:, -1]
+    total = int(counts.sum())
+    out = []
+    for a, (kind, is_real) in enumerate(zip(kinds, real)):
+        col = blocks[:, a]
+        vals = col.view(torch.float64) if is_real else col
+        nonempty = counts > 0
+        if kind in (0, 1):                                   # COUNT, SUM
+            v = vals.sum()
+            out.append((float(v) if is_real else int(v), True))
+        elif not bool(nonempty.any()):
+            out.append((0.0 if is_real else 0, False))        # MIN/MAX over an empty set
+        else:
+            sel = vals[nonempty]
+            v = sel.min() if kind == 2 else sel.max()
+            out.append((float(v) if is_real else int(v), True))
+    return out, total
+
+
+def allgather_blocks(block: torch.Tensor, group=None) -> torch.Tensor:
+    """Every rank's 1-D block -> [world, len(block)] on every rank (one collective)."""
+    world = dist.get_world_size(group)
+    parts = [torch.empty_like(block) for _ in range(world)]
+    dist.all_gather(parts, block, group=group)
+    return torch.stack(parts)
+
+
+def gather_rows(local: torch.Tensor, counts: Sequence[int], row_bytes: int, dst: int = 0, group=None) -> Optional[torch.Tensor]:
+    """Gather variable-length byte buffers (count[r] * row_bytes each) on `dst` in rank order.  `local` is a 1-D uint8
+    tensor of exactly counts[rank] * row_bytes bytes.  Returns the concatenation on dst, None elsewhere."""
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    if rank == dst:
+        total = torch.empty(sum(counts) * row_bytes, dtype=torch.uint8, device=local.device)
+        offs = [0]
+        for c in counts:
+            offs.append(offs[-1] + c * row_bytes)
+        total[offs[rank]:offs[rank + 1]].copy_(local)
+        ops = [dist.P2POp(dist.irecv, total[offs[r]:offs[r + 1]], r, group) for r in range(world) if r != dst and counts[r] > 0]
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        return total
+    if counts[rank] > 0:
+        for w in dist.batch_isend_irecv([dist.P2POp(dist.isend, local, dst, group)]):
+            w.wait()
+    return None
