@@ -452,52 +452,46 @@ __global__ void __launch_bounds__(kScanThreads, 2) filter_kernel(const __grid_co
 }
 
 // ---- pass 1.5: tile counts -> tile output offsets -----------------------------------------------------------
-// One block; 4096 counts per round (coalesced 128-bit loads, warp-shuffle scans), carry between rounds.
+// One block, one round: every thread owns a contiguous run of counts (all of its 128-bit loads are issued
+// before the first use), a two-level warp-shuffle scan combines the 1024 run totals.
 __global__ void __launch_bounds__(1024) tile_offsets_kernel(const uint32_t* counts, int ntiles, unsigned long long* tile_base,
                                                             long long* running /* in: offset so far, out: + total */) {
     __shared__ unsigned long long s_warp[32];
-    __shared__ unsigned long long s_carry;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) s_carry = (unsigned long long)*running;
-    __syncthreads();
-    for (int base = 0; base < ntiles; base += 4096) {
-        const int i0 = base + tid * 4;
-        uint32_t c[4] = {0, 0, 0, 0};
-        if (i0 + 3 < ntiles) {
-            uint4 q = *reinterpret_cast<const uint4*>(counts + i0);   // counts is 64-byte aligned, i0 a multiple of 4
-            c[0] = q.x; c[1] = q.y; c[2] = q.z; c[3] = q.w;
-        } else {
-            for (int j = 0; j < 4; ++j) if (i0 + j < ntiles) c[j] = counts[i0 + j];
-        }
-        const unsigned long long mine = (unsigned long long)c[0] + c[1] + c[2] + c[3];
-        unsigned long long incl = mine;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            unsigned long long n = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-            if (lane >= o) incl += n;
-        }
-        if (lane == 31) s_warp[warp] = incl;
-        __syncthreads();
-        unsigned long long wsum = s_warp[lane];                    // every warp scans the 32 warp totals itself
-        unsigned long long winc = wsum;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            unsigned long long n = __shfl_up_sync(0xFFFFFFFFu, winc, o);
-            if (lane >= o) winc += n;
-        }
-        const unsigned long long warp_excl = __shfl_sync(0xFFFFFFFFu, winc - wsum, warp);
-        const unsigned long long total = __shfl_sync(0xFFFFFFFFu, winc, 31);
-        unsigned long long run = s_carry + warp_excl + incl - mine;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            if (i0 + j < ntiles) tile_base[i0 + j] = run;
-            run += c[j];
-        }
-        __syncthreads();
-        if (tid == 0) s_carry += total;
-        __syncthreads();
+    const int per = ((ntiles + 1023) / 1024 + 3) & ~3;             // counts per thread, a multiple of 4
+    const int lo = tid * per;
+    unsigned long long mine = 0;
+    for (int i = lo; i < lo + per && i < ntiles; i += 4) {         // the counts buffer is padded: whole quads are readable
+        const uint4 q = *reinterpret_cast<const uint4*>(counts + i);
+        mine += (unsigned long long)q.x + (i + 1 < ntiles ? q.y : 0u) + (i + 2 < ntiles ? q.z : 0u) + (i + 3 < ntiles ? q.w : 0u);
     }
-    if (tid == 0) *running = (long long)s_carry;
+    unsigned long long incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        unsigned long long n = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        if (lane >= o) incl += n;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    unsigned long long wsum = s_warp[lane], winc = wsum;           // every warp scans the 32 warp totals itself
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        unsigned long long n = __shfl_up_sync(0xFFFFFFFFu, winc, o);
+        if (lane >= o) winc += n;
+    }
+    const unsigned long long warp_excl = __shfl_sync(0xFFFFFFFFu, winc - wsum, warp);
+    const unsigned long long total = __shfl_sync(0xFFFFFFFFu, winc, 31);
+    const unsigned long long start = (unsigned long long)*running;
+    unsigned long long run = start + warp_excl + incl - mine;
+    for (int i = lo; i < lo + per && i < ntiles; i += 4) {
+        const uint4 q = *reinterpret_cast<const uint4*>(counts + i);   // L1 hit
+        const uint32_t c[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (i + j < ntiles) { tile_base[i + j] = run; run += c[j]; }
+    }
+    __syncthreads();                                               // everyone has read *running
+    if (tid == 0) *running = (long long)(start + total);
 }
 
 // ---- pass 2: ordered write of the survivors ----------------------------------------------------------------------
