@@ -173,7 +173,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"        # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
+        os.environ.pop("NCCL_DEBUG", None)       # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
     ctx = mbcol.Context(local_rank)
     stream = torch.cuda.current_stream()
@@ -198,16 +198,16 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         ptrs = res.device_pointers()
         mine = torch.as_tensor(_CudaArray(ptrs["aggs"], 9 * 8), device=dev).view(torch.int64)      # 8 raw aggregates + count
         blocks = sharding.allgather_blocks(mine)                                                    # [world, 9] on every rank
-        folded = (blocks[:, 8].sum(), blocks[:, 1].sum(), blocks[:, 2].view(torch.float64).sum(), blocks[:, 3].min(), blocks[:, 4].max())
+        sums = blocks.sum(0)                                   # COUNT (col 8) and SUM(I2) (col 1) of the whole table
+        folded = (sums, blocks[:, 2].view(torch.float64).sum(), blocks[:, 3].min(), blocks[:, 4].max())
         if sel != SELECTIVITIES[0]:
             return folded
         counts = [int(c) for c in blocks[:, 8].cpu()]
         bufs = [(ptrs["positions"], 8)] + [res.column_device(i) for i in range(4)]
-        gathered = []
-        for ptr, stride in bufs:
-            local = torch.as_tensor(_CudaArray(ptr, max(res.count, 1) * stride), device=dev)[:res.count * stride]
-            gathered.append(sharding.gather_rows(local, counts, stride))
-        return folded
+        locals_ = [(torch.as_tensor(_CudaArray(ptr, max(res.count, 1) * stride), device=dev)[:res.count * stride], stride)
+                   for ptr, stride in bufs]
+        gathered = sharding.gather_rows_multi(locals_, counts)     # rank 0: the 1% result of the whole table, in position order
+        return folded, gathered
 
     def step(record=False):
         for s in SELECTIVITIES:

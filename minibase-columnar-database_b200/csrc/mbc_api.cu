@@ -119,6 +119,7 @@ int32_t mbc_init(int32_t device_id, mbc_ctx** out) {
     ctx->sm_count = prop.multiProcessorCount;
     MBC_CUDA(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
     MBC_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    MBC_CUDA(cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking));
     ctx->stream = ctx->own_stream;
     MBC_CUDA(cudaEventCreate(&ctx->ev_begin));
     MBC_CUDA(cudaEventCreate(&ctx->ev_end));
@@ -142,6 +143,7 @@ void mbc_shutdown(mbc_ctx* ctx) {
     cudaEventDestroy(ctx->ev_end);
     cudaStreamDestroy(ctx->own_stream);
     cudaStreamDestroy(ctx->copy_stream);
+    cudaStreamDestroy(ctx->d2h_stream);
     delete ctx;
 }
 

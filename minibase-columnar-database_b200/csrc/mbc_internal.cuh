@@ -93,6 +93,7 @@ struct mbc_ctx {
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;       // where kernels go (own_stream unless mbc_set_stream)
     cudaStream_t copy_stream = nullptr;  // H2D staging of mbc_scan_host
+    cudaStream_t d2h_stream = nullptr;   // results of mbc_scan_host streaming back while later chunks upload
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
     int64_t launches = 0;
     float last_ms = 0.f;

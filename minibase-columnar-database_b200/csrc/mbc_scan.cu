@@ -362,7 +362,8 @@ static int32_t launch_job(ScanJob* job, int tile_base, bool first) {
     return MBC_OK;
 }
 
-static int32_t finish_job(ScanJob* job, int64_t tiles_done) {
+// aggregate finish + count/aggregate readback (device work of a job is complete after this)
+static int32_t finish_job_device(ScanJob* job, int64_t tiles_done) {
     mbc_ctx* ctx = job->r->ctx;
     ScanParams& p = job->p;
     mbc_result* r = job->r;
@@ -371,7 +372,7 @@ static int32_t finish_job(ScanJob* job, int64_t tiles_done) {
         AggList list;
         memcpy(list.g, p.aggs, sizeof(list.g));
         agg_finish_kernel<<<p.nagg, 1024, 0, ctx->stream>>>(job->w.partials, (int)job->total_tiles, (int)tiles_done, list,
-                                                          job->w.agg_out);
+                                                           job->w.agg_out);
         ctx->launches++;
         MBC_CUDA(cudaGetLastError());
     }
@@ -384,7 +385,12 @@ static int32_t finish_job(ScanJob* job, int64_t tiles_done) {
     MBC_CUDA(cudaStreamSynchronize(ctx->stream));
     r->count = (int64_t)host_small[kMaxAgg];
     decode_aggs(r, p.aggs, p.nagg, host_small);
-    return finish_result_host(r);
+    return MBC_OK;
+}
+
+static int32_t finish_job(ScanJob* job, int64_t tiles_done) {
+    MBC_TRY(finish_job_device(job, tiles_done));
+    return finish_result_host(job->r);
 }
 
 int32_t run_scan(const ScanRequest& rq, mbc_result** out) {
@@ -474,6 +480,48 @@ static int32_t run_scan_host(mbc_ctx* ctx, int32_t ncols, const mbc_coldesc* col
     cudaStreamWaitEvent(ctx->copy_stream, ev_init, 0);
     cudaEventDestroy(ev_init);
 
+    // Results stream back while later chunks are still uploading (PCIe is full duplex): after every chunk the running
+    // count comes to the host, and the rows that chunk appended are copied out on a third stream.  The pinned result
+    // buffers are sized from the first chunk's selectivity (x1.3); if the estimate is exceeded the rest is copied at the end.
+    mbc_result* r = job.r;
+    const bool stream_out = (rq.want & MBC_WANT_HOST) && (rq.want & (MBC_WANT_POSITIONS | MBC_WANT_COLUMNS)) && nchunks > 2;
+    long long* h_counts = nullptr;
+    if (stream_out) {
+        s = pinned_for(r, (void**)&h_counts, (size_t)(nchunks + 1) * 8);
+        if (s != MBC_OK) { mbc_result_free(job.r); cleanup(); return s; }
+    }
+    int64_t out_cap = -1, copied = 0;
+    bool out_overflow = false;
+    auto copy_rows = [&](int64_t from, int64_t to) -> int32_t {          // rows [from, to) of every host-visible buffer
+        if (to <= from) return MBC_OK;
+        const size_t n = (size_t)(to - from);
+        if (r->h_pos) MBC_CUDA(cudaMemcpyAsync(r->h_pos + from, r->d_pos + from, n * 8, cudaMemcpyDeviceToHost, ctx->d2h_stream));
+        if (rq.want & MBC_WANT_COLUMNS)
+            for (auto& c : r->cols) {
+                if (c.stride == c.width)
+                    MBC_CUDA(cudaMemcpyAsync((char*)c.h + (size_t)from * c.width, (char*)c.d + (size_t)from * c.stride, n * c.width,
+                                             cudaMemcpyDeviceToHost, ctx->d2h_stream));
+                else
+                    MBC_CUDA(cudaMemcpy2DAsync((char*)c.h + (size_t)from * c.width, c.width, (char*)c.d + (size_t)from * c.stride, c.stride,
+                                               c.width, n, cudaMemcpyDeviceToHost, ctx->d2h_stream));
+            }
+        return MBC_OK;
+    };
+    auto drain = [&](int64_t k) -> int32_t {                              // chunk k has finished on the device
+        MBC_CUDA(cudaEventSynchronize(ev_done[k & 1]));
+        const int64_t c = h_counts[k];
+        if (out_cap < 0) {
+            out_cap = std::min<int64_t>(nrows, (int64_t)((double)c / (double)(k + 1) * (double)nchunks * 1.3) + 65536);
+            if ((rq.want & MBC_WANT_POSITIONS) && r->d_pos) MBC_TRY(pinned_for(r, (void**)&r->h_pos, (size_t)out_cap * 8));
+            if (rq.want & MBC_WANT_COLUMNS)
+                for (auto& col : r->cols) MBC_TRY(pinned_for(r, &col.h, (size_t)out_cap * col.width));
+        }
+        if (out_overflow || c > out_cap) { out_overflow = true; return MBC_OK; }
+        MBC_TRY(copy_rows(copied, c));
+        copied = c;
+        return MBC_OK;
+    };
+
     begin_timing(ctx);
     int64_t tiles_done = 0;
     for (int64_t k = 0; k < nchunks && s == MBC_OK; ++k) {
@@ -500,10 +548,36 @@ static int32_t run_scan_host(mbc_ctx* ctx, int32_t ncols, const mbc_coldesc* col
         bind_table(&job, st);
         s = launch_job(&job, (int)tiles_done, k == 0);
         tiles_done += job.p.ntiles;
+        if (stream_out && s == MBC_OK &&
+            cudaMemcpyAsync(&h_counts[k], job.w.count, 8, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) s = MBC_ERR_CUDA;
         cudaEventRecord(ev_done[b], ctx->stream);
+        // chunk k is queued; now that the copy engine is busy with it, hand chunk k-1's rows to the D2H stream
+        if (stream_out && s == MBC_OK && k >= 1) s = drain(k - 1);
     }
-    if (s == MBC_OK) s = finish_job(&job, tiles_done);
+    if (s == MBC_OK && stream_out) {
+        s = finish_job_device(&job, tiles_done);
+        if (s == MBC_OK) {
+            if (out_cap >= 0 && !out_overflow && r->count <= out_cap) {
+                s = copy_rows(copied, r->count);                          // the tail, then everything has landed
+                if (s == MBC_OK && cudaStreamSynchronize(ctx->d2h_stream) != cudaSuccess) s = MBC_ERR_CUDA;
+                if (s == MBC_OK && (rq.want & MBC_WANT_TUPLES)) {
+                    const uint32_t keep = r->want;
+                    r->want = MBC_WANT_TUPLES | MBC_WANT_HOST;            // only the tuple bytes are still missing
+                    s = finish_result_host(r);
+                    r->want = keep;
+                }
+            } else {
+                cudaStreamSynchronize(ctx->d2h_stream);
+                r->h_pos = nullptr;                                       // estimate exceeded: plain copy of the final result
+                for (auto& c : r->cols) c.h = nullptr;
+                s = finish_result_host(r);
+            }
+        }
+    } else if (s == MBC_OK) {
+        s = finish_job(&job, tiles_done);
+    }
     cudaStreamSynchronize(ctx->copy_stream);
+    cudaStreamSynchronize(ctx->d2h_stream);
     cudaStreamSynchronize(ctx->stream);
     cleanup();
     if (s != MBC_OK) { if (job.r) mbc_result_free(job.r); return s; }

@@ -48,27 +48,39 @@ def fold_aggregates(blocks: torch.Tensor, kinds: Sequence[int], real: Sequence[b
 def allgather_blocks(block: torch.Tensor, group=None) -> torch.Tensor:
     """Every rank's 1-D block -> [world, len(block)] on every rank (one collective)."""
     world = dist.get_world_size(group)
+    if block.is_cuda:                                        # NCCL: one call, no per-rank tensors
+        out = torch.empty(world * block.numel(), dtype=block.dtype, device=block.device)
+        dist.all_gather_into_tensor(out, block, group=group)
+        return out.view(world, block.numel())
     parts = [torch.empty_like(block) for _ in range(world)]
     dist.all_gather(parts, block, group=group)
     return torch.stack(parts)
 
 
-def gather_rows(local: torch.Tensor, counts: Sequence[int], row_bytes: int, dst: int = 0, group=None) -> Optional[torch.Tensor]:
-    """Gather variable-length byte buffers (count[r] * row_bytes each) on `dst` in rank order.  `local` is a 1-D uint8
-    tensor of exactly counts[rank] * row_bytes bytes.  Returns the concatenation on dst, None elsewhere."""
+def gather_rows_multi(locals_: Sequence[tuple], counts: Sequence[int], dst: int = 0, group=None) -> Optional[list]:
+    """Gather several variable-length byte buffers at once (positions + every projected column) on `dst` in rank
+    order with ONE batch of point-to-point operations.  locals_ = [(1-D uint8 tensor of counts[rank]*row_bytes bytes,
+    row_bytes)].  Returns the concatenations on dst, None elsewhere."""
     rank, world = dist.get_rank(group), dist.get_world_size(group)
-    if rank == dst:
-        total = torch.empty(sum(counts) * row_bytes, dtype=torch.uint8, device=local.device)
-        offs = [0]
-        for c in counts:
-            offs.append(offs[-1] + c * row_bytes)
-        total[offs[rank]:offs[rank + 1]].copy_(local)
-        ops = [dist.P2POp(dist.irecv, total[offs[r]:offs[r + 1]], r, group) for r in range(world) if r != dst and counts[r] > 0]
-        if ops:
-            for w in dist.batch_isend_irecv(ops):
-                w.wait()
-        return total
-    if counts[rank] > 0:
-        for w in dist.batch_isend_irecv([dist.P2POp(dist.isend, local, dst, group)]):
+    ops, totals = [], []
+    for local, row_bytes in locals_:
+        if rank == dst:
+            total = torch.empty(sum(counts) * row_bytes, dtype=torch.uint8, device=local.device)
+            offs = [0]
+            for c in counts:
+                offs.append(offs[-1] + c * row_bytes)
+            total[offs[rank]:offs[rank + 1]].copy_(local)
+            ops += [dist.P2POp(dist.irecv, total[offs[r]:offs[r + 1]], r, group) for r in range(world) if r != dst and counts[r] > 0]
+            totals.append(total)
+        elif counts[rank] > 0:
+            ops.append(dist.P2POp(dist.isend, local, dst, group))
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
             w.wait()
-    return None
+    return totals if rank == dst else None
+
+
+def gather_rows(local: torch.Tensor, counts: Sequence[int], row_bytes: int, dst: int = 0, group=None) -> Optional[torch.Tensor]:
+    """Single-buffer form of gather_rows_multi."""
+    out = gather_rows_multi([(local, row_bytes)], counts, dst, group)
+    return out[0] if out is not None else None
