@@ -190,34 +190,42 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     kernel_ms = {s: [] for s in SELECTIVITIES}
     counts = {}
 
-    def gather_results(res, sel):
-        """mbcol.sharding over NCCL: one all-gather of every rank's [aggregates..., count] block (each rank then folds
-        COUNT/SUM/MIN/MAX locally, which is the all-reduce), and the 1% query's positions + projected values
-        gathered on rank 0 in rank (= position) order."""
+    def exchange_step(results):
+        """mbcol.sharding over NCCL, once per step: ONE all-gather of every rank's [aggregates..., count] blocks of the
+        three scans (each rank then folds COUNT/SUM/MIN/MAX locally, which is the all-reduce), then the 1% query's
+        positions + projected values are gathered on rank 0 in rank (= position) order with one batch of P2P ops."""
         from mbcol import sharding
-        ptrs = res.device_pointers()
-        mine = torch.as_tensor(_CudaArray(ptrs["aggs"], 9 * 8), device=dev).view(torch.int64)      # 8 raw aggregates + count
-        blocks = sharding.allgather_blocks(mine)                                                    # [world, 9] on every rank
-        sums = blocks.sum(0)                                   # COUNT (col 8) and SUM(I2) (col 1) of the whole table
-        folded = (sums, blocks[:, 2].view(torch.float64).sum(), blocks[:, 3].min(), blocks[:, 4].max())
-        if sel != SELECTIVITIES[0]:
-            return folded
-        counts = [int(c) for c in blocks[:, 8].cpu()]
-        bufs = [(ptrs["positions"], 8)] + [res.column_device(i) for i in range(4)]
+        mine = torch.cat([torch.as_tensor(_CudaArray(r.device_pointers()["aggs"], 9 * 8), device=dev).view(torch.int64) for r in results])
+        blocks = sharding.allgather_blocks(mine).view(world, len(results), 9)      # every rank sees every rank's partials
+        sums = blocks.sum(0)                                    # per scan: COUNT (col 8), SUM(I2) (col 1)
+        folded = (sums, blocks[:, :, 2].view(torch.float64).sum(0), blocks[:, :, 3].amin(0), blocks[:, :, 4].amax(0))
+        res = results[0]                                        # the 1% scan
+        cnts = [int(c) for c in blocks[:, 0, 8].cpu()]
+        bufs = [(res.device_pointers()["positions"], 8)] + [res.column_device(i) for i in range(4)]
         locals_ = [(torch.as_tensor(_CudaArray(ptr, max(res.count, 1) * stride), device=dev)[:res.count * stride], stride)
                    for ptr, stride in bufs]
-        gathered = sharding.gather_rows_multi(locals_, counts)     # rank 0: the 1% result of the whole table, in position order
+        gathered = sharding.gather_rows_multi(locals_, cnts)    # rank 0: the whole table's 1% result, in position order
         return folded, gathered
 
+    dbg = {"scan": 0.0, "exchange": 0.0} if os.environ.get("MBC_BENCH_DEBUG") else None
+
     def step(record=False):
+        t0 = time.perf_counter()
+        results = []
         for s in SELECTIVITIES:
             res = table.scan(terms[s], proj=[0, 1, 2, 3], want=want_dev, aggs=AGGS)
             if record:
                 kernel_ms[s].append(ctx.last_kernel_ms)
                 counts[s] = res.count
-            if world > 1:
-                gather_results(res, s)
+            results.append(res)
+        t1 = time.perf_counter()
+        if world > 1:
+            exchange_step(results)
+        for res in results:
             res.close()
+        if dbg is not None and record:
+            dbg["scan"] += t1 - t0
+            dbg["exchange"] += time.perf_counter() - t1
 
     def barrier():
         if world > 1:
@@ -284,6 +292,8 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
     e2e_value = 3.0 * rows * world * e2e_steps / (float(e2e_t.item()) * 1e-3)
     clocks = sampler.stop() if rank == 0 else None
+    if dbg is not None:
+        print(f"[bench debug] rank {rank}: per step ms: " + ", ".join(f"{k}={1e3 * v / args.steps:.3f}" for k, v in dbg.items()), file=sys.stderr)
 
     if rank == 0:
         peak, peak_src = measured_peak_gbs()

@@ -57,10 +57,11 @@ def allgather_blocks(block: torch.Tensor, group=None) -> torch.Tensor:
     return torch.stack(parts)
 
 
-def gather_rows_multi(locals_: Sequence[tuple], counts: Sequence[int], dst: int = 0, group=None) -> Optional[list]:
+def gather_rows_multi(locals_: Sequence[tuple], counts: Sequence[int], dst: int = 0, group=None, wait: bool = True):
     """Gather several variable-length byte buffers at once (positions + every projected column) on `dst` in rank
     order with ONE batch of point-to-point operations.  locals_ = [(1-D uint8 tensor of counts[rank]*row_bytes bytes,
-    row_bytes)].  Returns the concatenations on dst, None elsewhere."""
+    row_bytes)].  Returns the concatenations on dst, None elsewhere; with wait=False returns (work handles, concatenations)
+    and the caller waits (the transfers then overlap whatever is launched next)."""
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     ops, totals = [], []
     for local, row_bytes in locals_:
@@ -74,9 +75,11 @@ def gather_rows_multi(locals_: Sequence[tuple], counts: Sequence[int], dst: int 
             totals.append(total)
         elif counts[rank] > 0:
             ops.append(dist.P2POp(dist.isend, local, dst, group))
-    if ops:
-        for w in dist.batch_isend_irecv(ops):
-            w.wait()
+    works = dist.batch_isend_irecv(ops) if ops else []
+    if not wait:
+        return works, (totals if rank == dst else None)
+    for w in works:
+        w.wait()
     return totals if rank == dst else None
 
 
