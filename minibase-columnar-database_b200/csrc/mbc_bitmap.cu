@@ -18,6 +18,7 @@
 // then streamed out with 128-bit stores, R/8 contiguous bytes per value.  The kernel is bound by
 // HBM writes: D*N/8 bytes out for 4*N bytes in.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 
@@ -43,11 +44,33 @@ constexpr uint32_t kMaxDirectRange = 1u << 16;
 
 __global__ void __launch_bounds__(256) column_minmax_kernel(const int32_t* col, int64_t nrows, const uint32_t* deleted, long long* out) {
     long long mn = INT64_MAX, mx = INT64_MIN;
-    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < nrows; r += (int64_t)gridDim.x * blockDim.x) {
-        if (deleted && ((deleted[r >> 5] >> (r & 31)) & 1u)) continue;
-        long long k = col[r];
-        mn = min(mn, k);
-        mx = max(mx, k);
+    const int64_t step = (int64_t)gridDim.x * blockDim.x;
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (!deleted) {                                                  // 128-bit loads, two in flight (columns are padded to 8192 rows)
+        const int64_t nq = nrows >> 2;
+        const int4* c4 = reinterpret_cast<const int4*>(col);
+        int64_t q = r;
+        for (; q + step < nq; q += 2 * step) {
+            const int4 a = __ldg(c4 + q), b = __ldg(c4 + q + step);
+            int lo = min(min(min(a.x, a.y), min(a.z, a.w)), min(min(b.x, b.y), min(b.z, b.w)));
+            int hi = max(max(max(a.x, a.y), max(a.z, a.w)), max(max(b.x, b.y), max(b.z, b.w)));
+            mn = min(mn, (long long)lo);
+            mx = max(mx, (long long)hi);
+        }
+        for (; q < nq; q += step) {
+            const int4 a = __ldg(c4 + q);
+            mn = min(mn, (long long)min(min(a.x, a.y), min(a.z, a.w)));
+            mx = max(mx, (long long)max(max(a.x, a.y), max(a.z, a.w)));
+        }
+        r = (nq << 2) + r;                                           // ragged tail below
+        for (; r < nrows; r += step) { mn = min(mn, (long long)col[r]); mx = max(mx, (long long)col[r]); }
+    } else {
+        for (; r < nrows; r += step) {
+            if ((deleted[r >> 5] >> (r & 31)) & 1u) continue;
+            long long k = col[r];
+            mn = min(mn, k);
+            mx = max(mx, k);
+        }
     }
     for (int o = 16; o > 0; o >>= 1) {
         mn = min(mn, __shfl_xor_sync(0xFFFFFFFFu, mn, o));
@@ -66,7 +89,24 @@ __global__ void __launch_bounds__(256) column_presence_kernel(const int32_t* col
     const uint32_t words = (range + 31) / 32;
     for (uint32_t i = threadIdx.x; i < words; i += blockDim.x) sh[i] = 0;
     __syncthreads();
-    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < nrows; r += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t step = (int64_t)gridDim.x * blockDim.x;
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (!deleted) {                                                  // 128-bit loads; the bit is almost always already set
+        const int64_t nq = nrows >> 2;
+        const int4* c4 = reinterpret_cast<const int4*>(col);
+        for (int64_t q = r; q < nq; q += step) {
+            const int4 a = __ldg(c4 + q);
+            const int v[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t k = (uint32_t)((long long)v[j] - kmin);
+                const uint32_t bit = 1u << (k & 31);
+                if (!(sh[k >> 5] & bit)) atomicOr(&sh[k >> 5], bit);
+            }
+        }
+        r = (nq << 2) + r;
+    }
+    for (; r < nrows; r += step) {
         if (deleted && ((deleted[r >> 5] >> (r & 31)) & 1u)) continue;
         const uint32_t k = (uint32_t)((long long)col[r] - kmin);
         const uint32_t bit = 1u << (k & 31);
@@ -150,7 +190,8 @@ struct BuildParams {
     HashTab h;
     const void* col;
     const uint32_t* deleted;
-    uint32_t* bitmaps;        // [nvalues][words_pad]
+    uint32_t* bitmaps;        // [chunk][nvalues_total][chunk_rows/32]
+    int64_t nvalues_total;
     int64_t nrows;
     int64_t words_pad;
     int64_t nchunks;
@@ -160,48 +201,76 @@ struct BuildParams {
     unsigned int* ticket;
 };
 
+constexpr int kMaxPerThread = 8192 / kBuildThreads;        // rows of one chunk a thread handles (chunk_rows <= 8192)
+
 __global__ void __launch_bounds__(kBuildThreads, 2) bitmap_build_kernel(const __grid_constant__ BuildParams p) {
     extern __shared__ uint4 sm4[];
     uint32_t* sm = reinterpret_cast<uint32_t*>(sm4);
-    __shared__ long long s_chunk;
     const int wpc = p.chunk_rows >> 5;                    // words per value per chunk
-    const int total_words = p.nv * wpc;
+    const int total_quads = p.nv * wpc / 4;
     const int lane = threadIdx.x & 31;
+    const int per = p.chunk_rows / kBuildThreads;         // 2..16 rows per thread per chunk
+    const bool fast = p.h.direct && !p.deleted;
+    const int32_t* col32 = reinterpret_cast<const int32_t*>(p.col);
 
-    while (true) {
-        if (threadIdx.x == 0) s_chunk = (long long)atomicAdd(p.ticket, 1u);
-        __syncthreads();
-        const int64_t chunk = s_chunk;
-        if (chunk >= p.nchunks) break;
-        for (int i = threadIdx.x; i < total_words / 4; i += kBuildThreads) sm4[i] = make_uint4(0, 0, 0, 0);
-        __syncthreads();
+    for (int i = threadIdx.x; i < total_quads; i += kBuildThreads) sm4[i] = make_uint4(0, 0, 0, 0);
 
+    // chunks are assigned statically (no CTA depends on another); the column values of the NEXT chunk are
+    // loaded while the current chunk's matrix streams out, so their HBM latency is off the critical path
+    int32_t pv[kMaxPerThread];
+    int64_t chunk = blockIdx.x;
+    if (fast && chunk < p.nchunks) {
+#pragma unroll
+        for (int q = 0; q < kMaxPerThread; ++q)
+            if (q < per) pv[q] = col32[chunk * p.chunk_rows + threadIdx.x + q * kBuildThreads];   // columns are padded: in bounds
+    }
+    __syncthreads();
+    for (; chunk < p.nchunks; chunk += gridDim.x) {
         const int64_t row0 = chunk * p.chunk_rows;
-        for (int r = threadIdx.x; r < p.chunk_rows; r += kBuildThreads) {   // a warp's 32 rows = one word column
-            const int64_t row = row0 + r;
-            int id = -1;
-            if (row < p.nrows && !(p.deleted && ((p.deleted[row >> 5] >> (row & 31)) & 1u))) {
-                if (p.h.direct) {
-                    id = (int)__ldg(p.h.id_of + (uint32_t)((long long)reinterpret_cast<const int32_t*>(p.col)[row] - p.h.kmin)) - p.v0;
-                } else {
-                    int s = probe<false>(p.h, p.col, p.stride, p.is_str != 0, row);
-                    if (s >= 0) id = (int)p.h.slot_id[s] - p.v0;
+        if (fast) {
+#pragma unroll
+            for (int q = 0; q < kMaxPerThread; ++q) {
+                if (q < per) {                                              // warp-uniform
+                    const int r = threadIdx.x + q * kBuildThreads;          // a warp's 32 rows = one word column
+                    int id = -1;
+                    if (row0 + r < p.nrows) {
+                        id = (int)__ldg(p.h.id_of + (uint32_t)((long long)pv[q] - p.h.kmin)) - p.v0;
+                        if (id < 0 || id >= p.nv) id = -1;
+                    }
+                    const uint32_t group = __match_any_sync(0xFFFFFFFFu, id);
+                    if (id >= 0 && (group & ((1u << lane) - 1)) == 0) sm[id * wpc + (r >> 5)] = group;   // leader of its value group
                 }
-                if (id < 0 || id >= p.nv) id = -1;
             }
-            const uint32_t group = __match_any_sync(0xFFFFFFFFu, id);
-            if (id >= 0 && (group & ((1u << lane) - 1)) == 0)               // leader of its value group
-                sm[id * wpc + (r >> 5)] = group;
+        } else {
+            for (int r = threadIdx.x; r < p.chunk_rows; r += kBuildThreads) {
+                const int64_t row = row0 + r;
+                int id = -1;
+                if (row < p.nrows && !(p.deleted && ((p.deleted[row >> 5] >> (row & 31)) & 1u))) {
+                    if (p.h.direct) {
+                        id = (int)__ldg(p.h.id_of + (uint32_t)((long long)col32[row] - p.h.kmin)) - p.v0;
+                    } else {
+                        int s = probe<false>(p.h, p.col, p.stride, p.is_str != 0, row);
+                        if (s >= 0) id = (int)p.h.slot_id[s] - p.v0;
+                    }
+                    if (id < 0 || id >= p.nv) id = -1;
+                }
+                const uint32_t group = __match_any_sync(0xFFFFFFFFu, id);
+                if (id >= 0 && (group & ((1u << lane) - 1)) == 0) sm[id * wpc + (r >> 5)] = group;
+            }
         }
         __syncthreads();
-
-        // stream the finished words out: wpc*4 contiguous bytes per value
-        const int qshift = 31 - __clz(wpc >> 2);               // quads per value is a power of two
-        const int qmask = (wpc >> 2) - 1;
-        uint32_t* dst0 = p.bitmaps + (int64_t)p.v0 * p.words_pad + chunk * wpc;
-        for (int i = threadIdx.x; i < total_words / 4; i += kBuildThreads) {
-            const int v = i >> qshift, q = i & qmask;
-            reinterpret_cast<uint4*>(dst0 + (int64_t)v * p.words_pad)[q] = sm4[i];
+        const int64_t next = chunk + gridDim.x;
+        if (fast && next < p.nchunks) {
+#pragma unroll
+            for (int q = 0; q < kMaxPerThread; ++q)
+                if (q < per) pv[q] = col32[next * p.chunk_rows + threadIdx.x + q * kBuildThreads];
+        }
+        // chunk-major layout: this pass's values of this chunk are ONE contiguous block; the matrix is zeroed for
+        // the next chunk in the same sweep
+        uint4* dst4 = reinterpret_cast<uint4*>(p.bitmaps + ((int64_t)chunk * p.nvalues_total + p.v0) * wpc);
+        for (int i = threadIdx.x; i < total_quads; i += kBuildThreads) {
+            dst4[i] = sm4[i];
+            sm4[i] = make_uint4(0, 0, 0, 0);
         }
         __syncthreads();
     }
@@ -211,29 +280,35 @@ __global__ void __launch_bounds__(kBuildThreads, 2) bitmap_build_kernel(const __
 
 constexpr int kMaxInlineBitmaps = 96;
 
+struct BmRef {                            // one value's bitmap inside a chunk-major index
+    const uint4* base;                    // first piece (chunk 0); NULL = empty bitmap (value never indexed)
+    uint32_t stride_quads;                // distance between consecutive pieces, in 16-byte units
+    uint32_t qshift;                      // log2(quads per piece)
+};
+
 struct CnfParams {
     int64_t nquads;                       // words_pad / 4
     uint4* out;
     const uint4* deleted;
-    const uint4* const* list;             // device list when there are more than kMaxInlineBitmaps
+    const BmRef* list;                    // device list when there are more than kMaxInlineBitmaps
     int32_t nconj, nbitmaps;
     int32_t conj_end[kMaxTerms];          // exclusive end index of each conjunct in the bitmap list
-    const uint4* inl[kMaxInlineBitmaps];  // NULL pointer = empty bitmap (value never indexed)
+    BmRef inl[kMaxInlineBitmaps];
 };
 
 __global__ void __launch_bounds__(256) bitmap_cnf_kernel(const __grid_constant__ CnfParams p) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t step = (int64_t)gridDim.x * blockDim.x;
-    const uint4* const* list = p.list ? p.list : p.inl;
+    const BmRef* list = p.list ? p.list : p.inl;
     for (; i < p.nquads; i += step) {
         uint4 acc = make_uint4(~0u, ~0u, ~0u, ~0u);
         int j = 0;
         for (int g = 0; g < p.nconj; ++g) {
             uint4 d = make_uint4(0, 0, 0, 0);
             for (; j < p.conj_end[g]; ++j) {
-                const uint4* bm = list[j];
-                if (bm) {
-                    uint4 w = __ldg(bm + i);
+                const BmRef bm = list[j];
+                if (bm.base) {
+                    const uint4 w = __ldg(bm.base + (i >> bm.qshift) * bm.stride_quads + (i & ((1u << bm.qshift) - 1)));
                     d.x |= w.x; d.y |= w.y; d.z |= w.z; d.w |= w.w;
                 }
             }
@@ -411,7 +486,12 @@ extern "C" int32_t mbc_bitmap_build(mbc_table* t, int32_t col) {
         // rows per chunk: as many as fit for the values of one pass, power of two in [1024, 8192]
         int R = 8192;
         while (R > 1024 && (size_t)std::min<int64_t>(D, 4096) * (R / 8) > smem_budget) R >>= 1;
+        if (const char* e = getenv("MBC_BM_CHUNK_ROWS")) {          // tuning knob: longer per-value segments, more passes
+            int v = atoi(e);
+            if (v == 1024 || v == 2048 || v == 4096 || v == 8192) R = v;
+        }
         const int max_nv = (int)std::min<int64_t>(D, (int64_t)(smem_budget / (R / 8)));
+        bi.chunk_rows = R;
         unsigned int* d_ticket = nullptr;
         MBC_TRY(dev_alloc(ctx, (void**)&d_ticket, 4, true));
         MBC_CUDA(cudaFuncSetAttribute(bitmap_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_budget));
@@ -423,6 +503,7 @@ extern "C" int32_t mbc_bitmap_build(mbc_table* t, int32_t col) {
             p.col = c.d;
             p.deleted = deleted;
             p.bitmaps = bi.d_words;
+            p.nvalues_total = D;
             p.nrows = t->nrows;
             p.words_pad = t->words_pad;
             p.chunk_rows = R;
@@ -434,7 +515,9 @@ extern "C" int32_t mbc_bitmap_build(mbc_table* t, int32_t col) {
             p.ticket = d_ticket;
             MBC_CUDA(cudaMemsetAsync(d_ticket, 0, 4, ctx->stream));
             size_t smem = (size_t)p.nv * (R / 8);
-            int grid = (int)std::min<int64_t>(p.nchunks, ctx->sm_count);
+            int per_sm = 1;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bitmap_build_kernel, kBuildThreads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+            int grid = (int)std::min<int64_t>(p.nchunks, (int64_t)ctx->sm_count * per_sm);
             bitmap_build_kernel<<<grid, kBuildThreads, smem, ctx->stream>>>(p);
             ctx->launches++;
         }
@@ -496,8 +579,15 @@ extern "C" int32_t mbc_bitmap_get(mbc_table* t, int32_t col, const void* value, 
     memset(out_words, 0, (size_t)nwords * 8);
     int64_t k = find_value(t, col, value);
     if (k < 0) return MBC_OK;                            // Columnarfile.java:1103-1127: empty BitMapFile
-    int64_t n = std::min<int64_t>(nwords, t->words_pad / 2);
-    MBC_CUDA(cudaMemcpyAsync(out_words, bi.d_words + k * t->words_pad, (size_t)n * 8, cudaMemcpyDeviceToHost, t->ctx->stream));
+    // the value's bitmap is one chunk_rows/8-byte piece per chunk: a pitched copy gathers them
+    const int64_t wpc = bi.chunk_rows / 32;
+    const int64_t nchunks = t->nrows_pad / bi.chunk_rows;
+    std::vector<uint32_t> tmp((size_t)(nchunks * wpc));
+    MBC_CUDA(cudaMemcpy2DAsync(tmp.data(), (size_t)wpc * 4, bi.d_words + k * wpc, (size_t)bi.nvalues * wpc * 4, (size_t)wpc * 4,
+                               (size_t)nchunks, cudaMemcpyDeviceToHost, t->ctx->stream));
+    MBC_CUDA(cudaStreamSynchronize(t->ctx->stream));
+    memcpy(out_words, tmp.data(), (size_t)std::min<int64_t>(nwords * 8, (int64_t)tmp.size() * 4));
+    return MBC_OK;
     MBC_CUDA(cudaStreamSynchronize(t->ctx->stream));
     return MBC_OK;
 }
@@ -517,7 +607,17 @@ static bool value_selected(int op, int cmp /* sign of compare(indexed value, lit
     }
 }
 
-int32_t resolve_bitmap_terms(mbc_table* t, const mbc_term* terms, int32_t nterms, std::vector<const uint4*>* list,
+static BmRef bm_ref(const BitmapIndex& bi, int64_t v) {
+    BmRef r;
+    const uint32_t wpc = (uint32_t)bi.chunk_rows / 32;
+    r.base = reinterpret_cast<const uint4*>(bi.d_words + v * wpc);
+    r.stride_quads = (uint32_t)(bi.nvalues * wpc / 4);
+    r.qshift = 0;
+    while ((1u << r.qshift) < wpc / 4) ++r.qshift;
+    return r;
+}
+
+int32_t resolve_bitmap_terms(mbc_table* t, const mbc_term* terms, int32_t nterms, std::vector<BmRef>* list,
                              std::vector<int>* conj_end) {
     if (nterms <= 0) MBC_FAIL(MBC_ERR_ARG, "bitmap scan needs at least one term (ColumnarIndexScan dereferences selects[0])");
     for (int k = 0; k < nterms; ++k) {
@@ -541,16 +641,16 @@ int32_t resolve_bitmap_terms(mbc_table* t, const mbc_term* terms, int32_t nterms
                 // String.compareTo over zero padded bytes; an over-long literal can only be greater on a tie
                 int cmp = memcmp(bi.svals.data() + v * c.width, lit.data(), c.width);
                 if (cmp == 0 && s.rhs.lit_slen > c.width) cmp = -1;
-                if (value_selected(s.op, cmp)) list->push_back(reinterpret_cast<const uint4*>(bi.d_words + v * t->words_pad));
+                if (value_selected(s.op, cmp)) list->push_back(bm_ref(bi, v));
             }
         } else {
             if (s.rhs.type != MBC_ATTR_INTEGER) MBC_FAIL(MBC_ERR_ARG, "bitmap term %d: int column needs an int literal", k);
             for (int64_t v = 0; v < bi.nvalues; ++v) {
                 int cmp = bi.ivals[v] < s.rhs.lit_i ? -1 : bi.ivals[v] > s.rhs.lit_i ? 1 : 0;
-                if (value_selected(s.op, cmp)) list->push_back(reinterpret_cast<const uint4*>(bi.d_words + v * t->words_pad));
+                if (value_selected(s.op, cmp)) list->push_back(bm_ref(bi, v));
             }
         }
-        if (list->size() == before) list->push_back(nullptr);   // nothing selected: an empty bitset takes the term's place
+        if (list->size() == before) list->push_back(BmRef{nullptr, 0, 0});   // nothing selected: an empty bitset takes the term's place
     }
     conj_end->push_back((int)list->size());
     if ((int)conj_end->size() > kMaxTerms) MBC_FAIL(MBC_ERR_UNSUPPORTED, "%d conjuncts (max %d)", (int)conj_end->size(), kMaxTerms);
@@ -560,7 +660,7 @@ int32_t resolve_bitmap_terms(mbc_table* t, const mbc_term* terms, int32_t nterms
 // runs K4 into a fresh device bitmap of t->words_pad words
 int32_t run_bitmap_cnf(mbc_table* t, const mbc_term* terms, int32_t nterms, uint32_t** d_out) {
     mbc_ctx* ctx = t->ctx;
-    std::vector<const uint4*> list;
+    std::vector<BmRef> list;
     std::vector<int> conj_end;
     MBC_TRY(resolve_bitmap_terms(t, terms, nterms, &list, &conj_end));
     MBC_TRY(dev_alloc(ctx, (void**)d_out, (size_t)t->words_pad * 4, false));
@@ -571,12 +671,12 @@ int32_t run_bitmap_cnf(mbc_table* t, const mbc_term* terms, int32_t nterms, uint
     p.nconj = (int)conj_end.size();
     p.nbitmaps = (int)list.size();
     for (int g = 0; g < p.nconj; ++g) p.conj_end[g] = conj_end[g];
-    const uint4** d_list = nullptr;
+    BmRef* d_list = nullptr;
     if ((int)list.size() <= kMaxInlineBitmaps) {
         for (size_t j = 0; j < list.size(); ++j) p.inl[j] = list[j];
     } else {
-        MBC_TRY(dev_alloc(ctx, (void**)&d_list, list.size() * sizeof(void*), false));
-        MBC_CUDA(cudaMemcpyAsync(d_list, list.data(), list.size() * sizeof(void*), cudaMemcpyHostToDevice, ctx->stream));
+        MBC_TRY(dev_alloc(ctx, (void**)&d_list, list.size() * sizeof(BmRef), false));
+        MBC_CUDA(cudaMemcpyAsync(d_list, list.data(), list.size() * sizeof(BmRef), cudaMemcpyHostToDevice, ctx->stream));
         MBC_CUDA(cudaStreamSynchronize(ctx->stream));    // `list` is pageable host memory
         p.list = d_list;
     }

@@ -81,7 +81,10 @@ struct BitmapIndex {
     int64_t  nvalues = 0;
     std::vector<int32_t> ivals;    // sorted distinct values (int columns)
     std::vector<uint8_t> svals;    // sorted distinct values, nvalues*width bytes (string columns)
-    uint32_t* d_words = nullptr;   // [nvalues][words_per_bitmap] uint32, bit p of a bitmap = word p/32, bit p%32
+    // chunk-major storage: [chunk][value][chunk_rows/32] uint32 words (bit p of a value's bitmap = word p/32, bit p%32).
+    // A build CTA writes one fully contiguous block per chunk; a scan reads a value's bitmap as chunk_rows/8-byte pieces.
+    uint32_t* d_words = nullptr;
+    int32_t   chunk_rows = 0;      // rows per chunk (power of two, 1024..8192)
     uint32_t* d_ids   = nullptr;   // per-row dense value id (kept for the join's low-cardinality path)
 };
 
