@@ -236,12 +236,11 @@ void decode_aggs(mbc_result* r, const DevAgg* dev, int nagg, const unsigned long
     }
 }
 
-// Workspace layout: [count:i64 @0][tile_counts: launch_tiles u32][warp_counts: 8 x launch_tiles u32][tile_out: launch_tiles u64]
+// Workspace layout: [count:i64 @0][tile_counts: launch_tiles u32][tile_out: launch_tiles + 1 u64]
 //                   [partials: nagg*total_tiles u64][agg out: 8 u64]
 struct Workspace {
     long long* count;
     uint32_t* tile_counts;
-    uint32_t* warp_counts;
     unsigned long long* tile_out;
     unsigned long long* partials;
     unsigned long long* agg_out;
@@ -249,18 +248,16 @@ struct Workspace {
 
 static int32_t carve_workspace(mbc_ctx* ctx, int64_t launch_tiles, int64_t total_tiles, int nagg, Workspace* w) {
     size_t counts_bytes = (size_t)round_up(launch_tiles * 4, 64);
-    size_t wcounts_bytes = (size_t)round_up(launch_tiles * 4 * kWarpsPerCta, 64);
-    size_t out_bytes = (size_t)launch_tiles * 8;
+    size_t out_bytes = (size_t)(launch_tiles + 1) * 8;
     size_t partial_bytes = (size_t)std::max(nagg, 1) * total_tiles * 8;
-    size_t total = 64 + counts_bytes + wcounts_bytes + out_bytes + partial_bytes + kMaxAgg * 8 + 64;
+    size_t total = 64 + counts_bytes + out_bytes + partial_bytes + kMaxAgg * 8 + 64;
     MBC_TRY(ensure_workspace(ctx, total));
     char* b = (char*)ctx->ws;
     w->count = (long long*)b;
     w->tile_counts = (uint32_t*)(b + 64);
-    w->warp_counts = (uint32_t*)(b + 64 + counts_bytes);
-    w->tile_out = (unsigned long long*)(b + 64 + counts_bytes + wcounts_bytes);
-    w->partials = (unsigned long long*)(b + 64 + counts_bytes + wcounts_bytes + out_bytes);
-    w->agg_out = (unsigned long long*)(b + 64 + counts_bytes + wcounts_bytes + out_bytes + partial_bytes);
+    w->tile_out = (unsigned long long*)(b + 64 + counts_bytes);
+    w->partials = (unsigned long long*)(b + 64 + counts_bytes + out_bytes);
+    w->agg_out = (unsigned long long*)(b + 64 + counts_bytes + out_bytes + partial_bytes);
     return MBC_OK;
 }
 
@@ -318,7 +315,6 @@ static int32_t prepare_job(const mbc_table* schema, const ScanRequest& rq, int64
     job->total_tiles = total_tiles;
     p.total_tiles = (int)total_tiles;
     p.tile_counts = job->w.tile_counts;
-    p.warp_counts = job->w.warp_counts;
     p.tile_out = job->w.tile_out;
     p.count = job->w.count;
     p.partials = job->w.partials;

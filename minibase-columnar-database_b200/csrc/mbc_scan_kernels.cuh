@@ -103,7 +103,6 @@ struct ScanParams {
     int64_t* out_pos;
     uint32_t* out_bitmap;
     uint32_t* tile_counts;        // qualifying rows per tile (pass 1 -> pass 2)
-    uint32_t* warp_counts;        // [tile][kWarpsPerCta] qualifying rows per 512-row warp chunk
     unsigned long long* tile_out; // global output offset of every tile (tile_offsets_kernel)
     long long* count;             // in: running output offset, out: offset after this launch
     long long* prof;              // optional phase timers (MBC_SCAN_PROFILE builds)
@@ -441,8 +440,6 @@ __global__ void __launch_bounds__(kScanThreads, 2) filter_kernel(const __grid_co
 #pragma unroll
             for (int w = 0; w < kWarpsPerCta; ++w) c += s_wcnt[w];
             p.tile_counts[tile] = c;
-#pragma unroll
-            for (int w = 0; w < kWarpsPerCta; ++w) p.warp_counts[(size_t)tile * kWarpsPerCta + w] = s_wcnt[w];
             const long long next = tile + (long long)S * gridDim.x;
             if (p.nstaged && next < p.ntiles) issue_tile(slot, (int)next);
         }
@@ -491,22 +488,108 @@ __global__ void __launch_bounds__(1024) tile_offsets_kernel(const uint32_t* coun
             if (i + j < ntiles) { tile_base[i + j] = run; run += c[j]; }
     }
     __syncthreads();                                               // everyone has read *running
-    if (tid == 0) *running = (long long)(start + total);
+    if (tid == 0) {
+        tile_base[ntiles] = start + total;                         // end of the last tile: groups read [first, last + 1]
+        *running = (long long)(start + total);
+    }
 }
 
 // ---- pass 2: ordered write of the survivors ----------------------------------------------------------------------
+// One CTA per tile; tiles form GROUPS of kGroupTiles.  In a dense group every CTA writes its own tile: ranks from the
+// bitmap, rank -> row list in shared memory, one thread per SURVIVOR, gathers issued in batches before the dependent
+// stores.  A sparse group (<= kSparseMax survivors) is written by its first CTA alone and the others exit: at low
+// selectivity a tile holds a few dozen survivors and a CTA's load -> scan -> gather -> store chain is pure latency,
+// so the group amortises it over 8x the rows.  There every thread owns kThreadWords consecutive words of the group's
+// selection bitmap (128-bit loads), a block scan of the popcounts ranks them, and the output columns go one per warp.
 #ifndef MBC_WRITE_MIN_CTAS
 #define MBC_WRITE_MIN_CTAS 4
 #endif
-__global__ void __launch_bounds__(kScanThreads, MBC_WRITE_MIN_CTAS) write_kernel(const __grid_constant__ ScanParams p) {
-    __shared__ uint16_t s_list[kTileRows];                         // survivor rows within the tile, by tile rank
-    __shared__ uint32_t s_wtot[kWarpsPerCta];
-    __shared__ unsigned long long s_aggw[kMaxAgg][kWarpsPerCta];
+#ifndef MBC_GROUP_TILES
+#define MBC_GROUP_TILES 8
+#endif
+#ifndef MBC_SPARSE_MAX
+#define MBC_SPARSE_MAX 4096
+#endif
+constexpr int kGroupTiles = MBC_GROUP_TILES;
+constexpr int kGroupRows = kGroupTiles * kTileRows;                // <= 65536: list entries are uint16
+constexpr int kGroupWords = kGroupRows / 32;
+constexpr int kThreadWords = kGroupWords / kScanThreads;           // 4 (or 8) -> one (two) 128-bit loads per thread
+constexpr int kListCap = MBC_SPARSE_MAX > kTileRows ? MBC_SPARSE_MAX : kTileRows;
+constexpr int kSparseMax = MBC_SPARSE_MAX;                         // survivors per group handled item-per-warp
+static_assert(kGroupRows <= 65536 && kThreadWords % 4 == 0 && kSparseMax <= kListCap, "group geometry");
 
+template <typename V>
+__device__ __forceinline__ void gather_store(const V* __restrict__ src, V* __restrict__ dst, const uint16_t* list, int first,
+                                             int step, int n) {
+    for (int k0 = first; k0 < n; k0 += step * kGatherBatch) {
+        V v[kGatherBatch];
+#pragma unroll
+        for (int b = 0; b < kGatherBatch; ++b) {
+            const int k = k0 + b * step;
+            if (k < n) v[b] = __ldg(src + list[k]);
+        }
+#pragma unroll
+        for (int b = 0; b < kGatherBatch; ++b) {
+            const int k = k0 + b * step;
+            if (k < n) dst[k] = v[b];
+        }
+    }
+}
+
+__device__ __forceinline__ void gather_store_wide(const DevProj& pr, int64_t row0, long long out0, const uint16_t* list, int first,
+                                                  int step, int n) {
+    const int words = pr.stride >> 2;
+    for (int k = first; k < n; k += step) {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(pr.src) + (row0 + list[k]) * pr.stride);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(pr.dst) + (out0 + k) * pr.stride);
+        for (int q = 0; q < words; ++q) dst[q] = __ldg(src + q);
+    }
+}
+
+// fold of one aggregate over list[first], list[first + step], ...; the result is butterflied across the warp
+__device__ __forceinline__ unsigned long long gather_fold(const DevAgg& g, int64_t row0, const uint16_t* list, int first, int step, int n) {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(g.src) + row0;
+    if (g.type == MBC_ATTR_INTEGER) {
+        long long acc = (long long)agg_identity(g);
+        for (int k0 = first; k0 < n; k0 += step * kGatherBatch) {
+            uint32_t v[kGatherBatch];
+#pragma unroll
+            for (int b = 0; b < kGatherBatch; ++b) {
+                const int k = k0 + b * step;
+                if (k < n) v[b] = __ldg(src + list[k]);
+            }
+#pragma unroll
+            for (int b = 0; b < kGatherBatch; ++b)
+                if (k0 + b * step < n) acc = agg_combine<long long>(g.kind, acc, (long long)(int32_t)v[b]);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc = agg_combine<long long>(g.kind, acc, __shfl_xor_sync(0xFFFFFFFFu, acc, o));
+        return (unsigned long long)acc;
+    }
+    double acc = __longlong_as_double((long long)agg_identity(g));
+    for (int k0 = first; k0 < n; k0 += step * kGatherBatch) {
+        uint32_t v[kGatherBatch];
+#pragma unroll
+        for (int b = 0; b < kGatherBatch; ++b) {
+            const int k = k0 + b * step;
+            if (k < n) v[b] = __ldg(src + list[k]);
+        }
+#pragma unroll
+        for (int b = 0; b < kGatherBatch; ++b)
+            if (k0 + b * step < n) acc = agg_combine<double>(g.kind, acc, (double)__uint_as_float(v[b]));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc = agg_combine<double>(g.kind, acc, __shfl_xor_sync(0xFFFFFFFFu, acc, o));
+    return (unsigned long long)__double_as_longlong(acc);
+}
+
+// One tile of a dense group: ranks from the bitmap in the filter pass's 16-rows-per-thread layout (the expansion is
+// 16 predicated stores), rank -> row list, one thread per survivor.  Writes the tile's own partials.
+__device__ __forceinline__ void write_dense_tile(const ScanParams& p, const int tile, uint16_t* s_list, uint32_t* s_wtot,
+                                                 unsigned long long (*s_aggw)[kWarpsPerCta]) {
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
-    const int tile = blockIdx.x;
     const int T = (int)p.tile_counts[tile];
     if (T == 0) {                                                  // block-uniform: nothing qualifies in this tile
         if (tid < p.nagg) p.partials[(size_t)tid * p.total_tiles + p.tile_base + tile] = agg_identity(p.aggs[tid]);
@@ -514,11 +597,8 @@ __global__ void __launch_bounds__(kScanThreads, MBC_WRITE_MIN_CTAS) write_kernel
     }
     const long long base = (long long)p.tile_out[tile];
     const int64_t tile_row0 = (int64_t)tile * kTileRows;
-
-    // ranks from the bitmap: same 16-rows-per-thread layout as the filter pass
     {
-        const int64_t warp_row0 = tile_row0 + warp * kWarpRows;
-        const uint32_t mask = load_bits(p.out_bitmap, warp_row0, lane);
+        const uint32_t mask = load_bits(p.out_bitmap, tile_row0 + warp * kWarpRows, lane);
         const uint32_t packed = __popc(mask & 0xFu) | (__popc(mask & 0xF0u) << 8) | (__popc(mask & 0xF00u) << 16) |
                                 (__popc(mask & 0xF000u) << 24);
         uint32_t incl = packed;
@@ -554,129 +634,23 @@ __global__ void __launch_bounds__(kScanThreads, MBC_WRITE_MIN_CTAS) write_kernel
         }
         __syncthreads();
     }
-
     const uint16_t* list = s_list;
-    if (T <= kScanThreads) {
-        // sparse tile: one work item (positions / one projected column / one aggregate) per warp, so the
-        // dependent load->store chains of the columns run side by side
-        const int nitems = 1 + p.nproj + p.nagg;
-        for (int item = warp; item < nitems; item += kWarpsPerCta) {
-            if (item == 0) {
-                if (p.out_pos)
-                    for (int k = lane; k < T; k += 32) p.out_pos[base + k] = p.pos_base + tile_row0 + list[k];
-            } else if (item <= p.nproj) {                          // iterator/Projection.java:103-144
-                const DevProj& pr = p.proj[item - 1];
-                if (pr.stride == 4) {
-                    const uint32_t* src = reinterpret_cast<const uint32_t*>(pr.src) + tile_row0;
-                    uint32_t* dst = reinterpret_cast<uint32_t*>(pr.dst) + base;
-                    for (int k = lane; k < T; k += 32) dst[k] = __ldg(src + list[k]);
-                } else if (pr.stride == 16) {
-                    const uint4* src = reinterpret_cast<const uint4*>(pr.src) + tile_row0;
-                    uint4* dst = reinterpret_cast<uint4*>(pr.dst) + base;
-                    for (int k = lane; k < T; k += 32) dst[k] = __ldg(src + list[k]);
-                } else {
-                    const int words = pr.stride >> 2;
-                    for (int k = lane; k < T; k += 32) {
-                        const uint32_t* src = reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(pr.src) +
-                                                                                (tile_row0 + list[k]) * pr.stride);
-                        uint32_t* dst = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(pr.dst) + (base + k) * pr.stride);
-                        for (int q = 0; q < words; ++q) dst[q] = __ldg(src + q);
-                    }
-                }
-            } else {
-                const int a = item - 1 - p.nproj;
-                const DevAgg& g = p.aggs[a];
-                unsigned long long v;
-                if (g.kind == MBC_AGG_COUNT) {
-                    v = (unsigned long long)T;
-                } else {
-                    const uint32_t* src = reinterpret_cast<const uint32_t*>(g.src) + tile_row0;
-                    if (g.type == MBC_ATTR_INTEGER) {
-                        long long acc = (long long)agg_identity(g);
-                        for (int k = lane; k < T; k += 32) acc = agg_combine<long long>(g.kind, acc, (long long)(int32_t)__ldg(src + list[k]));
-#pragma unroll
-                        for (int o = 16; o > 0; o >>= 1) acc = agg_combine<long long>(g.kind, acc, __shfl_xor_sync(0xFFFFFFFFu, acc, o));
-                        v = (unsigned long long)acc;
-                    } else {
-                        double acc = __longlong_as_double((long long)agg_identity(g));
-                        for (int k = lane; k < T; k += 32) acc = agg_combine<double>(g.kind, acc, (double)__uint_as_float(__ldg(src + list[k])));
-#pragma unroll
-                        for (int o = 16; o > 0; o >>= 1) acc = agg_combine<double>(g.kind, acc, __shfl_xor_sync(0xFFFFFFFFu, acc, o));
-                        v = (unsigned long long)__double_as_longlong(acc);
-                    }
-                }
-                if (lane == 0) p.partials[(size_t)a * p.total_tiles + p.tile_base + tile] = v;
-            }
-        }
-        return;
-    }
-
-    // dense tile: one thread per survivor, gathers issued in batches before the dependent stores
-    if (p.out_pos) {
+    if (p.out_pos)
         for (int k = tid; k < T; k += kScanThreads) p.out_pos[base + k] = p.pos_base + tile_row0 + list[k];
-    }
-    for (int c = 0; c < p.nproj; ++c) {
+    for (int c = 0; c < p.nproj; ++c) {                            // iterator/Projection.java:103-144
         const DevProj& pr = p.proj[c];
-        if (pr.stride == 4) {
-            const uint32_t* src = reinterpret_cast<const uint32_t*>(pr.src) + tile_row0;
-            uint32_t* dst = reinterpret_cast<uint32_t*>(pr.dst) + base;
-            for (int k0 = tid; k0 < T; k0 += kScanThreads * kGatherBatch) {
-                uint32_t v[kGatherBatch];
-#pragma unroll
-                for (int b = 0; b < kGatherBatch; ++b) {
-                    int k = k0 + b * kScanThreads;
-                    if (k < T) v[b] = __ldg(src + list[k]);
-                }
-#pragma unroll
-                for (int b = 0; b < kGatherBatch; ++b) {
-                    int k = k0 + b * kScanThreads;
-                    if (k < T) dst[k] = v[b];
-                }
-            }
-        } else if (pr.stride == 16) {
-            const uint4* src = reinterpret_cast<const uint4*>(pr.src) + tile_row0;
-            uint4* dst = reinterpret_cast<uint4*>(pr.dst) + base;
-            for (int k0 = tid; k0 < T; k0 += kScanThreads * kGatherBatch) {
-                uint4 v[kGatherBatch];
-#pragma unroll
-                for (int b = 0; b < kGatherBatch; ++b) {
-                    int k = k0 + b * kScanThreads;
-                    if (k < T) v[b] = __ldg(src + list[k]);
-                }
-#pragma unroll
-                for (int b = 0; b < kGatherBatch; ++b) {
-                    int k = k0 + b * kScanThreads;
-                    if (k < T) dst[k] = v[b];
-                }
-            }
-        } else {
-            const int words = pr.stride >> 2;
-            for (int k = tid; k < T; k += kScanThreads) {
-                const uint32_t* src = reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(pr.src) + (tile_row0 + list[k]) * pr.stride);
-                uint32_t* dst = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(pr.dst) + (base + k) * pr.stride);
-                for (int q = 0; q < words; ++q) dst[q] = __ldg(src + q);
-            }
-        }
+        if (pr.stride == 4)
+            gather_store(reinterpret_cast<const uint32_t*>(pr.src) + tile_row0, reinterpret_cast<uint32_t*>(pr.dst) + base, list, tid, kScanThreads, T);
+        else if (pr.stride == 16)
+            gather_store(reinterpret_cast<const uint4*>(pr.src) + tile_row0, reinterpret_cast<uint4*>(pr.dst) + base, list, tid, kScanThreads, T);
+        else
+            gather_store_wide(pr, tile_row0, base, list, tid, kScanThreads, T);
     }
     // aggregates: per-thread fold over its survivors, one butterfly per warp, warps combined in order
     for (int a = 0; a < p.nagg; ++a) {
         const DevAgg& g = p.aggs[a];
         if (g.kind == MBC_AGG_COUNT) continue;                     // the tile count is the count
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(g.src) + tile_row0;
-        unsigned long long v;
-        if (g.type == MBC_ATTR_INTEGER) {
-            long long acc = (long long)agg_identity(g);
-            for (int k = tid; k < T; k += kScanThreads) acc = agg_combine<long long>(g.kind, acc, (long long)(int32_t)__ldg(src + list[k]));
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) acc = agg_combine<long long>(g.kind, acc, __shfl_xor_sync(0xFFFFFFFFu, acc, o));
-            v = (unsigned long long)acc;
-        } else {
-            double acc = __longlong_as_double((long long)agg_identity(g));
-            for (int k = tid; k < T; k += kScanThreads) acc = agg_combine<double>(g.kind, acc, (double)__uint_as_float(__ldg(src + list[k])));
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) acc = agg_combine<double>(g.kind, acc, __shfl_xor_sync(0xFFFFFFFFu, acc, o));
-            v = (unsigned long long)__double_as_longlong(acc);
-        }
+        const unsigned long long v = gather_fold(g, tile_row0, list, tid, kScanThreads, T);
         if (lane == 0) s_aggw[a][warp] = v;
     }
     __syncthreads();
@@ -687,9 +661,101 @@ __global__ void __launch_bounds__(kScanThreads, MBC_WRITE_MIN_CTAS) write_kernel
             v = (unsigned long long)T;
         } else {
             v = s_aggw[tid][0];
-            for (int w = 1; w < kWarpsPerCta; ++w) v = agg_merge(g, v, s_aggw[tid][w]);
+            for (int x = 1; x < kWarpsPerCta; ++x) v = agg_merge(g, v, s_aggw[tid][x]);
         }
         p.partials[(size_t)tid * p.total_tiles + p.tile_base + tile] = v;
+    }
+}
+
+__global__ void __launch_bounds__(kScanThreads, MBC_WRITE_MIN_CTAS) write_kernel(const __grid_constant__ ScanParams p) {
+    __shared__ uint16_t s_list[kListCap];                          // survivor rows within the group / tile, by rank
+    __shared__ uint32_t s_wtot[kWarpsPerCta];
+    __shared__ unsigned long long s_aggw[kMaxAgg][kWarpsPerCta];
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    const int tile = blockIdx.x;
+    const int tile0 = tile & ~(kGroupTiles - 1);
+    const int ntl = min(kGroupTiles, p.ntiles - tile0);            // tiles of this group
+    const long long base = (long long)p.tile_out[tile0];
+    const int total = (int)((long long)p.tile_out[tile0 + ntl] - base);
+    if (total > kSparseMax) {                                      // block-uniform: dense group, every CTA writes its own tile
+        write_dense_tile(p, tile, s_list, s_wtot, s_aggw);
+        return;
+    }
+    // sparse group: its first CTA writes all of it; one partial for the group, the other tiles carry the identity
+    if (tile != tile0) {
+        if (tid < p.nagg) p.partials[(size_t)tid * p.total_tiles + p.tile_base + tile] = agg_identity(p.aggs[tid]);
+        return;
+    }
+    const size_t part0 = (size_t)p.tile_base + tile0;
+    if (total == 0) {
+        if (tid < p.nagg) p.partials[(size_t)tid * p.total_tiles + part0] = agg_identity(p.aggs[tid]);
+        return;
+    }
+    const int64_t row0 = (int64_t)tile0 * kTileRows;
+
+    uint32_t w[kThreadWords];
+    const int word0 = tid * kThreadWords;
+    int cnt = 0;
+#pragma unroll
+    for (int q = 0; q < kThreadWords; q += 4) {
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (word0 + q < ntl * (kTileRows / 32)) v = *reinterpret_cast<const uint4*>(p.out_bitmap + (row0 >> 5) + word0 + q);
+        w[q] = v.x; w[q + 1] = v.y; w[q + 2] = v.z; w[q + 3] = v.w;
+        cnt += __popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w);
+    }
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int n = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        if (lane >= o) incl += n;
+    }
+    if (lane == 31) s_wtot[warp] = (uint32_t)incl;
+    __syncthreads();
+    uint32_t below = (lane < warp) ? s_wtot[lane & (kWarpsPerCta - 1)] : 0u;
+#pragma unroll
+    for (int o = 1; o < kWarpsPerCta; o <<= 1) below += __shfl_xor_sync(0xFFFFFFFFu, below, o);
+    const int r0 = (int)__shfl_sync(0xFFFFFFFFu, below, 0) + incl - cnt;
+
+    // expansion: every thread walks its words, rank -> row within the group
+    if (cnt) {
+        int r = r0;
+#pragma unroll
+        for (int i = 0; i < kThreadWords; ++i) {
+            uint32_t bits = w[i];
+            const int rowb = (word0 + i) * 32;
+            while (bits) {
+                s_list[r++] = (uint16_t)(rowb + __ffs(bits) - 1);
+                bits &= bits - 1;
+            }
+        }
+    }
+    __syncthreads();
+    // one work item (positions / one projected column / one aggregate) per warp, so the dependent load -> store
+    // chains of the columns run side by side
+    const uint16_t* list = s_list;
+    const int T = total;
+    const int nitems = 1 + p.nproj + p.nagg;
+    for (int item = warp; item < nitems; item += kWarpsPerCta) {
+        if (item == 0) {
+            if (p.out_pos)
+                for (int k = lane; k < T; k += 32) p.out_pos[base + k] = p.pos_base + row0 + list[k];
+        } else if (item <= p.nproj) {                              // iterator/Projection.java:103-144
+            const DevProj& pr = p.proj[item - 1];
+            if (pr.stride == 4)
+                gather_store(reinterpret_cast<const uint32_t*>(pr.src) + row0, reinterpret_cast<uint32_t*>(pr.dst) + base, list, lane, 32, T);
+            else if (pr.stride == 16)
+                gather_store(reinterpret_cast<const uint4*>(pr.src) + row0, reinterpret_cast<uint4*>(pr.dst) + base, list, lane, 32, T);
+            else
+                gather_store_wide(pr, row0, base, list, lane, 32, T);
+        } else {
+            const int a = item - 1 - p.nproj;
+            const DevAgg& g = p.aggs[a];
+            const unsigned long long v = (g.kind == MBC_AGG_COUNT) ? (unsigned long long)T : gather_fold(g, row0, list, lane, 32, T);
+            if (lane == 0) p.partials[(size_t)a * p.total_tiles + part0] = v;
+        }
     }
 }
 
