@@ -134,6 +134,9 @@ int32_t mbc_host_alloc(void** p, int64_t bytes);
 void    mbc_host_free(void* p);
 /* Number of this library's kernels launched by the context since creation. */
 int64_t mbc_kernel_launches(const mbc_ctx* ctx);
+/* Bytes mbc_scan_host has moved host -> device since the context was created: explicit copies plus the
+ * survivors' rows it read in place from pinned host columns (late materialisation). */
+int64_t mbc_h2d_bytes(const mbc_ctx* ctx);
 /* Device-time of the last scan/bitmap/join call's kernels, CUDA events on the ctx stream. */
 float   mbc_last_kernel_ms(const mbc_ctx* ctx);
 

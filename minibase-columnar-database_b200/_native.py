@@ -65,6 +65,7 @@ _SIGNATURES = {
     "mbc_host_alloc": (C.c_int32, [C.POINTER(_VP), C.c_int64]),
     "mbc_host_free": (None, [_VP]),
     "mbc_kernel_launches": (C.c_int64, [_VP]),
+    "mbc_h2d_bytes": (C.c_int64, [_VP]),
     "mbc_last_kernel_ms": (C.c_float, [_VP]),
     "mbc_table_create": (C.c_int32, [_VP, C.c_int32, C.POINTER(mbc_coldesc), C.c_int64, C.c_int64, C.POINTER(_VP)]),
     "mbc_table_free": (None, [_VP]),

@@ -162,6 +162,8 @@ int32_t mbc_sync(mbc_ctx* ctx) {
 
 int64_t mbc_kernel_launches(const mbc_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
+int64_t mbc_h2d_bytes(const mbc_ctx* ctx) { return ctx ? ctx->h2d_bytes : 0; }
+
 float mbc_last_kernel_ms(const mbc_ctx* ctx) {
     if (!ctx) return 0.f;
     float ms = 0.f;

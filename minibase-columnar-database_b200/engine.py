@@ -95,6 +95,10 @@ class Context:
         return int(N.lib().mbc_kernel_launches(self._h))
 
     @property
+    def h2d_bytes(self) -> int:
+        return int(N.lib().mbc_h2d_bytes(self._h))
+
+    @property
     def last_kernel_ms(self) -> float:
         return float(N.lib().mbc_last_kernel_ms(self._h))
 
