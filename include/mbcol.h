@@ -218,7 +218,13 @@ int32_t mbc_bitmap_join(mbc_table* outer, mbc_table* inner,
                         const mbc_aggspec* aggs, int32_t nagg, mbc_result** out);
 
 /* ---- results -------------------------------------------------------------------------- */
+/* A device-resident result of mbc_scan (no MBC_WANT_HOST / MBC_WANT_TUPLES) completes asynchronously:
+ * mbc_scan returns with its kernels queued on the context's stream, and the first call of
+ * mbc_result_count / mbc_result_agg / mbc_result_kernel_ms waits for them.  The device buffers of
+ * mbc_result_device are valid in stream order at once. */
 int64_t        mbc_result_count(const mbc_result* r);
+/* Device time of the kernels that produced this result (CUDA events around them), ms; < 0 if unknown. */
+float          mbc_result_kernel_ms(const mbc_result* r);
 /* ascending positions, int64 (host; needs MBC_WANT_POSITIONS|MBC_WANT_HOST). For joins:
  * outer positions; mbc_result_positions2 gives the matching inner positions. */
 const int64_t* mbc_result_positions(const mbc_result* r);

@@ -82,6 +82,48 @@ void begin_timing(mbc_ctx* ctx) {
     cudaEventRecord(ctx->ev_begin, ctx->stream);
 }
 void end_timing(mbc_ctx* ctx) { cudaEventRecord(ctx->ev_end, ctx->stream); }
+cudaEvent_t event_get(mbc_ctx* ctx) {
+    if (!ctx->event_free.empty()) {
+        cudaEvent_t e = ctx->event_free.back();
+        ctx->event_free.pop_back();
+        return e;
+    }
+    cudaEvent_t e = nullptr;
+    return cudaEventCreate(&e) == cudaSuccess ? e : nullptr;
+}
+void event_put(mbc_ctx* ctx, cudaEvent_t e) {
+    if (!e) return;
+    if (ctx->event_free.size() >= 64) cudaEventDestroy(e);
+    else ctx->event_free.push_back(e);
+}
+
+int32_t result_finalize(mbc_result* r) {
+    if (!r->ev_ready) return MBC_OK;
+    mbc_ctx* ctx = r->ctx;
+    cudaError_t e = cudaEventSynchronize(r->ev_ready);
+    event_put(ctx, r->ev_ready);
+    r->ev_ready = nullptr;
+    if (e != cudaSuccess) MBC_FAIL(MBC_ERR_CUDA, "deferred scan failed: %s", cudaGetErrorString(e));
+    r->count = (int64_t)r->h_small[kMaxAgg];
+    for (size_t a = 0; a < r->aggs.size(); ++a) {
+        mbc_result::Agg& g = r->aggs[a];
+        const bool integral = g.kind == MBC_AGG_COUNT || g.type == MBC_ATTR_INTEGER;
+        if (integral) {
+            g.i = (int64_t)r->h_small[a];
+            g.f = (double)g.i;
+        } else {
+            double d;
+            memcpy(&d, &r->h_small[a], 8);
+            g.f = d;
+            g.i = (int64_t)d;
+        }
+        g.valid = (g.kind == MBC_AGG_COUNT || g.kind == MBC_AGG_SUM) ? 1 : (r->count > 0);
+        if (!g.valid) { g.i = 0; g.f = 0.0; }
+    }
+    if (r->ev_t0 && r->ev_t1 && cudaEventElapsedTime(&r->kernel_ms, r->ev_t0, r->ev_t1) != cudaSuccess) r->kernel_ms = -1.f;
+    return MBC_OK;
+}
+
 void split_timing(mbc_ctx* ctx) {
     cudaEventRecord(ctx->ev_end, ctx->stream);
     float ms = 0.f;
@@ -138,6 +180,7 @@ void mbc_shutdown(mbc_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     for (auto& b : ctx->pinned_free) cudaFreeHost(b.p);
+    for (auto e : ctx->event_free) cudaEventDestroy(e);
     if (ctx->ws) cudaFree(ctx->ws);
     cudaEventDestroy(ctx->ev_begin);
     cudaEventDestroy(ctx->ev_end);
@@ -312,7 +355,17 @@ int32_t mbc_table_set_deleted(mbc_table* t, const uint64_t* bitset_words, int64_
 
 // ---- results -----------------------------------------------------------------------------
 
-int64_t mbc_result_count(const mbc_result* r) { return r ? r->count : -1; }
+int64_t mbc_result_count(const mbc_result* r) {
+    if (!r) return -1;
+    if (result_finalize(const_cast<mbc_result*>(r)) != MBC_OK) return -1;
+    return r->count;
+}
+
+float mbc_result_kernel_ms(const mbc_result* r) {
+    if (!r) return -1.f;
+    if (result_finalize(const_cast<mbc_result*>(r)) != MBC_OK) return -1.f;
+    return r->kernel_ms;
+}
 const int64_t* mbc_result_positions(const mbc_result* r) { return r ? r->h_pos : nullptr; }
 const int64_t* mbc_result_positions2(const mbc_result* r) { return r ? r->h_pos2 : nullptr; }
 
@@ -331,6 +384,7 @@ const uint8_t* mbc_result_tuples(const mbc_result* r, int32_t* tuple_len) {
 int32_t mbc_result_agg(const mbc_result* r, int32_t i, int64_t* as_i64, double* as_f64, int32_t* valid) {
     if (!r || i < 0 || i >= (int)r->aggs.size()) MBC_FAIL(MBC_ERR_ARG, "mbc_result_agg: index %d of %d", i,
                                                           r ? (int)r->aggs.size() : 0);
+    MBC_TRY(result_finalize(const_cast<mbc_result*>(r)));
     if (as_i64) *as_i64 = r->aggs[i].i;
     if (as_f64) *as_f64 = r->aggs[i].f;
     if (valid) *valid = r->aggs[i].valid;
@@ -364,6 +418,9 @@ void mbc_result_free(mbc_result* r) {
     if (!r) return;
     mbc_ctx* ctx = r->ctx;
     cudaSetDevice(ctx->device);
+    result_finalize(r);                            // the pinned count/aggregate block must have landed before it is recycled
+    event_put(ctx, r->ev_t0);
+    event_put(ctx, r->ev_t1);
     dev_free(ctx, r->d_pos);
     dev_free(ctx, r->d_pos2);
     for (auto& c : r->cols) dev_free(ctx, c.d);

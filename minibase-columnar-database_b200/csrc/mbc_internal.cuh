@@ -109,6 +109,7 @@ struct mbc_ctx {
     // pinned host blocks recycled between results
     struct PinnedBlock { void* p; size_t bytes; };
     std::vector<PinnedBlock> pinned_free;
+    std::vector<cudaEvent_t> event_free;  // recycled timing / completion events
 };
 
 struct mbc_table {
@@ -148,6 +149,13 @@ struct mbc_result {
     // aggregates
     struct Agg { int32_t kind, type; int64_t i; double f; int32_t valid; };
     std::vector<Agg> aggs;
+    // Deferred completion (device-resident results of mbc_scan): the call returns with its kernels and the small
+    // count/aggregate copy queued; the first accessor that needs the count waits on ev_ready.  Back-to-back scans
+    // then run without host gaps between them.
+    cudaEvent_t ev_ready = nullptr;        // non-null while count/aggs are still in flight
+    cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;   // device time of this result's kernels
+    unsigned long long* h_small = nullptr; // pinned: nagg raw values + count
+    float kernel_ms = -1.f;
 };
 
 namespace mbc {
@@ -160,7 +168,10 @@ void    pinned_release(mbc_ctx* ctx, void* p, size_t bytes);
 int32_t ensure_workspace(mbc_ctx* ctx, size_t bytes);
 void    begin_timing(mbc_ctx* ctx);
 void    end_timing(mbc_ctx* ctx);
-void    split_timing(mbc_ctx* ctx);        // close a timed segment (sync), keep its time, the next begin_timing adds to it
+void    split_timing(mbc_ctx* ctx);
+int32_t result_finalize(mbc_result* r);   // wait for a deferred result's count/aggregates (no-op when final)
+cudaEvent_t event_get(mbc_ctx* ctx);
+void    event_put(mbc_ctx* ctx, cudaEvent_t e);        // close a timed segment (sync), keep its time, the next begin_timing adds to it
 
 // ---- the select -> compact -> project -> aggregate engine (mbc_scan.cu) ---------------------
 struct ScanRequest {
@@ -173,6 +184,7 @@ struct ScanRequest {
     uint32_t want = 0;
     const mbc_aggspec* aggs = nullptr;
     int32_t nagg = 0;
+    bool allow_deferred = false;              // mbc_scan: device-resident results may complete asynchronously
 };
 int32_t run_scan(const ScanRequest& rq, mbc_result** out);
 int32_t finish_result_host(mbc_result* r);     // tuple encode + D2H according to r->want

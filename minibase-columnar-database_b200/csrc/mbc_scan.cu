@@ -98,7 +98,6 @@ static int32_t plan_staging(mbc_ctx* ctx, ScanParams* p, size_t* smem_bytes, int
     }
     for (int c = 0; c < p->nproj; ++c) p->proj[c].staged = -1;
     for (int a = 0; a < p->nagg; ++a) p->aggs[a].staged = -1;
-    p->ngather = 0;
     // ring depth: as deep as ~100 KB of shared memory allows (two CTAs per SM), at least 2
     p->nstages = p->nstaged == 0 ? 2 : std::max(2, std::min(kMaxStages, (int)(100 * 1024 / (p->nstaged * kStageColBytes))));
     *smem_bytes = (size_t)p->nstages * p->nstaged * kStageColBytes;
@@ -236,28 +235,29 @@ void decode_aggs(mbc_result* r, const DevAgg* dev, int nagg, const unsigned long
     }
 }
 
-// Workspace layout: [count:i64 @0][tile_counts: launch_tiles u32][tile_out: launch_tiles + 1 u64]
-//                   [partials: nagg*total_tiles u64][agg out: 8 u64]
+// Workspace layout: [running count: 2 slots i64 @0][agg out: 8 u64 + count @64][tile_counts: launch_tiles u32]
+//                   [tile_out: launch_tiles + 1 u64][partials: nagg*total_tiles u64]
 struct Workspace {
-    long long* count;
+    long long* count;             // two slots: launch i reads slot i & 1 (not the first) and writes slot (i + 1) & 1
     uint32_t* tile_counts;
     unsigned long long* tile_out;
     unsigned long long* partials;
-    unsigned long long* agg_out;
+    unsigned long long* agg_out;  // [kMaxAgg] aggregates, [kMaxAgg] = the count (agg_finish_kernel)
 };
 
 static int32_t carve_workspace(mbc_ctx* ctx, int64_t launch_tiles, int64_t total_tiles, int nagg, Workspace* w) {
+    const size_t head = 64 + round_up((kMaxAgg + 1) * 8, 64);
     size_t counts_bytes = (size_t)round_up(launch_tiles * 4, 64);
-    size_t out_bytes = (size_t)(launch_tiles + 1) * 8;
+    size_t out_bytes = (size_t)round_up((launch_tiles + 1) * 8, 64);
     size_t partial_bytes = (size_t)std::max(nagg, 1) * total_tiles * 8;
-    size_t total = 64 + counts_bytes + out_bytes + partial_bytes + kMaxAgg * 8 + 64;
+    size_t total = head + counts_bytes + out_bytes + partial_bytes + 64;
     MBC_TRY(ensure_workspace(ctx, total));
     char* b = (char*)ctx->ws;
     w->count = (long long*)b;
-    w->tile_counts = (uint32_t*)(b + 64);
-    w->tile_out = (unsigned long long*)(b + 64 + counts_bytes);
-    w->partials = (unsigned long long*)(b + 64 + counts_bytes + out_bytes);
-    w->agg_out = (unsigned long long*)(b + 64 + counts_bytes + out_bytes + partial_bytes);
+    w->agg_out = (unsigned long long*)(b + 64);
+    w->tile_counts = (uint32_t*)(b + head);
+    w->tile_out = (unsigned long long*)(b + head + counts_bytes);
+    w->partials = (unsigned long long*)(b + head + counts_bytes + out_bytes);
     return MBC_OK;
 }
 
@@ -271,6 +271,8 @@ struct ScanJob {
     int64_t total_tiles = 0;
     size_t smem_bytes = 0;
     int max_grid = 1;
+    int launches = 0;             // launches so far: the running count is in slot launches & 1
+    long long* count_slot() const { return w.count + (launches & 1); }
     int grid_per_tiles(int ntiles) const { return std::max(1, std::min(ntiles, max_grid)); }
 };
 
@@ -310,13 +312,12 @@ static int32_t prepare_job(const mbc_table* schema, const ScanRequest& rq, int64
         }
         p.nproj = rq.nproj;
     }
-    MBC_TRY(dev_alloc(ctx, (void**)&r->d_aggs, (kMaxAgg + 1) * 8, true));
+    MBC_TRY(dev_alloc(ctx, (void**)&r->d_aggs, (kMaxAgg + 1) * 8, false));
     MBC_TRY(carve_workspace(ctx, launch_tiles, total_tiles, p.nagg, &job->w));
     job->total_tiles = total_tiles;
     p.total_tiles = (int)total_tiles;
     p.tile_counts = job->w.tile_counts;
     p.tile_out = job->w.tile_out;
-    p.count = job->w.count;
     p.partials = job->w.partials;
     p.out_pos = r->d_pos;
     p.ntiles = INT32_MAX;                         // the grid bound comes from the device; bind_table sets the real count
@@ -345,10 +346,14 @@ static int32_t launch_job(ScanJob* job, int tile_base, bool first) {
     mbc_ctx* ctx = job->r->ctx;
     ScanParams& p = job->p;
     p.tile_base = tile_base;
-    if (first) MBC_CUDA(cudaMemsetAsync(p.count, 0, 8, ctx->stream));   // later launches append at the running offset
+    if (first) job->launches = 0;
     if (p.ntiles == 0) return MBC_OK;
+    p.count_in = job->launches == 0 ? nullptr : job->count_slot();   // later launches append at the running offset
+    p.count_out = job->w.count + ((job->launches + 1) & 1);
     filter_kernel<<<job->grid_per_tiles(p.ntiles), kScanThreads, job->smem_bytes, ctx->stream>>>(p);
-    tile_offsets_kernel<<<1, 1024, 0, ctx->stream>>>(p.tile_counts, p.ntiles, p.tile_out, p.count);
+    tile_offsets_kernel<<<(p.ntiles + kOffsetsPerBlock - 1) / kOffsetsPerBlock, 1024, 0, ctx->stream>>>(p.tile_counts, p.ntiles, p.tile_out,
+                                                                                                      p.count_in, p.count_out);
+    job->launches++;
     ctx->launches += 2;
     if (p.out_pos || p.nproj > 0 || p.nagg > 0) {
         write_kernel<<<p.ntiles, kScanThreads, 0, ctx->stream>>>(p);
@@ -358,29 +363,45 @@ static int32_t launch_job(ScanJob* job, int tile_base, bool first) {
     return MBC_OK;
 }
 
-// aggregate finish + count/aggregate readback (device work of a job is complete after this)
-static int32_t finish_job_device(ScanJob* job, int64_t tiles_done) {
+// aggregate finish + count/aggregate readback.  Synchronous form: the device work of the job is complete after this.
+// Deferred form: everything is queued, the result carries the event and mbc::result_finalize() completes it.
+static int32_t finish_job_device(ScanJob* job, int64_t tiles_done, bool deferred = false) {
     mbc_ctx* ctx = job->r->ctx;
     ScanParams& p = job->p;
     mbc_result* r = job->r;
-    if (tiles_done == 0) MBC_CUDA(cudaMemsetAsync(p.count, 0, 8, ctx->stream));
+    if (job->launches == 0) MBC_CUDA(cudaMemsetAsync(job->w.count, 0, 16, ctx->stream));   // nothing was scanned
     if (p.nagg > 0) {
         AggList list;
         memcpy(list.g, p.aggs, sizeof(list.g));
         agg_finish_kernel<<<p.nagg, 1024, 0, ctx->stream>>>(job->w.partials, (int)job->total_tiles, (int)tiles_done, list,
-                                                           job->w.agg_out);
+                                                           job->w.agg_out, job->count_slot());
         ctx->launches++;
         MBC_CUDA(cudaGetLastError());
     }
     end_timing(ctx);
+    if (r->ev_t1) cudaEventRecord(r->ev_t1, ctx->stream);
     // count + aggregates come back in one small copy
+    if (p.nagg > 0) {
+        MBC_CUDA(cudaMemcpyAsync(r->d_aggs, job->w.agg_out, (kMaxAgg + 1) * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    } else {
+        MBC_CUDA(cudaMemcpyAsync(r->d_aggs + kMaxAgg, job->count_slot(), 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    if (deferred) {
+        r->aggs.resize(p.nagg);
+        for (int a = 0; a < p.nagg; ++a) { r->aggs[a].kind = p.aggs[a].kind; r->aggs[a].type = p.aggs[a].type; }
+        MBC_TRY(pinned_for(r, (void**)&r->h_small, (kMaxAgg + 1) * 8));
+        MBC_CUDA(cudaMemcpyAsync(r->h_small, r->d_aggs, (kMaxAgg + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        r->ev_ready = event_get(ctx);
+        if (!r->ev_ready) MBC_FAIL(MBC_ERR_CUDA, "cudaEventCreate failed");
+        MBC_CUDA(cudaEventRecord(r->ev_ready, ctx->stream));
+        return MBC_OK;
+    }
     unsigned long long host_small[kMaxAgg + 1];
-    MBC_CUDA(cudaMemcpyAsync(r->d_aggs, job->w.agg_out, kMaxAgg * 8, cudaMemcpyDeviceToDevice, ctx->stream));
-    MBC_CUDA(cudaMemcpyAsync(r->d_aggs + kMaxAgg, job->w.count, 8, cudaMemcpyDeviceToDevice, ctx->stream));
     MBC_CUDA(cudaMemcpyAsync(host_small, r->d_aggs, sizeof(host_small), cudaMemcpyDeviceToHost, ctx->stream));
     MBC_CUDA(cudaStreamSynchronize(ctx->stream));
     r->count = (int64_t)host_small[kMaxAgg];
     decode_aggs(r, p.aggs, p.nagg, host_small);
+    if (r->ev_t0 && r->ev_t1 && cudaEventElapsedTime(&r->kernel_ms, r->ev_t0, r->ev_t1) != cudaSuccess) r->kernel_ms = -1.f;
     return MBC_OK;
 }
 
@@ -403,16 +424,24 @@ int32_t run_scan(const ScanRequest& rq, mbc_result** out) {
         r->nrows = t->nrows;
         job.p.sel_bitmap = rq.d_sel_bitmap;
         // the filter pass always leaves the selection as a bitmap; it is the result's bitmap when asked for
-        s = dev_alloc(ctx, (void**)&r->d_bitmap, (size_t)t->words_pad * 4, true);
+        // (the filter writes every word of every tile: only the padding beyond the last tile is zeroed)
+        s = dev_alloc(ctx, (void**)&r->d_bitmap, (size_t)t->words_pad * 4, false);
+        const int64_t written = ntiles * (kTileRows / 32);
+        if (s == MBC_OK && t->words_pad > written &&
+            cudaMemsetAsync(r->d_bitmap + written, 0, (size_t)(t->words_pad - written) * 4, ctx->stream) != cudaSuccess) s = MBC_ERR_CUDA;
         r->bitmap_words32 = t->words_pad;
         job.p.out_bitmap = r->d_bitmap;
     }
     if (s == MBC_OK) {
         bind_table(&job, t);
         begin_timing(ctx);
+        job.r->ev_t0 = event_get(ctx);
+        job.r->ev_t1 = event_get(ctx);
+        if (job.r->ev_t0) cudaEventRecord(job.r->ev_t0, ctx->stream);
         s = launch_job(&job, 0, true);
     }
-    if (s == MBC_OK) s = finish_job(&job, ntiles);
+    const bool deferred = rq.allow_deferred && !(rq.want & (MBC_WANT_HOST | MBC_WANT_TUPLES)) && !getenv("MBC_SYNC_RESULTS");
+    if (s == MBC_OK) s = deferred ? finish_job_device(&job, ntiles, true) : finish_job(&job, ntiles);
     if (s != MBC_OK) {
         if (job.r) mbc_result_free(job.r);
         return s;
@@ -592,7 +621,7 @@ static int32_t run_scan_host(mbc_ctx* ctx, int32_t ncols, const mbc_coldesc* col
         s = launch_job(&job, (int)tiles_done, k == 0);
         tiles_done += job.p.ntiles;
         if (h_counts && s == MBC_OK &&
-            cudaMemcpyAsync(&h_counts[k], job.w.count, 8, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) s = MBC_ERR_CUDA;
+            cudaMemcpyAsync(&h_counts[k], job.count_slot(), 8, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) s = MBC_ERR_CUDA;
         cudaEventRecord(ev_done[b], ctx->stream);
         if (k == 0 && any_late && s == MBC_OK) {                          // the sample decides: late when <= 1/5 of the rows qualify
             // (measured on B200 / PCIe 5: 100 M C2 rows take 17.6 / 33.4 / 80 ms late vs 52 / 52 / 57 ms uploaded at 1 / 10 / 50 %)
@@ -653,6 +682,7 @@ extern "C" int32_t mbc_scan(mbc_table* t, const mbc_term* terms, int32_t nterms,
     rq.want = want;
     rq.aggs = aggs;
     rq.nagg = nagg;
+    rq.allow_deferred = true;
     return run_scan(rq, out);
 }
 

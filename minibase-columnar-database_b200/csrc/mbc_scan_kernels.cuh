@@ -73,13 +73,6 @@ struct DevAgg {
     int32_t staged;      // staged predicate column, or -1
 };
 
-struct DevGather {              // a column phase B gathers from HBM (not staged): prefetched to L2 in phase A
-    const void* ptr;
-    int32_t stride;
-    int32_t col;
-};
-
-constexpr int kMaxGather = 8;
 constexpr int kMaxStaged = 4;                    // 4-byte predicate columns staged through shared memory
 constexpr int kStageColBytes = kTileRows * 4;    // one column of one tile: 16 KB
 
@@ -96,15 +89,14 @@ struct ScanParams {
     int32_t nstages;              // depth of the tile ring (2..kMaxStages)
     const void* staged_src[kMaxStaged];
     int32_t staged_cols[kMaxStaged];   // host bookkeeping: table column of every staged slot
-    int32_t ngather, pad1;
-    DevGather gather[kMaxGather];
     const uint32_t* sel_bitmap;   // optional precomputed selection
     const uint32_t* deleted;      // optional markedDeleted bitmap
     int64_t* out_pos;
     uint32_t* out_bitmap;
     uint32_t* tile_counts;        // qualifying rows per tile (pass 1 -> pass 2)
     unsigned long long* tile_out; // global output offset of every tile (tile_offsets_kernel)
-    long long* count;             // in: running output offset, out: offset after this launch
+    const long long* count_in;    // running output offset before this launch (chunked scans append); NULL = 0
+    long long* count_out;         // ... and after it (a different slot)
     long long* prof;              // optional phase timers (MBC_SCAN_PROFILE builds)
     unsigned long long* partials; // [nagg][total_tiles]
     DevTerm terms[kMaxTerms];
@@ -449,48 +441,70 @@ __global__ void __launch_bounds__(kScanThreads, 2) filter_kernel(const __grid_co
 }
 
 // ---- pass 1.5: tile counts -> tile output offsets -----------------------------------------------------------
-// One block, one round: every thread owns a contiguous run of counts (all of its 128-bit loads are issued
-// before the first use), a two-level warp-shuffle scan combines the 1024 run totals.
+// Block b owns counts [b * 4096, (b + 1) * 4096), four per thread.  It sums every count before its range itself (the
+// counts of even a 500 M-row table are a few hundred KB in L2), so the blocks are independent: no chain, no look-back.
+// `start` is the running output offset left by the previous launch of a chunked scan (0 for the first launch); the
+// last block publishes the new running offset in a DIFFERENT slot, since other blocks may still be reading the old one.
+constexpr int kOffsetsPerBlock = 4096;
 __global__ void __launch_bounds__(1024) tile_offsets_kernel(const uint32_t* counts, int ntiles, unsigned long long* tile_base,
-                                                            long long* running /* in: offset so far, out: + total */) {
+                                                            const long long* running_in, long long* running_out) {
     __shared__ unsigned long long s_warp[32];
+    __shared__ unsigned long long s_prefix;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int per = ((ntiles + 1023) / 1024 + 3) & ~3;             // counts per thread, a multiple of 4
-    const int lo = tid * per;
-    unsigned long long mine = 0;
-    for (int i = lo; i < lo + per && i < ntiles; i += 4) {         // the counts buffer is padded: whole quads are readable
-        const uint4 q = *reinterpret_cast<const uint4*>(counts + i);
-        mine += (unsigned long long)q.x + (i + 1 < ntiles ? q.y : 0u) + (i + 2 < ntiles ? q.z : 0u) + (i + 3 < ntiles ? q.w : 0u);
+    const uint4* counts4 = reinterpret_cast<const uint4*>(counts);   // the buffer is padded: whole quads are readable
+    const int first_quad = blockIdx.x * (kOffsetsPerBlock / 4);
+    const unsigned long long start = running_in ? (unsigned long long)*running_in : 0ull;
+
+    unsigned long long before = 0;                                   // everything ahead of this block
+    for (int i = tid; i < first_quad; i += 1024) {
+        const uint4 q = counts4[i];
+        before += (unsigned long long)q.x + q.y + q.z + q.w;
     }
+    const int i0 = (first_quad + tid) * 4;
+    uint4 q = make_uint4(0u, 0u, 0u, 0u);
+    if (i0 < ntiles) q = counts4[first_quad + tid];
+    if (i0 + 1 >= ntiles) q.y = 0u;
+    if (i0 + 2 >= ntiles) q.z = 0u;
+    if (i0 + 3 >= ntiles) q.w = 0u;
+    const unsigned long long mine = (unsigned long long)q.x + q.y + q.z + q.w;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) before += __shfl_xor_sync(0xFFFFFFFFu, before, o);
     unsigned long long incl = mine;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-        unsigned long long n = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        const unsigned long long n = __shfl_up_sync(0xFFFFFFFFu, incl, o);
         if (lane >= o) incl += n;
     }
-    if (lane == 31) s_warp[warp] = incl;
+    if (lane == 0) s_warp[warp] = before;
     __syncthreads();
-    unsigned long long wsum = s_warp[lane], winc = wsum;           // every warp scans the 32 warp totals itself
+    if (warp == 0) {
+        unsigned long long v = s_warp[lane];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+        if (lane == 0) s_prefix = v;
+    }
+    __syncthreads();
+    if (lane == 31) s_warp[warp] = incl;                             // warp totals of the block's own counts
+    __syncthreads();
+    unsigned long long wsum = s_warp[lane], winc = wsum;             // every warp scans the 32 warp totals itself
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-        unsigned long long n = __shfl_up_sync(0xFFFFFFFFu, winc, o);
+        const unsigned long long n = __shfl_up_sync(0xFFFFFFFFu, winc, o);
         if (lane >= o) winc += n;
     }
     const unsigned long long warp_excl = __shfl_sync(0xFFFFFFFFu, winc - wsum, warp);
-    const unsigned long long total = __shfl_sync(0xFFFFFFFFu, winc, 31);
-    const unsigned long long start = (unsigned long long)*running;
-    unsigned long long run = start + warp_excl + incl - mine;
-    for (int i = lo; i < lo + per && i < ntiles; i += 4) {
-        const uint4 q = *reinterpret_cast<const uint4*>(counts + i);   // L1 hit
+    const unsigned long long block_total = __shfl_sync(0xFFFFFFFFu, winc, 31);
+    unsigned long long run = start + s_prefix + warp_excl + incl - mine;
+    if (i0 < ntiles) {
         const uint32_t c[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
         for (int j = 0; j < 4; ++j)
-            if (i + j < ntiles) { tile_base[i + j] = run; run += c[j]; }
+            if (i0 + j < ntiles) { tile_base[i0 + j] = run; run += c[j]; }
     }
-    __syncthreads();                                               // everyone has read *running
-    if (tid == 0) {
-        tile_base[ntiles] = start + total;                         // end of the last tile: groups read [first, last + 1]
-        *running = (long long)(start + total);
+    if (blockIdx.x == gridDim.x - 1 && tid == 0) {
+        const unsigned long long end = start + s_prefix + block_total;
+        tile_base[ntiles] = end;                                     // end of the last tile: groups read [first, last + 1]
+        *running_out = (long long)end;
     }
 }
 
@@ -767,7 +781,8 @@ struct AggList {
 
 __global__ void __launch_bounds__(1024) agg_finish_kernel(const unsigned long long* partials, int total_tiles,
                                                           int ntiles, const __grid_constant__ AggList list,
-                                                          unsigned long long* out) {
+                                                          unsigned long long* out, const long long* count) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) out[kMaxAgg] = (unsigned long long)*count;   // aggregates + count leave in one copy
     const DevAgg g = list.g[blockIdx.x];
     const unsigned long long* src = partials + (size_t)blockIdx.x * total_tiles;
     __shared__ unsigned long long sh[1024];

@@ -291,6 +291,11 @@ class Result:
     def count(self) -> int:
         return int(N.lib().mbc_result_count(self._h))
 
+    @property
+    def kernel_ms(self) -> float:
+        """Device time of this result's kernels (waits for a deferred result)."""
+        return float(N.lib().mbc_result_kernel_ms(self._h))
+
     def positions(self) -> np.ndarray:
         return _np_from_ptr(N.lib().mbc_result_positions(self._h), self.count * 8, np.int64)
 

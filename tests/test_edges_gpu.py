@@ -98,3 +98,36 @@ def test_many_conjuncts_and_wide_strings(ctx, oracle):
     check_result(oracle, res, exp, [descs[5], descs[4], descs[0]])
     res.close()
     t.close()
+
+
+def test_deferred_results_match_synchronous(ctx, oracle):
+    """Device-resident results of mbc_scan complete asynchronously: several scans are queued before the first count
+    is read; counts, aggregates, device positions / values equal the synchronous (MBC_WANT_HOST) results."""
+    import torch
+    from bench import _CudaArray
+    from util import C2_AGGS, c2_device_table, c2_terms
+    n = 300_000
+    t = c2_device_table(ctx, n)
+    sels = (0.01, 0.1, 0.5, 0.1)
+    want_dev = N.WANT_POSITIONS | N.WANT_COLUMNS | N.WANT_AGG
+    queued = [t.scan(c2_terms(oracle, s), proj=[1, 3], want=want_dev, aggs=C2_AGGS) for s in sels]
+    for s, r in zip(sels, queued):
+        ref = t.scan(c2_terms(oracle, s), proj=[1, 3], want=want_dev | N.WANT_HOST, aggs=C2_AGGS)
+        assert r.count == ref.count > 0 and r.kernel_ms > 0
+        for a in range(len(C2_AGGS)):
+            assert r.agg(a) == ref.agg(a)
+        ptrs = r.device_pointers()
+        pos = torch.as_tensor(_CudaArray(ptrs["positions"], r.count * 8), device="cuda:0").view(torch.int64).cpu().numpy()
+        np.testing.assert_array_equal(pos, ref.positions())
+        p1, s1 = r.column_device(0)
+        i2 = torch.as_tensor(_CudaArray(p1, r.count * s1), device="cuda:0").view(torch.int32).cpu().numpy()
+        np.testing.assert_array_equal(i2, ref.column(0))
+        p2, s2 = r.column_device(1)
+        sv = torch.as_tensor(_CudaArray(p2, r.count * s2), device="cuda:0").cpu().numpy().reshape(-1, s2)
+        np.testing.assert_array_equal(sv[:, :16], ref.column(1))
+        ref.close()
+    dropped = t.scan(c2_terms(oracle, 0.5), proj=[0], want=want_dev)      # freed without ever being read
+    dropped.close()
+    for r in queued:
+        r.close()
+    t.close()
