@@ -350,7 +350,12 @@ static int32_t launch_job(ScanJob* job, int tile_base, bool first) {
     if (p.ntiles == 0) return MBC_OK;
     p.count_in = job->launches == 0 ? nullptr : job->count_slot();   // later launches append at the running offset
     p.count_out = job->w.count + ((job->launches + 1) & 1);
-    filter_kernel<<<job->grid_per_tiles(p.ntiles), kScanThreads, job->smem_bytes, ctx->stream>>>(p);
+    if (p.nterms == 0 && p.sel_bitmap) {
+        const int grid = std::max(1, std::min((p.ntiles + kWarpsPerCta - 1) / kWarpsPerCta, ctx->sm_count * 8));
+        select_bitmap_kernel<<<grid, kScanThreads, 0, ctx->stream>>>(p.sel_bitmap, p.deleted, p.nrows, p.ntiles, p.out_bitmap, p.tile_counts);
+    } else {
+        filter_kernel<<<job->grid_per_tiles(p.ntiles), kScanThreads, job->smem_bytes, ctx->stream>>>(p);
+    }
     tile_offsets_kernel<<<(p.ntiles + kOffsetsPerBlock - 1) / kOffsetsPerBlock, 1024, 0, ctx->stream>>>(p.tile_counts, p.ntiles, p.tile_out,
                                                                                                       p.count_in, p.count_out);
     job->launches++;

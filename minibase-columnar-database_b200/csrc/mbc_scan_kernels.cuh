@@ -440,6 +440,37 @@ __global__ void __launch_bounds__(kScanThreads, 2) filter_kernel(const __grid_co
     }
 }
 
+// ---- pass 1 of a scan that has no predicate terms, only a precomputed selection (bitmap CNF scans, join sides) -------
+// One warp per tile, 128 bits per lane: selection AND NOT deleted, rows past the end cleared, tile count.  Independent
+// warps instead of the filter pass's staged CTA loop: there is nothing to stage, a tile is 512 bytes of bitmap.
+__global__ void __launch_bounds__(kScanThreads) select_bitmap_kernel(const uint32_t* __restrict__ sel, const uint32_t* __restrict__ deleted,
+                                                                     int64_t nrows, int ntiles, uint32_t* __restrict__ out,
+                                                                     uint32_t* __restrict__ tile_counts) {
+    const int lane = threadIdx.x & 31;
+    const int nwarps = gridDim.x * kWarpsPerCta;
+    for (int tile = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5); tile < ntiles; tile += nwarps) {
+        const size_t quad = (size_t)tile * (kTileRows / 128) + lane;
+        uint4 q = __ldg(reinterpret_cast<const uint4*>(sel) + quad);
+        if (deleted) {                                                 // TupleScan.java:85
+            const uint4 d = __ldg(reinterpret_cast<const uint4*>(deleted) + quad);
+            q.x &= ~d.x; q.y &= ~d.y; q.z &= ~d.z; q.w &= ~d.w;
+        }
+        const int64_t row0 = (int64_t)tile * kTileRows + lane * 128;
+        if (row0 + 128 > nrows) {
+            uint32_t* w = reinterpret_cast<uint32_t*>(&q);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int64_t valid = nrows - (row0 + 32 * j);
+                if (valid <= 0) w[j] = 0u;
+                else if (valid < 32) w[j] &= (1u << valid) - 1u;
+            }
+        }
+        reinterpret_cast<uint4*>(out)[quad] = q;
+        const uint32_t c = __reduce_add_sync(0xFFFFFFFFu, (uint32_t)(__popc(q.x) + __popc(q.y) + __popc(q.z) + __popc(q.w)));
+        if (lane == 0) tile_counts[tile] = c;
+    }
+}
+
 // ---- pass 1.5: tile counts -> tile output offsets -----------------------------------------------------------
 // Block b owns counts [b * 4096, (b + 1) * 4096), four per thread.  It sums every count before its range itself (the
 // counts of even a 500 M-row table are a few hundred KB in L2), so the blocks are independent: no chain, no look-back.
