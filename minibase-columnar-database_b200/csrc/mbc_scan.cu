@@ -235,7 +235,7 @@ void decode_aggs(mbc_result* r, const DevAgg* dev, int nagg, const unsigned long
     }
 }
 
-// Workspace layout: [running count: 2 slots i64 @0][agg out: 8 u64 + count @64][tile_counts: launch_tiles u32]
+// Workspace layout: [running count: 2 slots i64 @0][write-pass ticket counter u32 @32][agg out: 8 u64 + count @64][tile_counts: launch_tiles u32]
 //                   [tile_out: launch_tiles + 1 u64][partials: nagg*total_tiles u64]
 struct Workspace {
     long long* count;             // two slots: launch i reads slot i & 1 (not the first) and writes slot (i + 1) & 1
@@ -350,6 +350,7 @@ static int32_t launch_job(ScanJob* job, int tile_base, bool first) {
     if (p.ntiles == 0) return MBC_OK;
     p.count_in = job->launches == 0 ? nullptr : job->count_slot();   // later launches append at the running offset
     p.count_out = job->w.count + ((job->launches + 1) & 1);
+    p.work_counter = reinterpret_cast<unsigned int*>(job->w.count + 4);
     if (p.nterms == 0 && p.sel_bitmap) {
         const int grid = std::max(1, std::min((p.ntiles + kWarpsPerCta - 1) / kWarpsPerCta, ctx->sm_count * 8));
         select_bitmap_kernel<<<grid, kScanThreads, 0, ctx->stream>>>(p.sel_bitmap, p.deleted, p.nrows, p.ntiles, p.out_bitmap, p.tile_counts);
@@ -357,11 +358,21 @@ static int32_t launch_job(ScanJob* job, int tile_base, bool first) {
         filter_kernel<<<job->grid_per_tiles(p.ntiles), kScanThreads, job->smem_bytes, ctx->stream>>>(p);
     }
     tile_offsets_kernel<<<(p.ntiles + kOffsetsPerBlock - 1) / kOffsetsPerBlock, 1024, 0, ctx->stream>>>(p.tile_counts, p.ntiles, p.tile_out,
-                                                                                                      p.count_in, p.count_out);
+                                                                                                      p.count_in, p.count_out, p.work_counter);
     job->launches++;
     ctx->launches += 2;
     if (p.out_pos || p.nproj > 0 || p.nagg > 0) {
-        write_kernel<<<p.ntiles, kScanThreads, 0, ctx->stream>>>(p);
+        const char* pt = getenv("MBC_WRITE_PERSISTENT_TILES");          // tests force either form
+        const int persistent_min_tiles = pt ? atoi(pt) : 49152;
+        if (p.ntiles >= persistent_min_tiles) {
+            static int ctas_per_sm = 0;
+            if (!ctas_per_sm &&
+                (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, write_kernel<true>, kScanThreads, 0) != cudaSuccess || ctas_per_sm < 1))
+                ctas_per_sm = 1;
+            write_kernel<true><<<std::min(p.ntiles, ctx->sm_count * ctas_per_sm), kScanThreads, 0, ctx->stream>>>(p);
+        } else {
+            write_kernel<false><<<p.ntiles, kScanThreads, 0, ctx->stream>>>(p);
+        }
         ctx->launches++;
     }
     MBC_CUDA(cudaGetLastError());

@@ -97,6 +97,7 @@ struct ScanParams {
     unsigned long long* tile_out; // global output offset of every tile (tile_offsets_kernel)
     const long long* count_in;    // running output offset before this launch (chunked scans append); NULL = 0
     long long* count_out;         // ... and after it (a different slot)
+    unsigned int* work_counter;   // group tickets of the write pass (zeroed by tile_offsets_kernel)
     long long* prof;              // optional phase timers (MBC_SCAN_PROFILE builds)
     unsigned long long* partials; // [nagg][total_tiles]
     DevTerm terms[kMaxTerms];
@@ -361,7 +362,7 @@ __device__ __forceinline__ unsigned long long agg_merge(const DevAgg& g, unsigne
 __global__ void __launch_bounds__(kScanThreads, 2) filter_kernel(const __grid_constant__ ScanParams p) {
     extern __shared__ __align__(128) uint8_t stage_mem[];          // [nstages][nstaged][kTileRows] uint32
     __shared__ __align__(8) uint64_t s_full[kMaxStages];
-    __shared__ uint32_t s_wcnt[kWarpsPerCta];
+    __shared__ uint32_t s_wcnt[2][kWarpsPerCta];                   // by tile parity: see the note at the end of the loop
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
@@ -387,9 +388,9 @@ __global__ void __launch_bounds__(kScanThreads, 2) filter_kernel(const __grid_co
     }
     __syncthreads();
 
-    int slot = 0;
+    int slot = 0, flip = 0;
     uint32_t parity = 0;
-    for (long long tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+    for (long long tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, flip ^= 1) {
         if (p.nstaged) mbar_wait(&s_full[slot], parity);
         const uint32_t* stage = reinterpret_cast<const uint32_t*>(stage_mem + (size_t)slot * stage_bytes);
         const int64_t warp_row0 = (int64_t)tile * kTileRows + warp * kWarpRows;
@@ -425,18 +426,19 @@ __global__ void __launch_bounds__(kScanThreads, 2) filter_kernel(const __grid_co
             if ((lane & 7) == 0) p.out_bitmap[(warp_row0 >> 5) + u * (kUnitRows / 32) + (lane >> 3)] = w;
         }
         const uint32_t wcnt = __reduce_add_sync(0xFFFFFFFFu, (uint32_t)__popc(mask));
-        if (lane == 0) s_wcnt[warp] = wcnt;
+        if (lane == 0) s_wcnt[flip][warp] = wcnt;
         __syncthreads();                                           // every warp is done with the slot
         if (tid == 0) {
             uint32_t c = 0;
 #pragma unroll
-            for (int w = 0; w < kWarpsPerCta; ++w) c += s_wcnt[w];
+            for (int w = 0; w < kWarpsPerCta; ++w) c += s_wcnt[flip][w];
             p.tile_counts[tile] = c;
             const long long next = tile + (long long)S * gridDim.x;
             if (p.nstaged && next < p.ntiles) issue_tile(slot, (int)next);
         }
         if (++slot == S) { slot = 0; parity ^= 1u; }
-        // s_wcnt is rewritten only after the next iteration's work, which ends in the barrier above
+        // the other warps run ahead into the next tile while thread 0 is still summing: they write the other half of
+        // s_wcnt, and this half is rewritten only two tiles on, with the next tile's barrier in between
     }
 }
 
@@ -478,7 +480,8 @@ __global__ void __launch_bounds__(kScanThreads) select_bitmap_kernel(const uint3
 // last block publishes the new running offset in a DIFFERENT slot, since other blocks may still be reading the old one.
 constexpr int kOffsetsPerBlock = 4096;
 __global__ void __launch_bounds__(1024) tile_offsets_kernel(const uint32_t* counts, int ntiles, unsigned long long* tile_base,
-                                                            const long long* running_in, long long* running_out) {
+                                                            const long long* running_in, long long* running_out,
+                                                            unsigned int* work_counter) {
     __shared__ unsigned long long s_warp[32];
     __shared__ unsigned long long s_prefix;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -536,6 +539,7 @@ __global__ void __launch_bounds__(1024) tile_offsets_kernel(const uint32_t* coun
         const unsigned long long end = start + s_prefix + block_total;
         tile_base[ntiles] = end;                                     // end of the last tile: groups read [first, last + 1]
         *running_out = (long long)end;
+        *work_counter = 0u;
     }
 }
 
@@ -712,33 +716,13 @@ __device__ __forceinline__ void write_dense_tile(const ScanParams& p, const int 
     }
 }
 
-__global__ void __launch_bounds__(kScanThreads, MBC_WRITE_MIN_CTAS) write_kernel(const __grid_constant__ ScanParams p) {
-    __shared__ uint16_t s_list[kListCap];                          // survivor rows within the group / tile, by rank
-    __shared__ uint32_t s_wtot[kWarpsPerCta];
-    __shared__ unsigned long long s_aggw[kMaxAgg][kWarpsPerCta];
-
+// A sparse group (0 < total <= kSparseMax survivors in ntl tiles from tile0), written by one CTA.
+__device__ __forceinline__ void write_sparse_group(const ScanParams& p, const int tile0, const int ntl, const long long base, const int total,
+                                                   uint16_t* s_list, uint32_t* s_wtot) {
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
-    const int tile = blockIdx.x;
-    const int tile0 = tile & ~(kGroupTiles - 1);
-    const int ntl = min(kGroupTiles, p.ntiles - tile0);            // tiles of this group
-    const long long base = (long long)p.tile_out[tile0];
-    const int total = (int)((long long)p.tile_out[tile0 + ntl] - base);
-    if (total > kSparseMax) {                                      // block-uniform: dense group, every CTA writes its own tile
-        write_dense_tile(p, tile, s_list, s_wtot, s_aggw);
-        return;
-    }
-    // sparse group: its first CTA writes all of it; one partial for the group, the other tiles carry the identity
-    if (tile != tile0) {
-        if (tid < p.nagg) p.partials[(size_t)tid * p.total_tiles + p.tile_base + tile] = agg_identity(p.aggs[tid]);
-        return;
-    }
     const size_t part0 = (size_t)p.tile_base + tile0;
-    if (total == 0) {
-        if (tid < p.nagg) p.partials[(size_t)tid * p.total_tiles + part0] = agg_identity(p.aggs[tid]);
-        return;
-    }
     const int64_t row0 = (int64_t)tile0 * kTileRows;
 
     uint32_t w[kThreadWords];
@@ -802,6 +786,84 @@ __global__ void __launch_bounds__(kScanThreads, MBC_WRITE_MIN_CTAS) write_kernel
             if (lane == 0) p.partials[(size_t)a * p.total_tiles + part0] = v;
         }
     }
+}
+
+
+template <bool kPersistent>
+__global__ void __launch_bounds__(kScanThreads, MBC_WRITE_MIN_CTAS) write_kernel(const __grid_constant__ ScanParams p) {
+    __shared__ uint16_t s_list[kListCap];                          // survivor rows within the group / tile, by rank
+    __shared__ uint32_t s_wtot[kWarpsPerCta];
+    __shared__ unsigned long long s_aggw[kMaxAgg][kWarpsPerCta];
+    const int tid = threadIdx.x;
+  if constexpr (kPersistent) {
+    // Persistent form, for large tables: a few CTAs per SM take the groups by ticket (sparse ones are written whole),
+    // then stride over the tiles (those of dense groups).  One CTA per tile costs ~0.6 ns per CTA of pure dispatch,
+    // which a selective scan of 10^5 tiles, most of them skipped, would pay for nothing (C3 scan: 0.30 -> 0.21 ms).
+    __shared__ uint32_t s_flags[kWarpsPerCta];
+    __shared__ int s_group;
+    const int ngroups = (p.ntiles + kGroupTiles - 1) / kGroupTiles;
+    // groups are handed out by a counter (zeroed by tile_offsets_kernel): a few thousand groups over a few hundred
+    // CTAs would otherwise quantise into whole rounds.  The next ticket is in flight while the current group is written.
+    int ticket = 0;
+    if (tid == 0) ticket = (int)atomicAdd(p.work_counter, 1u);
+    for (;;) {
+        if (tid == 0) s_group = ticket;
+        __syncthreads();
+        const int g = s_group;
+        __syncthreads();                                           // everyone has the group before thread 0 moves on
+        if (g >= ngroups) break;
+        if (tid == 0) ticket = (int)atomicAdd(p.work_counter, 1u);
+        const int tile0 = g * kGroupTiles;
+        const int ntl = min(kGroupTiles, p.ntiles - tile0);
+        const long long base = (long long)p.tile_out[tile0];
+        const int total = (int)((long long)p.tile_out[tile0 + ntl] - base);
+        if (total > kSparseMax) continue;                          // block-uniform
+        for (int i = tid; i < p.nagg * ntl; i += kScanThreads) {   // one partial for the group (below), identity elsewhere
+            const int a = i / ntl, t = i % ntl;
+            if (t > 0 || total == 0) p.partials[(size_t)a * p.total_tiles + p.tile_base + tile0 + t] = agg_identity(p.aggs[a]);
+        }
+        if (total == 0) continue;
+        write_sparse_group(p, tile0, ntl, base, total, s_list, s_wtot);
+    }
+    const int niter = (p.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    for (int it0 = 0; it0 < niter; it0 += kScanThreads) {
+        // which of this CTA's next 256 tiles belong to dense groups: one round of loads for all of them
+        const int tile_t = blockIdx.x + (it0 + tid) * gridDim.x;
+        bool dense = false;
+        if (it0 + tid < niter) {
+            const int tile0 = tile_t & ~(kGroupTiles - 1);
+            const int ntl = min(kGroupTiles, p.ntiles - tile0);
+            dense = (long long)(p.tile_out[tile0 + ntl] - p.tile_out[tile0]) > (long long)kSparseMax;
+        }
+        const uint32_t flags = __ballot_sync(0xFFFFFFFFu, dense);
+        __syncthreads();                                           // the previous round is done with s_flags
+        if ((tid & 31) == 0) s_flags[tid >> 5] = flags;
+        __syncthreads();
+        const int n = min(kScanThreads, niter - it0);
+        for (int j = 0; j < n; ++j) {
+            if (!((s_flags[j >> 5] >> (j & 31)) & 1u)) continue;   // block-uniform
+            __syncthreads();                                       // the shared arrays are reused from tile to tile
+            write_dense_tile(p, blockIdx.x + (it0 + j) * gridDim.x, s_list, s_wtot, s_aggw);
+        }
+    }
+  } else {
+    // One CTA per tile: the hardware scheduler balances them (2 % faster than the persistent form on 10^4 tiles).
+    const int tile = blockIdx.x;
+    const int tile0 = tile & ~(kGroupTiles - 1);
+    const int ntl = min(kGroupTiles, p.ntiles - tile0);            // tiles of this group
+    const long long base = (long long)p.tile_out[tile0];
+    const int total = (int)((long long)p.tile_out[tile0 + ntl] - base);
+    if (total > kSparseMax) {                                      // block-uniform: dense group, every CTA writes its own tile
+        write_dense_tile(p, tile, s_list, s_wtot, s_aggw);
+        return;
+    }
+    // sparse group: its first CTA writes all of it; one partial for the group, the other tiles carry the identity
+    if (tile != tile0 || total == 0) {
+        if (tid < p.nagg) p.partials[(size_t)tid * p.total_tiles + p.tile_base + tile] = agg_identity(p.aggs[tid]);
+        return;
+    }
+    write_sparse_group(p, tile0, ntl, base, total, s_list, s_wtot);
+  }
 }
 
 // Reduce the per-tile partials of one aggregate (fixed association => reproducible sums): thread i folds

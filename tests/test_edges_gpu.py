@@ -131,3 +131,25 @@ def test_deferred_results_match_synchronous(ctx, oracle):
     for r in queued:
         r.close()
     t.close()
+
+
+def test_both_write_pass_forms(ctx, oracle, monkeypatch):
+    """The write pass has a one-CTA-per-tile form and a persistent form (tables of >= 49152 tiles); both are forced
+    here over the same mixed table: an all-qualifying stretch (dense groups), a sparse stretch and an empty one."""
+    n = 400_000
+    rng = np.random.default_rng(11)
+    key = np.concatenate([np.zeros(150_000, np.int32), rng.integers(0, 100, 150_000).astype(np.int32),
+                          np.full(100_000, 1000, np.int32)])
+    descs = [(1, 4), (2, 4), (0, 16)]
+    cols = [key, rng.random(n).astype(np.float32), oracle.synth_str(7, 3, n, 16, 0)]
+    t = load_table(ctx, descs, cols)
+    terms = [oracle.Term(oracle.OP_LT, ("col", 0), ("int", 3), 0)]
+    aggs = [(0, 0), (1, 0), (1, 1), (2, 1), (3, 1)]
+    exp = oracle.scan(descs, cols, terms, proj=[2, 1, 0], aggs=aggs)
+    assert 150_000 < exp["count"] < 160_000
+    for force in ("1", "1000000000"):
+        monkeypatch.setenv("MBC_WRITE_PERSISTENT_TILES", force)
+        res = t.scan(terms, proj=[2, 1, 0], want=ALL, aggs=aggs)
+        check_result(oracle, res, exp, [descs[2], descs[1], descs[0]])
+        res.close()
+    t.close()
