@@ -197,20 +197,52 @@ struct BuildParams {
     int64_t nchunks;
     int32_t stride, is_str;
     int32_t chunk_rows;       // R (multiple of 1024)
-    int32_t v0, nv;           // value ids handled by this pass: [v0, v0+nv)
-    unsigned int* ticket;
+    int32_t npass;            // the values are split into npass slices of nv_per; CTA b builds slice b % npass
+    int32_t nv_per;
+    int32_t identity;         // direct mode and every value of [kmin, kmax] occurs: id = value - kmin
 };
 
 constexpr int kMaxPerThread = 8192 / kBuildThreads;        // rows of one chunk a thread handles (chunk_rows <= 8192)
 
+// Fill of one chunk for <= 32 values (always chunk_rows = 8192): lane v assembles value v's word from one ballot per id
+// bit, so the cost does not depend on how many distinct values a warp sees.
+template <bool IDENT, bool FULL>
+__device__ __forceinline__ void fill_few_values(const BuildParams& p, uint32_t* sm, const int32_t (&pv)[kMaxPerThread], int nv, int v0,
+                                                int64_t row0) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int bits = 32 - __clz(max(nv - 1, 1));
+    uint32_t inv[5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) inv[k] = ((lane >> k) & 1) ? 0u : ~0u;
+    uint32_t* mine = sm + lane * (8192 / 32);
+    const int sw = (lane & 7) << 2;
+    const int base = IDENT ? (int)p.h.kmin + v0 : v0;
+#pragma unroll
+    for (int q = 0; q < kMaxPerThread; ++q) {
+        int id = IDENT ? pv[q] - base : (int)__ldg(p.h.id_of + (uint32_t)((long long)pv[q] - p.h.kmin)) - base;
+        bool ok = (unsigned)id < (unsigned)nv;
+        if (!FULL) ok = ok && row0 + threadIdx.x + q * kBuildThreads < p.nrows;
+        uint32_t w = __ballot_sync(0xFFFFFFFFu, ok);
+#pragma unroll
+        for (int k = 0; k < 5; ++k)
+            if (k < bits) w &= __ballot_sync(0xFFFFFFFFu, (id >> k) & 1) ^ inv[k];
+        if (lane < nv) mine[(warp + q * (kBuildThreads / 32)) ^ sw] = w;
+    }
+}
+
 __global__ void __launch_bounds__(kBuildThreads, 2) bitmap_build_kernel(const __grid_constant__ BuildParams p) {
     extern __shared__ uint4 sm4[];
     uint32_t* sm = reinterpret_cast<uint32_t*>(sm4);
+    const int pass = blockIdx.x % p.npass;                // value slices are a grid dimension, not successive launches: the
+    const int v0 = pass * p.nv_per;                       // column is read once from HBM (the other slices hit L2) and one
+    const int nv = (int)min((int64_t)p.nv_per, p.nvalues_total - v0);   // slice's row work overlaps another's write-out
+    const int cta = blockIdx.x / p.npass, nctas = gridDim.x / p.npass;
     const int wpc = p.chunk_rows >> 5;                    // words per value per chunk
-    const int total_quads = p.nv * wpc / 4;
+    const int total_quads = nv * wpc / 4;
     const int lane = threadIdx.x & 31;
     const int per = p.chunk_rows / kBuildThreads;         // 2..16 rows per thread per chunk
     const bool fast = p.h.direct && !p.deleted;
+    const bool few = fast && p.nvalues_total <= 32 && p.chunk_rows == 8192;
     const int32_t* col32 = reinterpret_cast<const int32_t*>(p.col);
 
     for (int i = threadIdx.x; i < total_quads; i += kBuildThreads) sm4[i] = make_uint4(0, 0, 0, 0);
@@ -218,27 +250,41 @@ __global__ void __launch_bounds__(kBuildThreads, 2) bitmap_build_kernel(const __
     // chunks are assigned statically (no CTA depends on another); the column values of the NEXT chunk are
     // loaded while the current chunk's matrix streams out, so their HBM latency is off the critical path
     int32_t pv[kMaxPerThread];
-    int64_t chunk = blockIdx.x;
+    int64_t chunk = cta;
     if (fast && chunk < p.nchunks) {
 #pragma unroll
         for (int q = 0; q < kMaxPerThread; ++q)
             if (q < per) pv[q] = col32[chunk * p.chunk_rows + threadIdx.x + q * kBuildThreads];   // columns are padded: in bounds
     }
     __syncthreads();
-    for (; chunk < p.nchunks; chunk += gridDim.x) {
+    // Shared-memory matrix [value][word of the chunk].  Rows are a multiple of 32 words, so the words of one chunk column
+    // would all fall into ONE bank: the word index is XOR-swizzled with the value id at 16-byte granularity (8 banks
+    // instead of 1; the write-out undoes it quad by quad).
+    const int qshift = 31 - __clz(wpc >> 2);              // log2(quads per value row), >= 3
+    for (; chunk < p.nchunks; chunk += nctas) {
         const int64_t row0 = chunk * p.chunk_rows;
-        if (fast) {
+        const bool full = row0 + p.chunk_rows <= p.nrows;
+        if (few) {
+            if (p.identity) {
+                if (full) fill_few_values<true, true>(p, sm, pv, nv, v0, row0);
+                else fill_few_values<true, false>(p, sm, pv, nv, v0, row0);
+            } else {
+                if (full) fill_few_values<false, true>(p, sm, pv, nv, v0, row0);
+                else fill_few_values<false, false>(p, sm, pv, nv, v0, row0);
+            }
+        } else if (fast) {
 #pragma unroll
             for (int q = 0; q < kMaxPerThread; ++q) {
                 if (q < per) {                                              // warp-uniform
                     const int r = threadIdx.x + q * kBuildThreads;          // a warp's 32 rows = one word column
                     int id = -1;
-                    if (row0 + r < p.nrows) {
-                        id = (int)__ldg(p.h.id_of + (uint32_t)((long long)pv[q] - p.h.kmin)) - p.v0;
-                        if (id < 0 || id >= p.nv) id = -1;
+                    if (full || row0 + r < p.nrows) {
+                        const uint32_t k = (uint32_t)((long long)pv[q] - p.h.kmin);
+                        id = (int)(p.identity ? k : __ldg(p.h.id_of + k)) - v0;
+                        if ((unsigned)id >= (unsigned)nv) id = -1;
                     }
                     const uint32_t group = __match_any_sync(0xFFFFFFFFu, id);
-                    if (id >= 0 && (group & ((1u << lane) - 1)) == 0) sm[id * wpc + (r >> 5)] = group;   // leader of its value group
+                    if (id >= 0 && (group & ((1u << lane) - 1)) == 0) sm[id * wpc + ((r >> 5) ^ ((id & 7) << 2))] = group;   // leader of its value group
                 }
             }
         } else {
@@ -247,30 +293,32 @@ __global__ void __launch_bounds__(kBuildThreads, 2) bitmap_build_kernel(const __
                 int id = -1;
                 if (row < p.nrows && !(p.deleted && ((p.deleted[row >> 5] >> (row & 31)) & 1u))) {
                     if (p.h.direct) {
-                        id = (int)__ldg(p.h.id_of + (uint32_t)((long long)col32[row] - p.h.kmin)) - p.v0;
+                        id = (int)__ldg(p.h.id_of + (uint32_t)((long long)col32[row] - p.h.kmin)) - v0;
                     } else {
                         int s = probe<false>(p.h, p.col, p.stride, p.is_str != 0, row);
-                        if (s >= 0) id = (int)p.h.slot_id[s] - p.v0;
+                        if (s >= 0) id = (int)p.h.slot_id[s] - v0;
                     }
-                    if (id < 0 || id >= p.nv) id = -1;
+                    if (id < 0 || id >= nv) id = -1;
                 }
                 const uint32_t group = __match_any_sync(0xFFFFFFFFu, id);
-                if (id >= 0 && (group & ((1u << lane) - 1)) == 0) sm[id * wpc + (r >> 5)] = group;
+                if (id >= 0 && (group & ((1u << lane) - 1)) == 0) sm[id * wpc + ((r >> 5) ^ ((id & 7) << 2))] = group;
             }
         }
         __syncthreads();
-        const int64_t next = chunk + gridDim.x;
+        const int64_t next = chunk + nctas;
         if (fast && next < p.nchunks) {
 #pragma unroll
             for (int q = 0; q < kMaxPerThread; ++q)
                 if (q < per) pv[q] = col32[next * p.chunk_rows + threadIdx.x + q * kBuildThreads];
         }
-        // chunk-major layout: this pass's values of this chunk are ONE contiguous block; the matrix is zeroed for
+        // chunk-major layout: this slice's values of this chunk are ONE contiguous block; the matrix is zeroed for
         // the next chunk in the same sweep
-        uint4* dst4 = reinterpret_cast<uint4*>(p.bitmaps + ((int64_t)chunk * p.nvalues_total + p.v0) * wpc);
+        uint4* dst4 = reinterpret_cast<uint4*>(p.bitmaps + ((int64_t)chunk * p.nvalues_total + v0) * wpc);
         for (int i = threadIdx.x; i < total_quads; i += kBuildThreads) {
-            dst4[i] = sm4[i];
-            sm4[i] = make_uint4(0, 0, 0, 0);
+            const int v = i >> qshift;
+            const int src = (v << qshift) + ((i & ((1 << qshift) - 1)) ^ (v & 7));
+            dst4[i] = sm4[src];
+            sm4[src] = make_uint4(0, 0, 0, 0);
         }
         __syncthreads();
     }
@@ -492,12 +540,10 @@ extern "C" int32_t mbc_bitmap_build(mbc_table* t, int32_t col) {
         }
         const int max_nv = (int)std::min<int64_t>(D, (int64_t)(smem_budget / (R / 8)));
         bi.chunk_rows = R;
-        unsigned int* d_ticket = nullptr;
-        MBC_TRY(dev_alloc(ctx, (void**)&d_ticket, 4, true));
         MBC_CUDA(cudaFuncSetAttribute(bitmap_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_budget));
         MBC_CUDA(cudaStreamSynchronize(ctx->stream));        // the allocation above is not kernel time
         begin_timing(ctx);
-        for (int64_t v0 = 0; v0 < D; v0 += max_nv) {
+        {
             BuildParams p{};
             p.h = h;
             p.col = c.d;
@@ -510,18 +556,18 @@ extern "C" int32_t mbc_bitmap_build(mbc_table* t, int32_t col) {
             p.nchunks = t->nrows_pad / R;                // nrows_pad is a multiple of kPadRows = 8192 >= R
             p.stride = c.stride;
             p.is_str = is_str;
-            p.v0 = (int)v0;
-            p.nv = (int)std::min<int64_t>(max_nv, D - v0);
-            p.ticket = d_ticket;
-            MBC_CUDA(cudaMemsetAsync(d_ticket, 0, 4, ctx->stream));
-            size_t smem = (size_t)p.nv * (R / 8);
+            p.npass = (int)((D + max_nv - 1) / max_nv);
+            p.nv_per = (int)(((D + p.npass - 1) / p.npass + 3) & ~3ll);       // even slices, whole quads
+            p.npass = (int)((D + p.nv_per - 1) / p.nv_per);
+            p.identity = direct && D == (int64_t)h.range;
+            size_t smem = (size_t)p.nv_per * (R / 8);
             int per_sm = 1;
             if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bitmap_build_kernel, kBuildThreads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
-            int grid = (int)std::min<int64_t>(p.nchunks, (int64_t)ctx->sm_count * per_sm);
-            bitmap_build_kernel<<<grid, kBuildThreads, smem, ctx->stream>>>(p);
+            int64_t grid = std::min<int64_t>(p.nchunks * p.npass, (int64_t)ctx->sm_count * per_sm);
+            grid = std::max<int64_t>(grid / p.npass, 1) * p.npass;           // every chunk stride carries all slices
+            bitmap_build_kernel<<<(int)grid, kBuildThreads, smem, ctx->stream>>>(p);
             ctx->launches++;
         }
-        dev_free(ctx, d_ticket);
         end_timing(ctx);
     } else {
         begin_timing(ctx);
