@@ -27,6 +27,23 @@ namespace mbc {
 
 __device__ __forceinline__ bool test_bit(const uint32_t* bm, int64_t r) { return (bm[r >> 5] >> (r & 31)) & 1u; }
 
+// L2 residency hints of the equi-join's counting pass: the per-group tables (n_outer / n_inner, 4 B per key) are hit at
+// random by every inner row and must stay in L2 while gigabytes of key / value columns stream past them.  Table accesses
+// carry an evict_last policy, the streamed columns are read evict-first (ld.global.cs).
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ uint32_t ld_keep_u32(const uint32_t* p, uint64_t pol) {
+    uint32_t v;
+    asm volatile("ld.global.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ void red_add_keep_u32(uint32_t* p, uint32_t v, uint64_t pol) {
+    asm volatile("red.global.add.L2::cache_hint.u32 [%0], %1, %2;" ::"l"(p), "r"(v), "l"(pol) : "memory");
+}
+
 __device__ __forceinline__ uint32_t mix32(uint32_t x) {
     x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
     return x;
@@ -305,7 +322,7 @@ __device__ __forceinline__ long long group_of_outer(const GroupMap& g, int64_t o
 // group of an INNER row, -1 when no outer row carries that key
 __device__ __forceinline__ long long group_of_inner(const GroupMap& g, int64_t i) {
     if (g.mode == 0) {
-        long long k = (long long)reinterpret_cast<const int32_t*>(g.ikey[0].ptr)[i];
+        long long k = (long long)__ldcs(reinterpret_cast<const int32_t*>(g.ikey[0].ptr) + i);
         return (k < g.kmin || k > g.kmax) ? -1 : k - g.kmin;
     }
     uint32_t s = key_hash(g.ikey, g.nkeys, g.okey, i) & g.mask;
@@ -323,7 +340,7 @@ struct JoinAgg {
     const void* src;      // column of the side the aggregate reads
     int32_t kind, type;   // MBC_AGG_*, MBC_ATTR_INTEGER/REAL
     int32_t side;         // 1 outer, 2 inner, 0 COUNT
-    int32_t pad;
+    int32_t slot;         // unique-key path: word of the group slot that carries this outer-side value (1..3)
 };
 
 struct EquiParams {
@@ -332,8 +349,9 @@ struct EquiParams {
     uint32_t* n_outer;
     uint32_t* n_inner;
     uint32_t* inner_match;         // optional bitmap of inner rows that found a partner
-    int* overflow;
+    int* overflow;                 // [0] hash table overflow, [1] some key occurs on more than one outer row, [2] selected outer rows
     int32_t nagg, pad;
+    int32_t pre[2];                // unique path: the (up to two) inner-side aggregates whose inputs are loaded with the keys, or -1
     JoinAgg aggs[kMaxJoinAgg];
     unsigned long long* partials;  // [nagg][gridDim.x]
 };
@@ -361,13 +379,14 @@ __global__ void __launch_bounds__(256) join_outer_count_kernel(const __grid_cons
         if (!side_selected(p.outer, o)) continue;
         long long g = group_of_outer(p.g, o, true);
         if (g < 0) { *p.overflow = 1; return; }
-        atomicAdd(p.n_outer + g, 1u);
+        if (atomicAdd(p.n_outer + g, 1u) != 0u) p.overflow[1] = 1;
+        atomicAdd(p.overflow + 2, 1);                      // selected outer rows (dense-key test of the unique path)
     }
 }
 
 __device__ __forceinline__ void agg_fold(const JoinAgg& a, bool integral, long long& ai, double& af, int64_t row, unsigned long long weight) {
     if (a.kind == MBC_AGG_COUNT) { ai += (long long)weight; return; }
-    uint32_t bits = reinterpret_cast<const uint32_t*>(a.src)[row];
+    uint32_t bits = __ldcs(reinterpret_cast<const uint32_t*>(a.src) + row);
     if (integral) {
         long long v = (int32_t)bits;
         if (a.kind == MBC_AGG_SUM) ai += v * (long long)weight;
@@ -394,14 +413,15 @@ __global__ void __launch_bounds__(256) join_agg_pass_kernel(const __grid_constan
         af[a] = (g.kind == MBC_AGG_MIN) ? (double)INFINITY : (g.kind == MBC_AGG_MAX) ? (double)-INFINITY : 0.0;
     }
     const JoinSide& s = SIDE == 2 ? p.inner : p.outer;
+    const uint64_t keep = l2_policy_evict_last();
     const int64_t nrows32 = (s.nrows + 31) & ~31ll;
     for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < nrows32; r += (int64_t)gridDim.x * blockDim.x) {
         unsigned long long weight = 0;
         if (side_selected(s, r)) {
             long long g = SIDE == 2 ? group_of_inner(p.g, r) : group_of_outer(p.g, r, false);
             if (g >= 0) {
-                weight = SIDE == 2 ? p.n_outer[g] : p.n_inner[g];
-                if (SIDE == 2 && weight) atomicAdd(p.n_inner + g, 1u);
+                weight = SIDE == 2 ? ld_keep_u32(p.n_outer + g, keep) : p.n_inner[g];
+                if (SIDE == 2 && weight) red_add_keep_u32(p.n_inner + g, 1u, keep);
             }
         }
         if (SIDE == 2 && p.inner_match) {
@@ -444,6 +464,150 @@ __global__ void __launch_bounds__(256) join_agg_pass_kernel(const __grid_constan
                 rf = additive ? rf + xf : g.kind == MBC_AGG_MIN ? fmin(rf, xf) : fmax(rf, xf);
             }
             p.partials[(size_t)a * gridDim.x + blockIdx.x] = integral ? (unsigned long long)ri : (unsigned long long)__double_as_longlong(rf);
+        }
+        __syncthreads();
+    }
+}
+
+// ---- unique-key aggregate path (PK-FK joins, aggregates only) ------------------------------------------------------
+// When every join key occurs on at most one outer row and no pair list is wanted, a pair is (inner row, THE outer row
+// of its key): a 1-bit-per-key presence bitmap plus a slot of the outer-side aggregate inputs per key, and a single
+// pass over the inner rows folds every aggregate from one bit test and ONE random slot read per row -- no n_inner
+// atomics, no outer pass.  The general path keeps two 4-byte tables per key (a random read and a random atomic per
+// inner row); for 10 M keys they do not stay in L2 next to the streamed columns and most accesses go to HBM as 64-byte
+// fetches, which is what bounds it.
+template <int VALW>      // value words per key: 0, 1, 2 or 4 (three columns are padded to four)
+__global__ void __launch_bounds__(256) join_slot_build_kernel(const __grid_constant__ EquiParams p, uint32_t* present, uint32_t* slots,
+                                                              const void* c1, const void* c2, const void* c3) {
+    const int32_t* key = reinterpret_cast<const int32_t*>(p.g.okey[0].ptr);
+    for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < p.outer.nrows; o += (int64_t)gridDim.x * blockDim.x) {
+        if (!side_selected(p.outer, o)) continue;
+        const long long g = (long long)key[o] - p.g.kmin;
+        atomicOr(present + (g >> 5), 1u << (g & 31));
+        if (VALW == 1) slots[g] = reinterpret_cast<const uint32_t*>(c1)[o];
+        if (VALW == 2) reinterpret_cast<uint2*>(slots)[g] = make_uint2(reinterpret_cast<const uint32_t*>(c1)[o], reinterpret_cast<const uint32_t*>(c2)[o]);
+        if (VALW == 4) reinterpret_cast<uint4*>(slots)[g] = make_uint4(reinterpret_cast<const uint32_t*>(c1)[o], reinterpret_cast<const uint32_t*>(c2)[o],
+                                                                       reinterpret_cast<const uint32_t*>(c3)[o], 0u);
+    }
+}
+
+// One 64-bit accumulator per aggregate (an aggregate is either integral or real, never both): half the registers of an
+// (int64, double) pair, which is what sets this kernel's occupancy.
+__device__ __forceinline__ unsigned long long acc_identity(const JoinAgg& g, bool integral) {
+    if (integral) return (unsigned long long)((g.kind == MBC_AGG_MIN) ? (long long)INT32_MAX : (g.kind == MBC_AGG_MAX) ? (long long)INT32_MIN : 0ll);
+    return (unsigned long long)__double_as_longlong((g.kind == MBC_AGG_MIN) ? (double)INFINITY : (g.kind == MBC_AGG_MAX) ? (double)-INFINITY : 0.0);
+}
+__device__ __forceinline__ unsigned long long acc_merge(const JoinAgg& g, bool integral, unsigned long long x, unsigned long long y) {
+    const bool additive = g.kind == MBC_AGG_COUNT || g.kind == MBC_AGG_SUM;
+    if (integral) {
+        const long long a = (long long)x, b = (long long)y;
+        return (unsigned long long)(additive ? a + b : g.kind == MBC_AGG_MIN ? min(a, b) : max(a, b));
+    }
+    const double a = __longlong_as_double((long long)x), b = __longlong_as_double((long long)y);
+    return (unsigned long long)__double_as_longlong(additive ? a + b : g.kind == MBC_AGG_MIN ? fmin(a, b) : fmax(a, b));
+}
+__device__ __forceinline__ unsigned long long acc_fold_bits(const JoinAgg& g, bool integral, unsigned long long acc, uint32_t bits) {
+    if (integral) return acc_merge(g, true, acc, (unsigned long long)(long long)(int32_t)bits);
+    return acc_merge(g, false, acc, (unsigned long long)__double_as_longlong((double)__uint_as_float(bits)));
+}
+
+constexpr int kJoinBatch = 4;      // inner rows a thread has in flight: key -> slot -> value loads are dependent HBM round trips
+
+template <int VALW, bool DENSE>      // DENSE: every key of [kmin, kmax] is on an outer row, no presence test
+__global__ void __launch_bounds__(256, 4) join_unique_pass_kernel(const __grid_constant__ EquiParams p, const uint32_t* __restrict__ present,
+                                                                  const uint32_t* __restrict__ slots) {
+    __shared__ unsigned long long sh[kMaxJoinAgg][8];
+    unsigned long long acc[kMaxJoinAgg];
+#pragma unroll
+    for (int a = 0; a < kMaxJoinAgg; ++a)                 // static indices everywhere: the accumulators live in registers
+        acc[a] = acc_identity(p.aggs[a], p.aggs[a].kind == MBC_AGG_COUNT || p.aggs[a].type == MBC_ATTR_INTEGER);
+    const uint64_t keep = l2_policy_evict_last();
+    const int32_t* fk = reinterpret_cast<const int32_t*>(p.g.ikey[0].ptr);
+    const int64_t nrows32 = (p.inner.nrows + 31) & ~31ll;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;               // a multiple of 32: a warp's rows stay consecutive
+    const uint32_t* pre_src0 = p.pre[0] >= 0 ? reinterpret_cast<const uint32_t*>(p.aggs[p.pre[0] & (kMaxJoinAgg - 1)].src) : nullptr;
+    const uint32_t* pre_src1 = p.pre[1] >= 0 ? reinterpret_cast<const uint32_t*>(p.aggs[p.pre[1] & (kMaxJoinAgg - 1)].src) : nullptr;
+    for (int64_t r0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r0 < nrows32; r0 += stride * kJoinBatch) {
+        long long k[kJoinBatch];
+        uint32_t pre0[kJoinBatch], pre1[kJoinBatch];
+#pragma unroll
+        for (int b = 0; b < kJoinBatch; ++b) {                            // round trip 1: the keys, and the inputs of the first
+            const int64_t r = r0 + b * stride;                            // two inner-side aggregates (they do not depend on the
+            const bool sel = side_selected(p.inner, r);                   // key; a row without a partner wastes its 8 bytes)
+            k[b] = sel ? (long long)__ldcs(fk + r) : p.g.kmin - 1;
+            pre0[b] = (sel && pre_src0) ? __ldcs(pre_src0 + r) : 0u;
+            pre1[b] = (sel && pre_src1) ? __ldcs(pre_src1 + r) : 0u;
+        }
+        uint32_t pw[kJoinBatch], v1[kJoinBatch], v2[kJoinBatch], v3[kJoinBatch];
+#pragma unroll
+        for (int b = 0; b < kJoinBatch; ++b) {                            // round trip 2: presence word and value slot together
+            pw[b] = v1[b] = v2[b] = v3[b] = 0u;
+            if (k[b] >= p.g.kmin && k[b] <= p.g.kmax) {
+                const long long g = k[b] - p.g.kmin;
+                pw[b] = DENSE ? 1u : __ldg(present + (g >> 5)) >> (g & 31);
+                if (VALW == 1) v1[b] = ld_keep_u32(slots + g, keep);
+                if (VALW == 2) {
+                    const uint2 v = __ldg(reinterpret_cast<const uint2*>(slots) + g);
+                    v1[b] = v.x; v2[b] = v.y;
+                }
+                if (VALW == 4) {
+                    const uint4 v = __ldg(reinterpret_cast<const uint4*>(slots) + g);
+                    v1[b] = v.x; v2[b] = v.y; v3[b] = v.z;
+                }
+            }
+        }
+        bool hit[kJoinBatch];
+        int nhit = 0;
+#pragma unroll
+        for (int b = 0; b < kJoinBatch; ++b) {
+            hit[b] = pw[b] & 1u;
+            nhit += hit[b];
+            if (p.inner_match) {
+                const int64_t r = r0 + b * stride;
+                const uint32_t word = __ballot_sync(0xFFFFFFFFu, hit[b]);
+                if ((threadIdx.x & 31) == 0 && r < nrows32) p.inner_match[r >> 5] = word;
+            }
+        }
+#pragma unroll
+        for (int a = 0; a < kMaxJoinAgg; ++a) {
+            if (a >= p.nagg) break;
+            const JoinAgg& g = p.aggs[a];
+            const bool integral = g.kind == MBC_AGG_COUNT || g.type == MBC_ATTR_INTEGER;
+            if (g.kind == MBC_AGG_COUNT) {
+                acc[a] += (unsigned long long)nhit;
+            } else if (g.side == 2) {                                     // round trip 3 (per inner-side aggregate): its column
+                uint32_t bits[kJoinBatch];
+#pragma unroll
+                for (int b = 0; b < kJoinBatch; ++b) {
+                    if (a == p.pre[0]) bits[b] = pre0[b];
+                    else if (a == p.pre[1]) bits[b] = pre1[b];
+                    else if (hit[b]) bits[b] = __ldcs(reinterpret_cast<const uint32_t*>(g.src) + r0 + b * stride);
+                }
+#pragma unroll
+                for (int b = 0; b < kJoinBatch; ++b)
+                    if (hit[b]) acc[a] = acc_fold_bits(g, integral, acc[a], bits[b]);
+            } else {
+#pragma unroll
+                for (int b = 0; b < kJoinBatch; ++b)
+                    if (hit[b]) acc[a] = acc_fold_bits(g, integral, acc[a], g.slot == 1 ? v1[b] : g.slot == 2 ? v2[b] : v3[b]);
+            }
+        }
+    }
+    // block reduction, one partial per block per aggregate (fixed order -> reproducible sums)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int a = 0; a < kMaxJoinAgg; ++a) {
+        if (a >= p.nagg) break;
+        const JoinAgg& g = p.aggs[a];
+        const bool integral = g.kind == MBC_AGG_COUNT || g.type == MBC_ATTR_INTEGER;
+        unsigned long long v = acc[a];
+        for (int o = 16; o > 0; o >>= 1) v = acc_merge(g, integral, v, __shfl_xor_sync(0xFFFFFFFFu, v, o));
+        if (lane == 0) sh[a][warp] = v;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned long long r = sh[a][0];
+            for (int w8 = 1; w8 < 8; ++w8) r = acc_merge(g, integral, r, sh[a][w8]);
+            p.partials[(size_t)a * gridDim.x + blockIdx.x] = r;
         }
         __syncthreads();
     }
@@ -757,7 +921,7 @@ extern "C" int32_t mbc_bitmap_join(mbc_table* outer, mbc_table* inner, const mbc
         }
         JTRY(talloc((void**)&ep.n_outer, (size_t)g.ngroups * 4, true));
         JTRY(talloc((void**)&ep.n_inner, (size_t)g.ngroups * 4, true));
-        JTRY(talloc((void**)&ep.overflow, 4, true));
+        JTRY(talloc((void**)&ep.overflow, 16, true));
         ep.outer = so;
         ep.inner = si;
         ep.nagg = nagg;
@@ -810,7 +974,53 @@ extern "C" int32_t mbc_bitmap_join(mbc_table* outer, mbc_table* inner, const mbc
             ep_inner.partials = ep.partials;
             part.resize((size_t)(nagg + 1) * pgrid);
         }
-        if (inner->nrows > 0) {
+        // unique-key aggregate path: direct addressing, aggregates only, every key on at most one outer row, and at most
+        // three distinct outer-side aggregate columns (they ride in the key's slot)
+        bool unique_fast = false;
+        // (an inner side thinned by a selection bitmap keeps the general path: measured 3.1 ms vs 4.5 ms on C4's 10 % run --
+        // most lanes of the batched kernel idle there)
+        const char* force = getenv("MBC_JOIN_UNIQUE");               // tests: "0" = never, "1" = whenever legal
+        const bool allow = force ? atoi(force) != 0 : !si.sel;
+        if (direct && !want_pairs && allow && outer->nrows > 0 && inner->nrows > 0 && g.kmin <= g.kmax) {
+            const void* slot_cols[3] = {nullptr, nullptr, nullptr};
+            int nslot = 0;
+            bool fits = true;
+            for (int a = 0; a < ep_inner.nagg && fits; ++a) {
+                JoinAgg& ga = ep_inner.aggs[a];
+                if (ga.side != 1) continue;
+                int w = -1;
+                for (int c = 0; c < nslot; ++c) if (slot_cols[c] == ga.src) w = c;
+                if (w < 0) { if (nslot == 3) { fits = false; break; } slot_cols[nslot] = ga.src; w = nslot++; }
+                ga.slot = w + 1;
+            }
+            const int valw = nslot == 3 ? 4 : nslot;
+            ep_inner.pre[0] = ep_inner.pre[1] = -1;
+            for (int a = 0, n = 0; a < ep_inner.nagg && n < 2; ++a)
+                if (ep_inner.aggs[a].side == 2 && ep_inner.aggs[a].kind != MBC_AGG_COUNT) ep_inner.pre[n++] = a;
+            if (fits) {
+                int flags[2] = {0, 0};                                    // duplicate flag, selected outer rows
+                JCUDA(cudaMemcpyAsync(flags, ep.overflow + 1, 8, cudaMemcpyDeviceToHost, ctx->stream));
+                JCUDA(cudaStreamSynchronize(ctx->stream));
+                if (!flags[0]) {
+                    const bool dense = (uint32_t)flags[1] == g.ngroups;       // unique + as many rows as keys in range
+                    uint32_t *present = nullptr, *slots = nullptr;
+                    JTRY(talloc((void**)&present, ((size_t)g.ngroups + 31) / 32 * 4, true));
+                    if (valw) JTRY(talloc((void**)&slots, (size_t)g.ngroups * valw * 4, false));
+#define MBC_UNIQUE(V)                                                                                                          \
+    join_slot_build_kernel<V><<<grid_o, 256, 0, ctx->stream>>>(ep_inner, present, slots, slot_cols[0], slot_cols[1], slot_cols[2]); \
+    if (dense) join_unique_pass_kernel<V, true><<<grid_i, 256, 0, ctx->stream>>>(ep_inner, present, slots);                      \
+    else join_unique_pass_kernel<V, false><<<grid_i, 256, 0, ctx->stream>>>(ep_inner, present, slots)
+                    if (valw == 0) { MBC_UNIQUE(0); }
+                    else if (valw == 1) { MBC_UNIQUE(1); }
+                    else if (valw == 2) { MBC_UNIQUE(2); }
+                    else { MBC_UNIQUE(4); }
+#undef MBC_UNIQUE
+                    ctx->launches += 2;
+                    unique_fast = true;
+                }
+            }
+        }
+        if (!unique_fast && inner->nrows > 0) {
             join_agg_pass_kernel<2><<<grid_i, 256, 0, ctx->stream>>>(ep_inner);
             ctx->launches++;
         }
@@ -828,7 +1038,7 @@ extern "C" int32_t mbc_bitmap_join(mbc_table* outer, mbc_table* inner, const mbc
             (void)na;
             if (inner->nrows > 0) {
                 for (int a = 0; a < nagg; ++a) {
-                    const bool mine = ja[a].side == 0 || ja[a].side == 2;
+                    const bool mine = ja[a].side == 0 || ja[a].side == 2 || unique_fast;
                     if (!mine) continue;
                     const bool integral = ja[a].kind == MBC_AGG_COUNT || ja[a].type == MBC_ATTR_INTEGER;
                     const bool additive = ja[a].kind == MBC_AGG_COUNT || ja[a].kind == MBC_AGG_SUM;
@@ -849,7 +1059,7 @@ extern "C" int32_t mbc_bitmap_join(mbc_table* outer, mbc_table* inner, const mbc
         // outer pass: outer-side aggregates weighted by n_inner
         bool any_outer_agg = false;
         for (int a = 0; a < nagg; ++a) any_outer_agg |= ja[a].side == 1;
-        if (any_outer_agg && outer->nrows > 0) {
+        if (any_outer_agg && outer->nrows > 0 && !unique_fast) {
             JCUDA(cudaMemsetAsync(ep.partials, 0, (size_t)std::max(nagg, 1) * pgrid * 8, ctx->stream));
             join_agg_pass_kernel<1><<<grid_o, 256, 0, ctx->stream>>>(ep);
             ctx->launches++;

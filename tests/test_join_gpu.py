@@ -71,7 +71,7 @@ def test_golden_bmj_commands(ctx, oracle, minidata, golden):
 
 
 @pytest.mark.parametrize("mode", ["direct", "hash_sparse", "dups"])
-def test_int_equi_join_against_oracle(ctx, oracle, mode):
+def test_int_equi_join_against_oracle(ctx, oracle, mode, monkeypatch):
     """R(key, v) join S(fk, w, x): BASELINE config C4's shape at a size the oracle finishes in seconds."""
     rng = np.random.default_rng(5)
     nR, nS = 20_000, 300_000
@@ -109,8 +109,46 @@ def test_int_equi_join_against_oracle(ctx, oracle, mode):
     exp = oracle.bitmap_join(Rd, Rc, Sd, Sc, jt, proj, aggs=aggs, outer_sel=so.bitmap(), inner_sel=si2.bitmap(), inner_deleted=dele)
     res3 = mbcol.bitmap_join(R, S, jt, proj, ALL, aggs=aggs, outer_sel=so, inner_sel=si2)
     _check_join(oracle, res3, exp, None)
+    # aggregates only under the filters, with the unique-key slot path forced on (it is legal for unique keys only;
+    # duplicates fall back to the general path by themselves) and off
+    for force in ("1", "0"):
+        monkeypatch.setenv("MBC_JOIN_UNIQUE", force)
+        res4 = mbcol.bitmap_join(R, S, jt, proj, N.WANT_AGG, aggs=aggs, outer_sel=so, inner_sel=si2)
+        for a in range(len(aggs)):
+            assert res4.agg(a) == res3.agg(a), (force, a, res4.agg(a), res3.agg(a))
+        res4.close()
+    monkeypatch.delenv("MBC_JOIN_UNIQUE")
     for x in (res, res2, res3, so, si, si2):
         x.close()
+    R.close(); S.close()
+
+
+def test_unique_key_aggregate_path_matches_general(ctx, oracle, monkeypatch):
+    """PK-FK join, aggregates only: the slot path (outer-side values ride next to the key's presence flag) against the
+    general counting path and the oracle, with three distinct outer-side columns (16-byte slots) and with four (falls back)."""
+    rng = np.random.default_rng(9)
+    nR, nS = 50_000, 400_000
+    Rd, Sd = [(1, 4), (1, 4), (2, 4), (1, 4), (1, 4)], [(1, 4), (1, 4)]
+    Rc = [oracle.synth_perm(nR, nR) - 7] + [rng.integers(-500, 500, nR).astype(np.int32), (rng.integers(0, 999, nR) / 8).astype(np.float32),
+                                             rng.integers(0, 9, nR).astype(np.int32), rng.integers(0, 9, nR).astype(np.int32)]
+    Sc = [rng.integers(-20, nR + 20, nS).astype(np.int32), rng.integers(0, 100, nS).astype(np.int32)]
+    R, S = load_table(ctx, Rd, Rc), load_table(ctx, Sd, Sc)
+    jt = [mbcol.Term(N.OP_EQ, ("col", 0), ("icol", 0), 0)]
+    proj = [(1, 1), (1, 2), (1, 3), (1, 4), (2, 1)]
+    for aggs in ([(0, 0), (1, 0), (2, 0), (1, 1), (3, 1), (3, 2), (1, 4)],          # three outer columns + one inner
+                 [(1, 0), (1, 1), (1, 2), (1, 3), (0, 0)]):                         # four outer columns: general path
+        exp = oracle.bitmap_join(Rd, Rc, Sd, Sc, jt, proj, aggs=aggs)
+        monkeypatch.setenv("MBC_JOIN_UNIQUE", "1")
+        fast = mbcol.bitmap_join(R, S, jt, proj, N.WANT_AGG, aggs=aggs)
+        monkeypatch.setenv("MBC_JOIN_UNIQUE", "0")
+        gen = mbcol.bitmap_join(R, S, jt, proj, N.WANT_AGG, aggs=aggs)
+        monkeypatch.delenv("MBC_JOIN_UNIQUE")
+        assert fast.count == gen.count == exp["count"] > 0
+        for a, (ei, ef, ev) in enumerate(exp["aggs"]):
+            assert fast.agg(a)[2] == gen.agg(a)[2] == ev
+            assert fast.agg(a)[0] == gen.agg(a)[0] == ei or abs(fast.agg(a)[1] - ef) <= 1e-9 * abs(ef)
+            assert abs(fast.agg(a)[1] - gen.agg(a)[1]) <= 1e-9 * max(abs(ef), 1.0)
+        fast.close(); gen.close()
     R.close(); S.close()
 
 
