@@ -150,6 +150,16 @@ def run_reference(args, rank: int, world: int):
     }))
 
 
+def measured_traffic(rows_per_gpu):
+    """DRAM bytes per scan (mean of the three selectivities) from the committed ncu --set full capture of this workload
+    (profiles/r1/traffic.json); null for any other table size or when the file is absent."""
+    path = os.path.join(ROOT, "profiles", "r1", "traffic.json")
+    if rows_per_gpu != 100_000_000 or not os.path.exists(path):
+        return None
+    with open(path) as f:
+        return json.load(f)["per_scan_mean"]
+
+
 def workload_config(args, rows_per_gpu):
     return {"workload": "C2: synthetic 4-column table (I1,I2 int in [0,2^20); R real in [0,1000); S char(16)), "
                         "{(I1,<,t1)}^{(R,<,t2)} at 1%/10%/50% selectivity, project [I1,I2,R,S], COUNT/SUM(I2)/SUM(R)/MIN(I1)/MAX(I1)",
@@ -190,20 +200,29 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     kernel_ms = {s: [] for s in SELECTIVITIES}
     counts = {}
 
+    views = {}
+
+    def dev_bytes(ptr, nbytes):
+        """uint8 view of device memory owned by the library.  The pool hands the same buffers back step after step, so
+        the torch view of (pointer, size) is built once."""
+        key = (ptr, nbytes)
+        v = views.get(key)
+        if v is None:
+            v = views[key] = torch.as_tensor(_CudaArray(ptr, nbytes), device=dev)
+        return v
+
     def exchange_step(results):
         """mbcol.sharding over NCCL, once per step: ONE all-gather of every rank's [aggregates..., count] blocks of the
-        three scans (each rank then folds COUNT/SUM/MIN/MAX locally, which is the all-reduce), then the 1% query's
+        three scans (each rank then folds COUNT/SUM/MIN/MAX on the host, which is the all-reduce), then the 1% query's
         positions + projected values are gathered on rank 0 in rank (= position) order with one batch of P2P ops."""
         from mbcol import sharding
-        mine = torch.cat([torch.as_tensor(_CudaArray(r.device_pointers()["aggs"], 9 * 8), device=dev).view(torch.int64) for r in results])
-        blocks = sharding.allgather_blocks(mine).view(world, len(results), 9)      # every rank sees every rank's partials
-        sums = blocks.sum(0)                                    # per scan: COUNT (col 8), SUM(I2) (col 1)
-        folded = (sums, blocks[:, :, 2].view(torch.float64).sum(0), blocks[:, :, 3].amin(0), blocks[:, :, 4].amax(0))
+        mine = torch.cat([dev_bytes(r.device_pointers()["aggs"], 9 * 8) for r in results]).view(torch.int64)
+        blocks = sharding.allgather_blocks(mine).view(world, len(results), 9).cpu().numpy()   # every rank sees every rank's partials
+        folded = (blocks.sum(0), blocks[:, :, 2].copy().view(np.float64).sum(0), blocks[:, :, 3].min(0), blocks[:, :, 4].max(0))
         res = results[0]                                        # the 1% scan
-        cnts = [int(c) for c in blocks[:, 0, 8].cpu()]
+        cnts = [int(c) for c in blocks[:, 0, 8]]
         bufs = [(res.device_pointers()["positions"], 8)] + [res.column_device(i) for i in range(4)]
-        locals_ = [(torch.as_tensor(_CudaArray(ptr, max(res.count, 1) * stride), device=dev)[:res.count * stride], stride)
-                   for ptr, stride in bufs]
+        locals_ = [(dev_bytes(ptr, rows * stride)[:res.count * stride], stride) for ptr, stride in bufs]
         gathered = sharding.gather_rows_multi(locals_, cnts)    # rank 0: the whole table's 1% result, in position order
         return folded, gathered
 
@@ -333,7 +352,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "mbc scan = filter_kernel + tile_offsets_kernel + write_kernel + agg_finish_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "frac_of_nominal_8000": achieved / 8000.0, "peak_source": peak_src,
-                         "traffic": None, "algorithmic_bytes_per_launch": tot_bytes / 3,
+                         "traffic": measured_traffic(rows), "algorithmic_bytes_per_launch": tot_bytes / 3,
                          "per_selectivity": per_sel},
             "cpu_baseline": cpu,
         }
