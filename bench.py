@@ -214,7 +214,8 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     def exchange_step(results):
         """mbcol.sharding over NCCL, once per step: ONE all-gather of every rank's [aggregates..., count] blocks of the
         three scans (each rank then folds COUNT/SUM/MIN/MAX on the host, which is the all-reduce), then the 1% query's
-        positions + projected values are gathered on rank 0 in rank (= position) order with one batch of P2P ops."""
+        positions + projected values are gathered on rank 0 in rank (= position) order through one all-gather of
+        padded blocks (mbcol.sharding.allgather_rows; MBC_BENCH_GATHER=p2p selects the grouped send/recv form)."""
         from mbcol import sharding
         mine = torch.cat([dev_bytes(r.device_pointers()["aggs"], 9 * 8) for r in results]).view(torch.int64)
         blocks = sharding.allgather_blocks(mine).view(world, len(results), 9).cpu().numpy()   # every rank sees every rank's partials
@@ -223,7 +224,10 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         cnts = [int(c) for c in blocks[:, 0, 8]]
         bufs = [(res.device_pointers()["positions"], 8)] + [res.column_device(i) for i in range(4)]
         locals_ = [(dev_bytes(ptr, rows * stride)[:res.count * stride], stride) for ptr, stride in bufs]
-        gathered = sharding.gather_rows_multi(locals_, cnts)    # rank 0: the whole table's 1% result, in position order
+        if os.environ.get("MBC_BENCH_GATHER") == "p2p":
+            gathered = sharding.gather_rows_multi(locals_, cnts)
+        else:                                                   # rank 0: the whole table's 1% result, in position order
+            gathered = sharding.allgather_rows(locals_, cnts)
         return folded, gathered
 
     dbg = {"scan": 0.0, "exchange": 0.0} if os.environ.get("MBC_BENCH_DEBUG") else None

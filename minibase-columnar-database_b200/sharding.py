@@ -83,6 +83,56 @@ def gather_rows_multi(locals_: Sequence[tuple], counts: Sequence[int], dst: int 
     return totals if rank == dst else None
 
 
+def gather_rows_packed(locals_: Sequence[tuple], counts: Sequence[int], dst: int = 0, group=None):
+    """Same result as gather_rows_multi with ONE message per rank: every rank packs its buffers back to back
+    ([buffer 0 rows | buffer 1 rows | ...], one device copy), dst receives world - 1 blocks and splits them back into
+    the per-buffer concatenations in rank order.  With many ranks the fixed cost of a point-to-point operation
+    (not its bytes) is what a result gather pays, so fewer, larger messages win."""
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    widths = [rb for _, rb in locals_]
+    row_total = sum(widths)
+    mine = torch.cat([t for t, _ in locals_]) if len(locals_) > 1 else locals_[0][0]
+    if rank != dst:
+        if counts[rank] > 0:
+            for w in dist.batch_isend_irecv([dist.P2POp(dist.isend, mine, dst, group)]):
+                w.wait()
+        return None
+    blocks = [mine if r == rank else torch.empty(counts[r] * row_total, dtype=torch.uint8, device=mine.device) for r in range(world)]
+    ops = [dist.P2POp(dist.irecv, blocks[r], r, group) for r in range(world) if r != dst and counts[r] > 0]
+    for w in (dist.batch_isend_irecv(ops) if ops else []):
+        w.wait()
+    outs, before = [], 0
+    for rb in widths:
+        outs.append(torch.cat([blocks[r][counts[r] * before:counts[r] * (before + rb)] for r in range(world)]))
+        before += rb
+    return outs
+
+
+def allgather_rows(locals_: Sequence[tuple], counts: Sequence[int], dst: Optional[int] = 0, group=None):
+    """The same concatenations as gather_rows_multi through ONE all-gather: every rank packs its buffers into a block
+    padded to the largest count (buffer j at byte max_count * sum(row_bytes[:j])), the blocks are all-gathered, and dst
+    (every rank when dst is None) cuts the rank-ordered pieces back out.  NCCL's all-gather runs at NVSwitch collective
+    bandwidth, its grouped send/recv at a fraction of it, so on 8 GPUs moving 8x the bytes this way is still ~3x faster
+    than the many-to-one gather (measured, profiles/README.md)."""
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    widths = [rb for _, rb in locals_]
+    maxc = max(max(counts), 1)
+    dev = locals_[0][0].device
+    block = torch.empty(maxc * sum(widths), dtype=torch.uint8, device=dev)
+    before = 0
+    for (t, rb) in locals_:
+        block[maxc * before:maxc * before + counts[rank] * rb].copy_(t)
+        before += rb
+    blocks = allgather_blocks(block, group)                  # [world, maxc * row_total]
+    if dst is not None and rank != dst:
+        return None
+    outs, before = [], 0
+    for rb in widths:
+        outs.append(torch.cat([blocks[r, maxc * before:maxc * before + counts[r] * rb] for r in range(world)]))
+        before += rb
+    return outs
+
+
 def gather_rows(local: torch.Tensor, counts: Sequence[int], row_bytes: int, dst: int = 0, group=None) -> Optional[torch.Tensor]:
     """Single-buffer form of gather_rows_multi."""
     out = gather_rows_multi([(local, row_bytes)], counts, dst, group)

@@ -64,7 +64,7 @@ def main():
             total = sum(cnts)
             bufs = [(res.device_pointers()["positions"], 8)] + [res.column_device(i) for i in range(3)]
             locals_ = [(torch.as_tensor(_CudaArray(p, max(res.count, 1) * s), device=dev)[:res.count * s], s) for p, s in bufs]
-            got = sharding.gather_rows_multi(locals_, cnts)
+            got = sharding.gather_rows_multi(locals_, cnts)      # 100 MB per rank: the grouped send/recv form wins here (profiles/README.md)
             if rank == 0:
                 pos = got[0].view(torch.int64)
                 assert pos.numel() == total and bool((pos[1:] > pos[:-1]).all())      # rank order = position order

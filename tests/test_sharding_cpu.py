@@ -44,9 +44,15 @@ def _worker(rank, world, port, sel, out):
         allpos = sharding.gather_rows(pos, counts, 8)
         s_col = torch.from_numpy(np.ascontiguousarray(cols[3][res["positions"]])).reshape(-1)
         alls = sharding.gather_rows(s_col, counts, 16)
+        packed = sharding.gather_rows_packed([(pos, 8), (s_col, 16)], counts)     # one message per rank: same concatenations
+        dense = sharding.allgather_rows([(pos, 8), (s_col, 16)], counts)         # one all-gather of padded blocks
         if rank == 0:
+            assert torch.equal(packed[0], allpos) and torch.equal(packed[1], alls)
+            assert torch.equal(dense[0], allpos) and torch.equal(dense[1], alls)
             out.put({"folded": folded, "total": total, "positions": allpos.view(torch.int64).numpy().copy(),
                      "S": alls.numpy().reshape(-1, 16).copy()})
+        else:
+            assert packed is None and dense is None
     finally:
         dist.destroy_process_group()
 
