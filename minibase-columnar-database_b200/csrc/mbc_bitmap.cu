@@ -634,8 +634,6 @@ extern "C" int32_t mbc_bitmap_get(mbc_table* t, int32_t col, const void* value, 
     MBC_CUDA(cudaStreamSynchronize(t->ctx->stream));
     memcpy(out_words, tmp.data(), (size_t)std::min<int64_t>(nwords * 8, (int64_t)tmp.size() * 4));
     return MBC_OK;
-    MBC_CUDA(cudaStreamSynchronize(t->ctx->stream));
-    return MBC_OK;
 }
 
 namespace mbc {

@@ -96,8 +96,6 @@ static int32_t plan_staging(mbc_ctx* ctx, ScanParams* p, size_t* smem_bytes, int
         if (t.lhs.kind == 1) t.lhs.staged = stage_of(t.lhs.col);
         if (t.rhs.kind == 1) t.rhs.staged = stage_of(t.rhs.col);
     }
-    for (int c = 0; c < p->nproj; ++c) p->proj[c].staged = -1;
-    for (int a = 0; a < p->nagg; ++a) p->aggs[a].staged = -1;
     // ring depth: as deep as ~100 KB of shared memory allows (two CTAs per SM), at least 2
     p->nstages = p->nstaged == 0 ? 2 : std::max(2, std::min(kMaxStages, (int)(100 * 1024 / (p->nstaged * kStageColBytes))));
     *smem_bytes = (size_t)p->nstages * p->nstaged * kStageColBytes;

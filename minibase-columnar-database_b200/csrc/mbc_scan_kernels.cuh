@@ -61,8 +61,6 @@ struct DevProj {
     void* dst;
     int32_t stride;      // 4, or the device string stride (multiple of 4)
     int32_t col;         // host bookkeeping
-    int32_t staged;      // staged predicate column to read the value from, or -1 (gather from HBM)
-    int32_t pad;
 };
 
 struct DevAgg {
@@ -70,7 +68,7 @@ struct DevAgg {
     int32_t kind;        // MBC_AGG_*
     int32_t type;        // MBC_ATTR_INTEGER / REAL
     int32_t col;         // host bookkeeping
-    int32_t staged;      // staged predicate column, or -1
+    int32_t pad;
 };
 
 constexpr int kMaxStaged = 4;                    // 4-byte predicate columns staged through shared memory
@@ -98,7 +96,6 @@ struct ScanParams {
     const long long* count_in;    // running output offset before this launch (chunked scans append); NULL = 0
     long long* count_out;         // ... and after it (a different slot)
     unsigned int* work_counter;   // group tickets of the write pass (zeroed by tile_offsets_kernel)
-    long long* prof;              // optional phase timers (MBC_SCAN_PROFILE builds)
     unsigned long long* partials; // [nagg][total_tiles]
     DevTerm terms[kMaxTerms];
     DevProj proj[kMaxProj];
