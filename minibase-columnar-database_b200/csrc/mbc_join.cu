@@ -375,13 +375,19 @@ __global__ void __launch_bounds__(256) join_minmax_kernel(const int32_t* key, Jo
 }
 
 __global__ void __launch_bounds__(256) join_outer_count_kernel(const __grid_constant__ EquiParams p) {
+    int selected = 0;
     for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < p.outer.nrows; o += (int64_t)gridDim.x * blockDim.x) {
         if (!side_selected(p.outer, o)) continue;
         long long g = group_of_outer(p.g, o, true);
-        if (g < 0) { *p.overflow = 1; return; }
+        if (g < 0) { *p.overflow = 1; break; }
         if (atomicAdd(p.n_outer + g, 1u) != 0u) p.overflow[1] = 1;
-        atomicAdd(p.overflow + 2, 1);                      // selected outer rows (dense-key test of the unique path)
+        ++selected;
     }
+    // selected outer rows (dense-key test of the unique path): one atomic per warp, not one per row on a single address
+    __syncwarp();
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) selected += __shfl_xor_sync(0xFFFFFFFFu, selected, o);
+    if ((threadIdx.x & 31) == 0 && selected) atomicAdd(p.overflow + 2, selected);
 }
 
 __device__ __forceinline__ void agg_fold(const JoinAgg& a, bool integral, long long& ai, double& af, int64_t row, unsigned long long weight) {
