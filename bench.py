@@ -38,6 +38,7 @@ SELECTIVITIES = (0.01, 0.10, 0.50)
 DESCS = [(1, 4), (1, 4), (2, 4), (0, 16)]                # I1 int, I2 int, R real, S char(16)
 AGGS = [(0, 0), (1, 1), (1, 2), (2, 0), (3, 0)]          # COUNT, SUM(I2), SUM(R), MIN(I1), MAX(I1)
 ROW_BYTES_IN = 28                                        # every referenced column read once
+ROW_BYTES_PRED = 8                                       # the two compared columns (pass 1 reads only these)
 ROW_BYTES_OUT = 36                                       # 8 B position + 28 B projected values
 
 
@@ -200,6 +201,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     terms = {s: c2_terms(mbcol.Term, s) for s in SELECTIVITIES}
     want_dev = N.WANT_POSITIONS | N.WANT_COLUMNS | N.WANT_AGG
     kernel_ms = {s: [] for s in SELECTIVITIES}
+    phase_ms = {s: [] for s in SELECTIVITIES}
     counts = {}
 
     views = {}
@@ -268,6 +270,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             counts[s] = res.count
             if record:
                 kernel_ms[s].append(res.kernel_ms)
+                phase_ms[s].append(res.phase_ms)
         t1 = time.perf_counter()
         if pipelined:
             pending.append((results, scans_done))
@@ -368,6 +371,23 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             tot_bytes += b
             tot_ms += m
         achieved = tot_bytes / (tot_ms * 1e-3) / 1e9
+        # per kernel (CUDA events between the launches of every scan): its own algorithmic bytes over its own time
+        kernels = {}
+        names = ("filter_kernel", "tile_offsets_kernel", "write_kernel", "agg_finish_kernel")
+        for s in SELECTIVITIES:
+            ph = np.asarray(phase_ms[s], dtype=np.float64).mean(0)
+            alg = {"filter_kernel": rows * (ROW_BYTES_PRED + 1 / 8),                       # predicate columns in, bitmap out
+                   "write_kernel": rows * (1 / 8 + s * (ROW_BYTES_IN + ROW_BYTES_OUT))}    # bitmap + survivors' values in, rows out
+            for i, name in enumerate(names):
+                k = kernels.setdefault(name, {"ms_per_step": 0.0, "algorithmic_bytes_per_step": 0.0, "per_selectivity_ms": {}})
+                k["ms_per_step"] += float(ph[i])
+                k["per_selectivity_ms"][str(s)] = float(ph[i])
+                k["algorithmic_bytes_per_step"] += alg.get(name, 0.0)
+        for name, k in kernels.items():
+            k["achieved_gbs"] = k["algorithmic_bytes_per_step"] / (k["ms_per_step"] * 1e-3) / 1e9 if k["ms_per_step"] > 0 else None
+            k["frac"] = k["achieved_gbs"] / peak if k["achieved_gbs"] else None
+            k["share_of_step"] = k["ms_per_step"] / tot_ms
+        dominant = max(kernels, key=lambda n: kernels[n]["ms_per_step"])
         cpu = None
         if not args.no_cpu_baseline:
             from oracle import oracle as orc
@@ -390,7 +410,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             "roofline": {"bound": "hbm", "kernel": "mbc scan = filter_kernel + tile_offsets_kernel + write_kernel + agg_finish_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "frac_of_nominal_8000": achieved / 8000.0, "peak_source": peak_src,
                          "traffic": measured_traffic(rows), "algorithmic_bytes_per_launch": tot_bytes / 3,
-                         "per_selectivity": per_sel},
+                         "per_selectivity": per_sel, "dominant_kernel": dominant, "kernels": kernels},
             "cpu_baseline": cpu,
         }
         print(json.dumps(out))

@@ -225,6 +225,9 @@ int32_t mbc_bitmap_join(mbc_table* outer, mbc_table* inner,
 int64_t        mbc_result_count(const mbc_result* r);
 /* Device time of the kernels that produced this result (CUDA events around them), ms; < 0 if unknown. */
 float          mbc_result_kernel_ms(const mbc_result* r);
+/* The same per kernel for a scan over a resident table: ms4 = {pass 1 (filter_kernel / select_bitmap_kernel),
+ * tile_offsets_kernel, write_kernel, agg_finish_kernel}; -1 where unknown. */
+int32_t        mbc_result_phase_ms(const mbc_result* r, float* ms4);
 /* ascending positions, int64 (host; needs MBC_WANT_POSITIONS|MBC_WANT_HOST). For joins:
  * outer positions; mbc_result_positions2 gives the matching inner positions. */
 const int64_t* mbc_result_positions(const mbc_result* r);

@@ -93,6 +93,7 @@ _SIGNATURES = {
                                     C.c_int32, C.c_uint32, C.POINTER(mbc_aggspec), C.c_int32, C.POINTER(_VP)]),
     "mbc_result_count": (C.c_int64, [_VP]),
     "mbc_result_kernel_ms": (C.c_float, [_VP]),
+    "mbc_result_phase_ms": (C.c_int32, [_VP, C.POINTER(C.c_float)]),
     "mbc_result_positions": (_VP, [_VP]),
     "mbc_result_positions2": (_VP, [_VP]),
     "mbc_result_column": (_VP, [_VP, C.c_int32, C.POINTER(C.c_int32)]),

@@ -97,6 +97,13 @@ void event_put(mbc_ctx* ctx, cudaEvent_t e) {
     else ctx->event_free.push_back(e);
 }
 
+void result_phase_times(mbc_result* r) {
+    if (!r->ev_t0 || !r->ev_t1 || !r->ev_mid[0] || !r->ev_mid[1] || !r->ev_mid[2]) return;
+    cudaEvent_t e[5] = {r->ev_t0, r->ev_mid[0], r->ev_mid[1], r->ev_mid[2], r->ev_t1};
+    for (int i = 0; i < 4; ++i)
+        if (cudaEventElapsedTime(&r->phase_ms[i], e[i], e[i + 1]) != cudaSuccess) r->phase_ms[i] = -1.f;
+}
+
 int32_t result_finalize(mbc_result* r) {
     if (!r->ev_ready) return MBC_OK;
     mbc_ctx* ctx = r->ctx;
@@ -121,6 +128,7 @@ int32_t result_finalize(mbc_result* r) {
         if (!g.valid) { g.i = 0; g.f = 0.0; }
     }
     if (r->ev_t0 && r->ev_t1 && cudaEventElapsedTime(&r->kernel_ms, r->ev_t0, r->ev_t1) != cudaSuccess) r->kernel_ms = -1.f;
+    result_phase_times(r);
     return MBC_OK;
 }
 
@@ -361,6 +369,13 @@ int64_t mbc_result_count(const mbc_result* r) {
     return r->count;
 }
 
+int32_t mbc_result_phase_ms(const mbc_result* r, float* ms4) {
+    if (!r || !ms4) MBC_FAIL(MBC_ERR_ARG, "mbc_result_phase_ms: bad argument");
+    MBC_TRY(result_finalize(const_cast<mbc_result*>(r)));
+    for (int i = 0; i < 4; ++i) ms4[i] = r->phase_ms[i];
+    return MBC_OK;
+}
+
 float mbc_result_kernel_ms(const mbc_result* r) {
     if (!r) return -1.f;
     if (result_finalize(const_cast<mbc_result*>(r)) != MBC_OK) return -1.f;
@@ -421,6 +436,7 @@ void mbc_result_free(mbc_result* r) {
     result_finalize(r);                            // the pinned count/aggregate block must have landed before it is recycled
     event_put(ctx, r->ev_t0);
     event_put(ctx, r->ev_t1);
+    for (auto& e : r->ev_mid) event_put(ctx, e);
     dev_free(ctx, r->d_pos);
     dev_free(ctx, r->d_pos2);
     for (auto& c : r->cols) dev_free(ctx, c.d);

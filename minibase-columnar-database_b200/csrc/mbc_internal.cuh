@@ -154,6 +154,8 @@ struct mbc_result {
     // then run without host gaps between them.
     cudaEvent_t ev_ready = nullptr;        // non-null while count/aggs are still in flight
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;   // device time of this result's kernels
+    cudaEvent_t ev_mid[3] = {nullptr, nullptr, nullptr};   // resident scans: after pass 1, after the offsets, after the write pass
+    float phase_ms[4] = {-1.f, -1.f, -1.f, -1.f};          // pass 1, tile offsets, write pass, aggregate finish
     unsigned long long* h_small = nullptr; // pinned: nagg raw values + count
     float kernel_ms = -1.f;
 };
@@ -169,6 +171,7 @@ int32_t ensure_workspace(mbc_ctx* ctx, size_t bytes);
 void    begin_timing(mbc_ctx* ctx);
 void    end_timing(mbc_ctx* ctx);
 void    split_timing(mbc_ctx* ctx);
+void    result_phase_times(mbc_result* r);  // fills phase_ms from the events of a completed resident scan
 int32_t result_finalize(mbc_result* r);   // wait for a deferred result's count/aggregates (no-op when final)
 cudaEvent_t event_get(mbc_ctx* ctx);
 void    event_put(mbc_ctx* ctx, cudaEvent_t e);        // close a timed segment (sync), keep its time, the next begin_timing adds to it

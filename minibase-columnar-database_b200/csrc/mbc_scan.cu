@@ -355,10 +355,12 @@ static int32_t launch_job(ScanJob* job, int tile_base, bool first) {
     } else {
         filter_kernel<<<job->grid_per_tiles(p.ntiles), kScanThreads, job->smem_bytes, ctx->stream>>>(p);
     }
+    if (job->r->ev_mid[0]) cudaEventRecord(job->r->ev_mid[0], ctx->stream);
     tile_offsets_kernel<<<(p.ntiles + kOffsetsPerBlock - 1) / kOffsetsPerBlock, 1024, 0, ctx->stream>>>(p.tile_counts, p.ntiles, p.tile_out,
                                                                                                       p.count_in, p.count_out, p.work_counter);
     job->launches++;
     ctx->launches += 2;
+    if (job->r->ev_mid[1]) cudaEventRecord(job->r->ev_mid[1], ctx->stream);
     if (p.out_pos || p.nproj > 0 || p.nagg > 0) {
         const char* pt = getenv("MBC_WRITE_PERSISTENT_TILES");          // tests force either form
         const int persistent_min_tiles = pt ? atoi(pt) : 49152;
@@ -373,6 +375,7 @@ static int32_t launch_job(ScanJob* job, int tile_base, bool first) {
         }
         ctx->launches++;
     }
+    if (job->r->ev_mid[2]) cudaEventRecord(job->r->ev_mid[2], ctx->stream);
     MBC_CUDA(cudaGetLastError());
     return MBC_OK;
 }
@@ -416,6 +419,7 @@ static int32_t finish_job_device(ScanJob* job, int64_t tiles_done, bool deferred
     r->count = (int64_t)host_small[kMaxAgg];
     decode_aggs(r, p.aggs, p.nagg, host_small);
     if (r->ev_t0 && r->ev_t1 && cudaEventElapsedTime(&r->kernel_ms, r->ev_t0, r->ev_t1) != cudaSuccess) r->kernel_ms = -1.f;
+    result_phase_times(r);
     return MBC_OK;
 }
 
@@ -451,6 +455,7 @@ int32_t run_scan(const ScanRequest& rq, mbc_result** out) {
         begin_timing(ctx);
         job.r->ev_t0 = event_get(ctx);
         job.r->ev_t1 = event_get(ctx);
+        for (auto& e : job.r->ev_mid) e = event_get(ctx);      // per-kernel times of a resident scan (mbc_result_phase_ms)
         if (job.r->ev_t0) cudaEventRecord(job.r->ev_t0, ctx->stream);
         s = launch_job(&job, 0, true);
     }

@@ -296,6 +296,13 @@ class Result:
         """Device time of this result's kernels (waits for a deferred result)."""
         return float(N.lib().mbc_result_kernel_ms(self._h))
 
+    @property
+    def phase_ms(self) -> tuple:
+        """(pass 1, tile offsets, write pass, aggregate finish) device times of a resident scan, ms."""
+        ms = (C.c_float * 4)()
+        N.check(N.lib().mbc_result_phase_ms(self._h, ms))
+        return tuple(float(x) for x in ms)
+
     def positions(self) -> np.ndarray:
         return _np_from_ptr(N.lib().mbc_result_positions(self._h), self.count * 8, np.int64)
 
