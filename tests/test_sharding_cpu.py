@@ -93,3 +93,45 @@ def test_shard_ranges_cover_the_table():
             assert r[0][0] == 0 and r[-1][1] == total
             assert all(a[1] == b[0] for a, b in zip(r, r[1:]))
             assert all(lo % sharding.TILE == 0 or lo == total for lo, _ in r)
+
+
+def _gather_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from mbcol import sharding
+        counts = [5, 0, 3][:world]                                  # rank 1 found nothing
+        n = counts[rank]
+        a = (torch.arange(n * 8, dtype=torch.int64) + 1000 * rank).to(torch.uint8)          # 8-byte rows
+        b = (torch.arange(n * 20, dtype=torch.int64) * 3 + rank).to(torch.uint8)            # 20-byte rows
+        forms = {"multi": sharding.gather_rows_multi([(a, 8), (b, 20)], counts),
+                 "packed": sharding.gather_rows_packed([(a, 8), (b, 20)], counts),
+                 "allgather": sharding.allgather_rows([(a, 8), (b, 20)], counts),
+                 "everyone": sharding.allgather_rows([(a, 8), (b, 20)], counts, dst=None)}
+        assert forms["everyone"] is not None and forms["everyone"][0].numel() == sum(counts) * 8
+        if rank == 0:
+            out.put({k: [t.numpy().copy() for t in v] for k, v in forms.items()})
+        else:
+            assert forms["multi"] is None and forms["packed"] is None and forms["allgather"] is None
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gather_forms_agree_with_an_empty_rank():
+    world = 3
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    procs = [ctx.Process(target=_gather_worker, args=(r, world, 29650, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = out.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    counts = [5, 0, 3]
+    exp_a = np.concatenate([((np.arange(c * 8) + 1000 * r) % 256).astype(np.uint8) for r, c in enumerate(counts)])
+    exp_b = np.concatenate([((np.arange(c * 20) * 3 + r) % 256).astype(np.uint8) for r, c in enumerate(counts)])
+    for form, (a, b) in got.items():
+        np.testing.assert_array_equal(a, exp_a, err_msg=form)
+        np.testing.assert_array_equal(b, exp_b, err_msg=form)
