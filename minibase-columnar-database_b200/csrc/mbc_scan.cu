@@ -97,7 +97,7 @@ static int32_t plan_staging(mbc_ctx* ctx, ScanParams* p, size_t* smem_bytes, int
         if (t.rhs.kind == 1) t.rhs.staged = stage_of(t.rhs.col);
     }
     // ring depth: as deep as ~100 KB of shared memory allows (two CTAs per SM), at least 2
-    p->nstages = p->nstaged == 0 ? 2 : std::max(2, std::min(kMaxStages, (int)(100 * 1024 / (p->nstaged * kStageColBytes))));
+    p->nstages = p->nstaged == 0 ? 2 : std::max(2, std::min(kMaxStages, (int)(200 * 1024 / MBC_FILTER_CTAS / (p->nstaged * kStageColBytes))));
     *smem_bytes = (size_t)p->nstages * p->nstaged * kStageColBytes;
     static bool configured = false;
     if (!configured) {

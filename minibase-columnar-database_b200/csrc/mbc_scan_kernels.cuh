@@ -356,7 +356,10 @@ __device__ __forceinline__ unsigned long long agg_merge(const DevAgg& g, unsigne
 }
 
 // ---- pass 1: CNF -> selection bitmap + tile counts ------------------------------------------------------
-__global__ void __launch_bounds__(kScanThreads, 2) filter_kernel(const __grid_constant__ ScanParams p) {
+#ifndef MBC_FILTER_CTAS
+#define MBC_FILTER_CTAS 2
+#endif
+__global__ void __launch_bounds__(kScanThreads, MBC_FILTER_CTAS) filter_kernel(const __grid_constant__ ScanParams p) {
     extern __shared__ __align__(128) uint8_t stage_mem[];          // [nstages][nstaged][kTileRows] uint32
     __shared__ __align__(8) uint64_t s_full[kMaxStages];
     __shared__ uint32_t s_wcnt[2][kWarpsPerCta];                   // by tile parity: see the note at the end of the loop

@@ -10,7 +10,7 @@ from .columnar import Columnarfile
 from .engine import Term, bitmap_join
 from .global_ import AttrOperator, AttrType, IndexType, SystemDefs
 from .index import ColumnarIndexScan
-from .iterator import ColumnarFileScan, CondExpr, FldSpec, RelSpec
+from .iterator import ColumnarColumnScan, ColumnarFileScan, CondExpr, FldSpec, RelSpec
 
 
 def _emit(lines: list, text: str, echo: bool) -> None:
@@ -115,7 +115,14 @@ class Query:
                 raise Exception("Bitmap index does not exist on column " + parts[0])
             it = ColumnarIndexScan(cf, fnums, itypes, inames, cf.getAttributeTypes(), cf.getStringSizes(), cf.getFieldCount(),
                                    len(cols), cols, proj, exprs, False)
-        else:                                                     # executeFileScan (:121-155); COLUMNSCAN gives the same rows
+        elif access.upper() == "COLUMNSCAN":                      # Query.executeColumnScan (:157-196)
+            import copy
+            colscan = copy.deepcopy(exprs)                        # buildQueryCondExprColscan: the column is field 1 of the
+            for e in colscan:                                     # one-column predicate tuple
+                if e is not None and e.type1.attrType == AttrType.attrSymbol:
+                    e.operand1.symbol = FldSpec(RelSpec(RelSpec.outer), 1)
+            it = ColumnarColumnScan(cf, cf.colNameToIndex(parts[0].strip()), len(cols), cols, proj, colscan)
+        else:                                                     # executeFileScan (:121-155)
             it = ColumnarFileScan(cfname, cf.getAttributeTypes(), cf.getStringSizes(), cf.getFieldCount(), len(cols), proj, exprs)
         while True:
             t = it.get_next()

@@ -160,9 +160,11 @@ class Iterator:
 class _ResultCursor:
     """Slices an engine Result into reference Tuples, reusing ONE Jtuple like the Java iterators do."""
 
-    def __init__(self, result, out_types: Sequence[AttrType], jtuple: Tuple):
+    def __init__(self, result, out_types: Sequence[AttrType], jtuple: Tuple, whole_fields: bool = False, str_sizes=()):
         self.result = result
         self.jtuple = jtuple
+        self.whole_fields = whole_fields        # Tuple.setFld of the stored record: the whole slot is rewritten
+        self.str_sizes = list(str_sizes)        # declared width of every output field (0 for numbers)
         self.types = [t.attrType for t in out_types]
         self.positions = result.positions()
         self.cols = [result.column(i) for i in range(len(self.types))]
@@ -173,6 +175,17 @@ class _ResultCursor:
             return None
         k = self.i
         self.i += 1
+        if self.whole_fields:
+            import struct
+            for f, t in enumerate(self.types):                 # Jtuple.setFld(j, record bytes) (ColumnarColumnScan.java:167)
+                if t == AttrType.attrInteger:
+                    self.jtuple.setFld(f + 1, struct.pack(">i", int(self.cols[f][k])))
+                elif t == AttrType.attrReal:
+                    self.jtuple.setFld(f + 1, struct.pack(">f", float(self.cols[f][k])))
+                else:
+                    b = bytes(self.cols[f][k]).rstrip(b"\0")
+                    self.jtuple.setFld(f + 1, struct.pack(">H", len(b)) + b.ljust(self.str_sizes[f], b"\0"))
+            return self.jtuple
         for f, t in enumerate(self.types):                     # Projection.Project (:103-144)
             if t == AttrType.attrInteger:
                 self.jtuple.setIntFld(f + 1, int(self.cols[f][k]))
@@ -274,3 +287,104 @@ class ColumnarFileScan(Iterator):
             out.append((i if integral else f, v))
         res.close()
         return out
+
+
+class _ColumnsScan(Iterator):
+    """Shared body of ColumnarColumnScan / ColumnarColumnsScan: the predicate is evaluated over a
+    tuple of the scanned columns only (CondExpr field k = the k-th scanned column), the output fields are fetched by
+    position from the columns `out_indexes`; deleted rows are skipped (columnar/ColumnScan.java getNext).  Same GPU
+    scan as ColumnarFileScan: the filter pass reads only the compared columns, the write pass gathers the rest."""
+
+    def __init__(self, columnarfile, colNos: Sequence[int], rest: tuple, usage: str):
+        super().__init__()
+        if len(rest) == 4:
+            n_out_flds, out_indexes, proj_list, outFilter = rest
+            self.deleteQuery = False
+        elif len(rest) == 1:                                    # "Only use for delete query": positions only
+            (outFilter,) = rest
+            n_out_flds, out_indexes, proj_list = 0, [], []
+            self.deleteQuery = True
+        else:
+            raise TypeError(usage)
+        self.f = columnarfile
+        self.colNos = [int(c) for c in colNos]
+        self._in1 = columnarfile.getAttributeTypes()
+        self.in1_len = columnarfile.getFieldCount()
+        self.s_sizes = columnarfile.getStringSizes()
+        if any(c < 0 or c >= self.in1_len for c in self.colNos):
+            raise FileScanException(None, "openTupleScan() failed")
+        self.OutputFilter = outFilter
+        self.perm_mat = list(proj_list)
+        self.nOutFlds = n_out_flds
+        self.outIndexes = [int(i) for i in out_indexes]
+        self.Jtuple = Tuple()
+        self._out_types: list = [None] * n_out_flds
+        if not self.deleteQuery:
+            setup_op_tuple(self.Jtuple, self._out_types, self._in1, self.in1_len, self.s_sizes, self.perm_mat, n_out_flds)
+        self.destType = [self._in1[c] for c in self.colNos]     # the predicate tuple's field types
+        self._cursor: Optional[_ResultCursor] = None
+        self._result = None
+
+    def show(self):
+        return self.perm_mat
+
+    def _open(self) -> _ResultCursor:
+        if self._cursor is None:
+            terms = []
+            for t in flatten_condexpr(self.OutputFilter):       # field k of the predicate tuple -> table column colNos[k]
+                ops = []
+                for kind, val in (t.lhs, t.rhs):
+                    if kind == "col":
+                        if not 0 <= val < len(self.colNos):
+                            raise PredEvalException(None, "FieldNumberOutOfBoundException is caught by PredEval.java")
+                        val = self.colNos[val]
+                    ops.append((kind, val))
+                terms.append(Term(t.op, ops[0], ops[1], t.conj))
+            try:
+                self._result = self.f.table.scan(terms, proj=self.outIndexes, want=N.WANT_POSITIONS | N.WANT_COLUMNS | N.WANT_HOST)
+            except N.MbcError as e:
+                raise PredEvalException(e, "TupleUtilsException is caught by PredEval.java")
+            sizes = self.f.getAttrSizes()
+            self._cursor = _ResultCursor(self._result, self._out_types, self.Jtuple, whole_fields=True,
+                                         str_sizes=[sizes[i] if self._in1[i].attrType == AttrType.attrString else 0 for i in self.outIndexes])
+        return self._cursor
+
+    def get_next(self) -> Optional[Tuple]:
+        return self._open().next_tuple()
+
+    def get_next_tid(self) -> Optional[TID]:
+        """The position of the next qualifying row.  (The Java looks the last scanned column's RID up in the FIRST
+        column's heap file, ColumnarColumnsScan.java:219 vs :191 -- wrong when the two columns' records differ in size;
+        the position returned here is the right one.)"""
+        pos = self._open().next_position()
+        return None if pos is None else TID(self.in1_len, pos)
+
+    def close(self) -> None:
+        if not self.closeFlag:
+            if self._result is not None:
+                self._result.close()
+            self._cursor = self._result = None
+            self.closeFlag = True
+
+
+class ColumnarColumnScan(_ColumnsScan):
+    """iterator/ColumnarColumnScan.java:39-88,151-196.
+
+    ColumnarColumnScan(columnarfile, colNo, n_out_flds, out_indexes, proj_list, outFilter)
+    ColumnarColumnScan(columnarfile, colNo, outFilter)                  (delete query: get_next_tid only)"""
+
+    def __init__(self, columnarfile, colNo: int, *rest):
+        super().__init__(columnarfile, [colNo], rest,
+                         "ColumnarColumnScan(columnarfile, colNo, [n_out_flds, out_indexes, proj_list,] outFilter)")
+        self.colNo = int(colNo)
+
+
+class ColumnarColumnsScan(_ColumnsScan):
+    """iterator/ColumnarColumnsScan.java:39-101,176-224.
+
+    ColumnarColumnsScan(columnarfile, colNos, n_out_flds, out_indexes, proj_list, outFilter)
+    ColumnarColumnsScan(columnarfile, colNos, outFilter)                (delete query: get_next_tid only)"""
+
+    def __init__(self, columnarfile, colNos: Sequence[int], *rest):
+        super().__init__(columnarfile, colNos, rest,
+                         "ColumnarColumnsScan(columnarfile, colNos, [n_out_flds, out_indexes, proj_list,] outFilter)")

@@ -13,7 +13,7 @@ from mbcol.columnar import Columnarfile
 from mbcol.global_ import AttrOperator, AttrType, IndexType, IntegerValue, StringValue, SystemDefs, TID
 from mbcol.index import ColumnarIndexScan, ColumnIndexScan
 from mbcol.input import BitMapQuery, Index, MultiIndexQuery, Query, build_cnf_condexpr
-from mbcol.iterator import ColumnarFileScan, CondExpr, FldSpec, RelSpec
+from mbcol.iterator import ColumnarColumnScan, ColumnarColumnsScan, ColumnarFileScan, CondExpr, FldSpec, RelSpec
 
 pytestmark = pytest.mark.gpu
 
@@ -129,6 +129,70 @@ def test_columnarfilescan_iterator_contract(db, oracle, minidata):
     assert sum(1 for _ in iter(fs2.get_next_tid, None)) == 500
     assert fs2.aggregate([(0, 0), (1, 2), (2, 3), (3, 3)]) == [(500, True), (int(cols[2].sum()), True), (int(cols[3].min()), True), (int(cols[3].max()), True)]
     fs2.close()
+
+
+def _cond(op, fld, lit):
+    e = CondExpr()
+    e.op = AttrOperator(op)
+    e.type1 = AttrType(AttrType.attrSymbol)
+    e.operand1.symbol = FldSpec(RelSpec(RelSpec.outer), fld)
+    if isinstance(lit, str):
+        e.type2, e.operand2.string = AttrType(AttrType.attrString), lit
+    else:
+        e.type2, e.operand2.integer = AttrType(AttrType.attrInteger), lit
+    return e
+
+
+def test_columnar_column_scans(db, oracle, minidata):
+    """iterator.ColumnarColumnScan / ColumnarColumnsScan.  The CondExpr addresses the fields of the
+    tuple of SCANNED columns (field k = colNos[k-1]), the output fields are fetched by position from out_indexes, the
+    reused Jtuple is rewritten whole (Tuple.setFld of the stored record: clean padding, unlike ColumnarFileScan), deleted
+    rows are skipped, and `query ... COLUMNSCAN` prints what FILESCAN prints."""
+    names, descs, cols = minidata
+    cf = Columnarfile("cf")
+    # one scanned column: C >= 5 (field 1 of the predicate tuple), output [D, A]
+    proj = [FldSpec(RelSpec(RelSpec.outer), 4), FldSpec(RelSpec(RelSpec.outer), 1)]
+    cs = ColumnarColumnScan(cf, 2, 2, [3, 0], proj, [_cond(AttrOperator.aopGE, 1, 5), None])
+    exp = oracle.scan(descs, cols, [oracle.Term(oracle.OP_GE, ("col", 2), ("int", 5), 0)], proj=[3, 0])
+    got = []
+    while (t := cs.get_next()) is not None:
+        assert t is cs.Jtuple
+        got.append(t.getTupleByteArray())
+    assert len(got) == exp["count"] > 0 and got == [bytes(x) for x in exp["tuples"]]       # clean Tuple bytes
+    cs.close(); cs.close()
+    # two scanned columns [A, D]: (A <= "Delaware" OR D = 3) AND A != "Alabama"; fields 1 and 2 of the predicate tuple
+    e1 = _cond(AttrOperator.aopLE, 1, "Delaware")
+    e1.next = _cond(AttrOperator.aopEQ, 2, 3)
+    e2 = _cond(AttrOperator.aopNE, 1, "Alabama")
+    proj = [FldSpec(RelSpec(RelSpec.outer), i) for i in (2, 3, 1)]
+    ms = ColumnarColumnsScan(cf, [0, 3], 3, [1, 2, 0], proj, [e1, e2, None])
+    terms = [oracle.Term(oracle.OP_LE, ("col", 0), ("str", "Delaware"), 0), oracle.Term(oracle.OP_EQ, ("col", 3), ("int", 3), 0),
+             oracle.Term(oracle.OP_NE, ("col", 0), ("str", "Alabama"), 1)]
+    exp = oracle.scan(descs, cols, terms, proj=[1, 2, 0])
+    got = [t.getTupleByteArray() for t in iter(ms.get_next, None)]
+    assert 0 < exp["count"] < 500 and got == [bytes(x) for x in exp["tuples"]]
+    ms.close()
+    # delete-query constructors: positions only; a field number beyond the scanned columns is an error
+    dq = ColumnarColumnsScan(cf, [0, 3], [e1, e2, None])
+    assert [tid.position for tid in iter(dq.get_next_tid, None)] == exp["positions"].tolist()
+    dq.close()
+    dq1 = ColumnarColumnScan(cf, 3, [_cond(AttrOperator.aopEQ, 1, 3), None])
+    assert [tid.position for tid in iter(dq1.get_next_tid, None)] == np.flatnonzero(cols[3] == 3).tolist()
+    dq1.close()
+    with pytest.raises(Exception):
+        ColumnarColumnScan(cf, 3, [_cond(AttrOperator.aopEQ, 2, 3), None]).get_next_tid()
+    # deleted rows are skipped (ColumnScan.getNext), on the table with deleted positions {0, 5, 77, 12345, n-1}
+    sd, sc, n = db["syn"]
+    syn = Columnarfile("syn")
+    ss = ColumnarColumnScan(syn, 0, [_cond(AttrOperator.aopGE, 1, 0), None])
+    seen = [tid.position for tid in iter(ss.get_next_tid, None)]
+    assert len(seen) == n - 5 and seen[:3] == [1, 2, 3] and 12345 not in seen
+    ss.close()
+    # the driver: COLUMNSCAN prints the same lines as FILESCAN
+    for cons in ("{C,>=,6}", "{A,<,Delaware}", "{D,!=,3}"):
+        a = Query().execute(["db", "cf", "[B,D,A]", cons, "100", "COLUMNSCAN"], echo=False)
+        b = Query().execute(["db", "cf", "[B,D,A]", cons, "100", "FILESCAN"], echo=False)
+        assert a == b and len(a) > 3
 
 
 def test_index_and_bitmap_accessors(db, oracle, minidata, golden):
