@@ -225,3 +225,73 @@ class BitMapQuery:
     def _constraint_bitset(cf: Columnarfile, cnf: str) -> ColumnarIndexScan:
         exprs, itypes, fnums, inames = build_cnf_condexpr(cnf, cf)
         return ColumnarIndexScan(cf, fnums, itypes, inames, cf.getAttributeTypes(), cf.getStringSizes(), cf.getFieldCount(), exprs)
+
+
+class NljQuery:
+    """input/NljQuery.java:33-330: `nlj DB OUTER INNER OUTERCONST INNERCONST JOINCONST OUTERACCESS INNERACCESS [targets]
+    NUMBUF MEM`.  The reference runs a block nested-loop join over two column scans
+    (iterator/ColumnarNestedLoopJoins.java:157-207); here both side constraints are GPU filter scans that leave
+    selection bitmaps and the join is the same K6 as `bmj` (equi path or tiled theta kernel).  Same pair SET as the
+    reference; the pairs come out outer-ascending x inner-ascending, the Java's block order depends on MEM."""
+
+    def execute(self, args: Sequence[str], echo: bool = True) -> list[str]:
+        if len(args) < 11:
+            raise Exception("Invalid number of attributes.")
+        outer_name, inner_name, ocnf, icnf, jcnf, oacc, iacc, targets = args[1:9]
+        for acc in (oacc, iacc):
+            if acc.upper() not in ("FILESCAN", "COLUMNSCAN", "BTREE", "BITMAP"):
+                raise Exception("access type invalid.")
+            if acc.upper() == "BTREE":
+                raise Exception("BTREE access stays in Java (out of scope for the GPU path)")
+        if not (targets.startswith("[") and targets.endswith("]")):
+            raise Exception("[TARGETCOLUMNNAMES] format invalid.")
+        outer, inner = Columnarfile(outer_name), Columnarfile(inner_name)
+        osel = self._constraint(outer, ocnf, oacc)
+        isel = self._constraint(inner, icnf, iacc)
+        names = [t.strip() for t in targets[1:-1].split(",")]
+        proj, out_types = [], []
+        for n in names:
+            rel, col = n.split(".")
+            cf, side = (outer, N.OPERAND_OUTER) if rel == outer_name else (inner, N.OPERAND_INNER)
+            proj.append((side, cf.colNameToIndex(col)))
+            out_types.append(cf.getAttributeTypes()[proj[-1][1]].attrType)
+        join_terms = []
+        for ci, conj in enumerate(jcnf.split("^")):
+            if not (conj.startswith("{") and conj.endswith("}")):
+                raise Exception("Invalid query format")
+            for dis in conj[1:-1].split("|"):
+                parts = [p.strip() for p in dis[1:-1].strip().split(",")]
+                if len(parts) != 3:
+                    raise Exception("Invalid VALUECONSTRAINT elements")
+                oc, ic = outer.colNameToIndex(parts[0]), inner.colNameToIndex(parts[2])
+                if outer.getAttributeTypes()[oc].attrType != inner.getAttributeTypes()[ic].attrType:
+                    raise Exception("Invalid JOIN COLUMN ATTR TYPE NOT MATCH.")
+                join_terms.append(Term(AttrOperator.findOperator(parts[1]).attrOperator, ("col", oc), ("icol", ic), ci))
+        res = bitmap_join(outer.table, inner.table, join_terms, proj,
+                          N.WANT_POSITIONS | N.WANT_COLUMNS | N.WANT_TUPLES | N.WANT_AGG | N.WANT_HOST, aggs=[(N.AGG_COUNT, 0)],
+                          outer_sel=osel, inner_sel=isel)
+        lines: list[str] = []
+        _emit(lines, ", ".join(names), echo)
+        from .heap import Tuple
+        for raw in res.tuples():
+            t = Tuple(bytes(raw))
+            t._adopt_header()
+            _emit(lines, _fmt(t, out_types), echo)
+        count = res.count
+        res.close(); osel.close(); isel.close()
+        _footer(lines, count, echo)
+        self.resultCount = count
+        return lines
+
+    @staticmethod
+    def _constraint(cf: Columnarfile, cnf: str, access: str):
+        """The side's qualifying rows as a selection bitmap: a filter scan (FILESCAN / COLUMNSCAN) or the bitmap
+        indexes (BITMAP)."""
+        exprs, itypes, fnums, inames = build_cnf_condexpr(cnf, cf)
+        if access.upper() == "BITMAP":
+            scan = ColumnarIndexScan(cf, fnums, itypes, inames, cf.getAttributeTypes(), cf.getStringSizes(), cf.getFieldCount(), exprs)
+            scan.getOutputPositions()
+            res, scan._result = scan._result, None                 # the selection outlives the scan object
+            return res
+        from .iterator import flatten_condexpr
+        return cf.table.scan(flatten_condexpr(exprs), want=N.WANT_BITMAP)

@@ -12,7 +12,7 @@ from mbcol import _native as N
 from mbcol.columnar import Columnarfile
 from mbcol.global_ import AttrOperator, AttrType, IndexType, IntegerValue, StringValue, SystemDefs, TID
 from mbcol.index import ColumnarIndexScan, ColumnIndexScan
-from mbcol.input import BitMapQuery, Index, MultiIndexQuery, Query, build_cnf_condexpr
+from mbcol.input import BitMapQuery, Index, MultiIndexQuery, NljQuery, Query, build_cnf_condexpr
 from mbcol.iterator import ColumnarColumnScan, ColumnarColumnsScan, ColumnarFileScan, CondExpr, FldSpec, RelSpec
 
 pytestmark = pytest.mark.gpu
@@ -242,6 +242,29 @@ def test_bmj_golden(db, golden):
         assert lines[1] == "{" + ", ".join(map(str, e["outer_bitset"])) + "}"
         assert lines[3] == "{" + ", ".join(map(str, e["inner_bitset"])) + "}"
         assert lines[4] == e["header"] and lines[5:5 + e["count"]] == e["rows"], e["cmd"]
+        n += 1
+    assert n >= 8
+
+
+def test_nlj_golden(db, golden):
+    """G5, G8 through NljQuery.execute: every `nlj` command of the transcript on cf/cf1/cf2, any
+    access path the GPU side serves (FILESCAN / COLUMNSCAN / BITMAP).  Count, header and the row MULTISET must match
+    what the Java printed (its block nested loop emits the pairs in another order)."""
+    import hashlib
+    seen, n = set(), 0
+    for e in golden:
+        if e["kind"] != "nlj" or e.get("failed") or e["cmd"] in seen or "ff1." in e["cmd"] or "BTREE" in e["cmd"]:
+            continue
+        seen.add(e["cmd"])
+        q = NljQuery()
+        lines = q.execute(e["cmd"].split()[1:], echo=False)
+        assert q.resultCount == e["count"], e["cmd"]
+        assert lines[0] == e["header"], e["cmd"]
+        rows = lines[1:1 + e["count"]]
+        if "rows" in e and isinstance(e["rows"], list):
+            assert sorted(rows) == sorted(e["rows"]), e["cmd"]
+        else:
+            assert hashlib.sha256("\n".join(sorted(rows)).encode()).hexdigest() == e["rows_sorted_sha256"], e["cmd"]
         n += 1
     assert n >= 8
 
