@@ -217,6 +217,15 @@ int32_t mbc_bitmap_join(mbc_table* outer, mbc_table* inner,
                         const mbc_projspec* proj, int32_t nproj, uint32_t want,
                         const mbc_aggspec* aggs, int32_t nagg, mbc_result** out);
 
+/* ---- sort (input/ColumnarSort.java:73-400: `sort DB CF [sort columns] [projection] ASC|DSC ...`) --------------
+ * Rows ordered by the key columns, first key most significant: ints numerically, strings in byte order
+ * (= String.compareTo for BMP text, the comparator of ColumnarSort.java:163-205), reals numerically; `descending`
+ * reverses all keys at once.  Equal keys come out in ascending position (the reference's external merge leaves the
+ * order of ties unspecified).  Deleted rows are skipped.  The result carries the positions in sorted order
+ * (MBC_WANT_POSITIONS) and the projected columns / Tuple bytes of those rows (MBC_WANT_COLUMNS / MBC_WANT_TUPLES). */
+int32_t mbc_sort(mbc_table* t, const int32_t* key_cols, int32_t nkeys, int32_t descending,
+                 const int32_t* proj_cols, int32_t nproj, uint32_t want, mbc_result** out);
+
 /* ---- results -------------------------------------------------------------------------- */
 /* A device-resident result of mbc_scan (no MBC_WANT_HOST / MBC_WANT_TUPLES) completes asynchronously:
  * mbc_scan returns with its kernels queued on the context's stream, and the first call of

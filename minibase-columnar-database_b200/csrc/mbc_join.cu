@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(kSortThreads) rsort_scatter_kernel(const uint3
 }
 
 // sorts in place (result ends in keys/vals); tmp buffers of the same size are allocated here
-static int32_t radix_sort_pairs(mbc_ctx* ctx, uint32_t* d_keys, uint32_t* d_vals, int64_t n, int key_bits) {
+int32_t radix_sort_pairs(mbc_ctx* ctx, uint32_t* d_keys, uint32_t* d_vals, int64_t n, int key_bits) {
     if (n <= 1) return MBC_OK;
     uint32_t *tk = nullptr, *tv = nullptr, *hist = nullptr;
     unsigned long long* offs = nullptr;

@@ -223,6 +223,14 @@ class Table:
         """K4+K5: CNF over bitmap indexes."""
         return self._run(N.lib().mbc_bitmap_scan, terms, proj, want, aggs)
 
+    def sort(self, key_cols: Sequence[int], descending: bool = False, proj: Sequence[int] = (), want: int = 0) -> "Result":
+        """ColumnarSort: positions (and projected fields) of the live rows ordered by the key columns, ties by position."""
+        karr = (C.c_int32 * max(len(key_cols), 1))(*key_cols)
+        parr = (C.c_int32 * max(len(proj), 1))(*proj)
+        h = C.c_void_p()
+        N.check(N.lib().mbc_sort(self._h, karr, len(key_cols), 1 if descending else 0, parr, len(proj), want, C.byref(h)))
+        return Result(self.ctx, h, [self.coldescs[c] for c in proj], want, 0)
+
     # ---- bitmap indexes --------------------------------------------------------------------
     def bitmap_build(self, col: int) -> None:
         N.check(N.lib().mbc_bitmap_build(self._h, col))

@@ -295,3 +295,48 @@ class NljQuery:
             return res
         from .iterator import flatten_condexpr
         return cf.table.scan(flatten_condexpr(exprs), want=N.WANT_BITMAP)
+
+
+class ColumnarSort:
+    """input/ColumnarSort.java:73-400: `sort DB CF [sort columns] [projected columns] ASC|DSC NUMBUF SORTBUF`
+    (SURVEY.md 8f rank 4).  The reference runs an external merge sort over (keys, position) records; here the row ids
+    are radix-sorted on the GPU (mbc_sort) and the projected fields gathered in that order.  Same printed lines
+    `<projected values> :<position>`; rows with equal keys come out in ascending position."""
+
+    def execute(self, args: Sequence[str], echo: bool = True) -> list[str]:
+        if len(args) < 7:
+            raise Exception("Invalid number of attributes.")
+        cfname, sort_cols, proj_cols, order = args[1], args[2], args[3], args[4]
+        if not (sort_cols.startswith("[") and sort_cols.endswith("]")):
+            raise Exception("[TARGETCOLUMNNAMES] format invalid.")
+        if not (proj_cols.startswith("[") and proj_cols.endswith("]")):
+            raise Exception("[PROJECTIONCOLUMNNAMES] format invalid.")
+        if order not in ("ASC", "DSC"):
+            raise Exception("This sorting order is not supported")
+        try:
+            numbuf, sortbuf = int(args[5]), int(args[6])
+        except ValueError:
+            raise Exception("NUMBUF is not integer.")
+        if numbuf < 1:
+            raise Exception("NUMBUF is not more than 1.")
+        lines: list[str] = []
+        if sortbuf < 3:
+            _emit(lines, "NUMBUF_SORT is less than 3. External Sort Merge needs minimum 3 pages for the operation", echo)
+            return lines
+        cf = Columnarfile(cfname)
+        keys = [cf.colNameToIndex(n.strip()) for n in sort_cols[1:-1].split(",")]
+        proj = [cf.colNameToIndex(n.strip()) for n in proj_cols[1:-1].split(",")]
+        types = [cf.getAttributeTypes()[c].attrType for c in proj]
+        res = cf.table.sort(keys, descending=(order == "DSC"), proj=proj,
+                            want=N.WANT_POSITIONS | N.WANT_COLUMNS | N.WANT_HOST)
+        _emit(lines, "SORTED COLUMNS", echo)
+        pos = res.positions()
+        cols = [res.column(i) for i in range(len(proj))]
+        for k in range(res.count):                                  # printRecordsByPages: values, blank separated, then :position
+            vals = [str(int(cols[f][k])) if t == AttrType.attrInteger else repr(float(cols[f][k])) if t == AttrType.attrReal
+                    else bytes(cols[f][k]).rstrip(b"\0").decode("utf-8") for f, t in enumerate(types)]
+            _emit(lines, " ".join(vals) + " :" + str(int(pos[k])), echo)
+        _emit(lines, str(res.count), echo)
+        self.resultCount = res.count
+        res.close()
+        return lines

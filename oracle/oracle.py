@@ -278,6 +278,30 @@ def synth_str(seed: int, col: int, nrows: int, width: int, position_base: int = 
 # ---------------------------------------------------------------------------------------------
 # strings <-> fixed-width zero padded byte rows
 # ---------------------------------------------------------------------------------------------
+def sort(coldescs, columns, key_cols: Sequence[int], descending: bool = False, deleted_positions=()) -> np.ndarray:
+    """input/ColumnarSort.java:163-205 comparator, restated: the live positions ordered by the key columns (first key most
+    significant; ints numerically, strings by String.compareTo = byte order of the zero-padded BMP text), all keys
+    ascending or all descending.  Ties keep ascending position (the Java's external merge sort leaves tie order
+    unspecified: its golden output is compared as key sequence + row multiset)."""
+    n = nrows_of(coldescs, columns)
+    if n == 0:
+        return np.empty(0, dtype=np.int64)
+    live = np.ones(n, dtype=bool)
+    live[list(deleted_positions)] = False
+    ranks = []
+    for c in key_cols:
+        t, w = coldescs[c]
+        col = np.asarray(columns[c])
+        if t == 0:
+            keys = np.ascontiguousarray(col.reshape(n, -1)[:, :w]).view(f"S{w}").reshape(n)     # bytes compare, NUL padded
+        else:
+            keys = col.reshape(n)
+        _, inv = np.unique(keys, return_inverse=True)                                            # dense rank per column
+        ranks.append(-inv if descending else inv)
+    order = np.lexsort(tuple(reversed(ranks))) if ranks else np.arange(n)                        # stable: ties by position
+    return order[live[order]].astype(np.int64)
+
+
 def pack_strings(values: Sequence[str], width: int) -> np.ndarray:
     out = np.zeros((len(values), width), dtype=np.uint8)
     for i, s in enumerate(values):

@@ -6,7 +6,7 @@ Reads (never at test time -- only when this script is run in the authoring conta
     /root/reference/minidata.txt    the 500-row table every command in it was run on
 Writes:
     tests/golden/minidata.tsv       the data fixture (header `name:type`, tab separated)
-    tests/golden/phase3_golden.json one entry per index / indexes_query / bmj / nlj command:
+    tests/golden/phase3_golden.json one entry per index / indexes_query / bmj / nlj / sort command:
         the command line, the result count the reference printed, the printed rows (or their
         sha256 when there are more than 400), the side-filter bitsets `bmj` prints, and the
         per-value `BitSet.toByteArray().length` list `index ... bitmap` prints.
@@ -73,6 +73,21 @@ def main():
                         e["outer_bitset"] = [int(x) for x in re.findall(r"\d+", body[i + 1])]
                     if ln.startswith("InnerConstraint Bitset"):
                         e["inner_bitset"] = [int(x) for x in re.findall(r"\d+", body[i + 1])]
+        elif kind == "sort":
+            # `sort DB CF [sort columns] [projected columns] ASC|DSC NUMBUF SORTBUF`: after "SORTED COLUMNS" one line per row,
+            # "<projected values separated by blanks> :<position>", then the row count
+            if "SORTED COLUMNS" not in body:
+                e["failed"] = True
+            else:
+                start = body.index("SORTED COLUMNS") + 1
+                rows = []
+                for ln in body[start:]:
+                    if re.fullmatch(r"\d+", ln.strip()):
+                        e["count"] = int(ln.strip())
+                        break
+                    if ln.strip():
+                        rows.append(ln.rstrip())
+                e["rows"] = rows
         else:
             continue
         rp = [re.match(r"Read Page Count: (\d+)", ln) for ln in body]

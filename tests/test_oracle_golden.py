@@ -9,6 +9,8 @@ import re
 import numpy as np
 import pytest
 
+from util import check_sorted_like_golden
+
 
 def _fmt_rows(oracle, tuples, descs):
     return [", ".join(str(v) for v in oracle.decode_tuple(bytes(t), descs)) for t in tuples]
@@ -177,3 +179,27 @@ def test_stale_padding_mode_only_changes_padding(minidata, oracle):
     assert not np.array_equal(canon["tuples"], stale["tuples"])
     for a, b in zip(canon["tuples"], stale["tuples"]):
         assert oracle.decode_tuple(bytes(a), descs) == oracle.decode_tuple(bytes(b), descs)
+
+
+def _sort_lines(oracle, minidata, cmd):
+    names, descs, cols = minidata
+    parts = cmd.split()
+    keys = [names.index(x) for x in parts[3][1:-1].split(",")]
+    proj = [names.index(x) for x in parts[4][1:-1].split(",")]
+    order = oracle.sort(descs, cols, keys, descending=(parts[5] == "DSC"))
+    strs = {c: oracle.unpack_strings(cols[c]) for c in proj if descs[c][0] == 0}
+    lines = [" ".join(strs[c][p] if c in strs else str(int(cols[c][p])) for c in proj) + " :" + str(int(p)) for p in order]
+    return lines, len(keys), proj[:len(keys)] == keys
+
+
+def test_sort_golden(golden, minidata, oracle):
+    """`sort db cf [keys] [projection] ASC|DSC ...` (phase3_output:24-3156): six runs, one and four key columns."""
+    n = 0
+    for e in golden:
+        if e["kind"] != "sort" or e.get("failed"):
+            continue
+        lines, nkeys, lead = _sort_lines(oracle, minidata, e["cmd"])
+        assert e["count"] == len(lines) == 500
+        check_sorted_like_golden(lines, e["rows"], nkeys, lead)
+        n += 1
+    assert n == 6

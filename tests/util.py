@@ -73,3 +73,13 @@ def check_result(oracle, res, exp, proj_descs, want_tuples=True, real_rel_tol=1e
             assert gi == ei, f"agg {a}: {gi} != {ei}"
         else:
             assert abs(gf - ef) <= real_rel_tol * max(abs(ef), 1e-30), f"agg {a}: {gf} vs {ef}"
+
+
+def check_sorted_like_golden(lines, golden_rows, nkeys, keys_lead_projection):
+    """`sort` output against the reference's transcript.  The Java leaves the order of equal keys unspecified: the row
+    MULTISET must match, and -- when the projected fields start with the sort keys -- the sequence of key tuples must be
+    identical line by line."""
+    assert sorted(lines) == sorted(golden_rows)
+    if keys_lead_projection:
+        key = lambda ln: ln.rsplit(" :", 1)[0].split(" ")[:nkeys]
+        assert [key(a) for a in lines] == [key(b) for b in golden_rows]
