@@ -144,7 +144,8 @@ static int32_t exclusive_scan_u32(mbc_ctx* ctx, const uint32_t* d_in, int64_t n,
 // ---- stable LSD radix sort of (uint32 key, uint32 value) pairs, 8 bits per pass ---------------------------
 constexpr int kSortThreads = 256;
 constexpr int kSortWarps = kSortThreads / 32;
-constexpr int kSortChunk = 2048;                      // elements per block; each warp owns 256 consecutive ones
+constexpr int kSortRounds = 32;                                   // elements per lane
+constexpr int kSortChunk = kSortThreads * kSortRounds;            // 8192 elements per block; each warp owns 1024 consecutive ones
 
 __global__ void __launch_bounds__(kSortThreads) rsort_hist_kernel(const uint32_t* keys, int64_t n, int shift, uint32_t* hist /*[256][nblocks]*/) {
     __shared__ uint32_t sh[256];
@@ -159,52 +160,92 @@ __global__ void __launch_bounds__(kSortThreads) rsort_hist_kernel(const uint32_t
     hist[(size_t)threadIdx.x * gridDim.x + blockIdx.x] = sh[threadIdx.x];
 }
 
-__global__ void __launch_bounds__(kSortThreads) rsort_scatter_kernel(const uint32_t* keys, const uint32_t* vals, int64_t n, int shift,
-                                                                     const unsigned long long* offsets /*[256][nblocks] scanned*/,
-                                                                     uint32_t* out_keys, uint32_t* out_vals) {
-    __shared__ uint32_t cnt[kSortWarps][256];         // per-warp digit counts, then running cursors
+// lanes of the warp that hold the same digit (d < 0: none): one ballot per digit bit -- constant cost, where
+// __match_any_sync's grows with the number of distinct digits in the warp (~32 here)
+__device__ __forceinline__ uint32_t same_digit_lanes(int d) {
+    uint32_t peers = __ballot_sync(0xFFFFFFFFu, d >= 0);
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+        const uint32_t v = __ballot_sync(0xFFFFFFFFu, (d >> b) & 1);
+        peers &= ((d >> b) & 1) ? v : ~v;
+    }
+    return peers;
+}
+
+__global__ void __launch_bounds__(kSortThreads) rsort_scatter_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, int64_t n,
+                                                                     int shift, const unsigned long long* __restrict__ offsets /*[256][nblocks] scanned*/,
+                                                                     uint32_t* __restrict__ out_keys, uint32_t* __restrict__ out_vals) {
+    extern __shared__ uint32_t stage[];               // [kSortChunk] keys then [kSortChunk] values, in block-sorted order
+    __shared__ uint32_t cnt[kSortWarps][256];         // per-warp digit counts, then running cursors (block-local positions)
+    __shared__ uint32_t dstart[256];                  // block-local start of every digit's run
+    __shared__ unsigned long long gbase[256];         // global start of every digit's run of this block
+    __shared__ uint32_t wsum[kSortWarps];
+    uint32_t* s_key = stage;
+    uint32_t* s_val = stage + kSortChunk;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int d = lane; d < 256; d += 32) cnt[warp][d] = 0;
     __syncwarp();
-    const int64_t wbase = (int64_t)blockIdx.x * kSortChunk + warp * (kSortChunk / kSortWarps);
-    // phase A: digit histogram of this warp's 256 consecutive elements
-    for (int r = 0; r < kSortChunk / kSortWarps / 32; ++r) {
-        int64_t i = wbase + r * 32 + lane;
-        int d = i < n ? (int)((keys[i] >> shift) & 255u) : -1;
-        uint32_t grp = __match_any_sync(0xFFFFFFFFu, d);
-        if (d >= 0 && (grp & ((1u << lane) - 1)) == 0) cnt[warp][d] += __popc(grp);
-        __syncwarp();
+    const int64_t bbase = (int64_t)blockIdx.x * kSortChunk;
+    const int64_t wbase = bbase + warp * (kSortChunk / kSortWarps);
+    const int nblk = (int)min((int64_t)kSortChunk, n - bbase);
+    // phase A: the warp's 1024 consecutive keys into registers (all loads in flight at once) and its digit histogram
+    uint32_t key[kSortRounds];
+#pragma unroll
+    for (int r = 0; r < kSortRounds; ++r) {
+        const int64_t i = wbase + r * 32 + lane;
+        key[r] = i < n ? keys[i] : 0u;
     }
+#pragma unroll
+    for (int r = 0; r < kSortRounds; ++r)
+        if (wbase + r * 32 + lane < n) atomicAdd(&cnt[warp][(key[r] >> shift) & 255u], 1u);
     __syncthreads();
-    // phase B: exclusive prefix over the warps per digit -> starting cursor of every (warp, digit)
+    // phase B: thread d owns digit d: prefix over the warps, then an exclusive scan of the 256 digit totals of the block
     {
-        const int d = threadIdx.x;                    // 256 threads = 256 digits
-        unsigned long long base = offsets[(size_t)d * gridDim.x + blockIdx.x];
+        const int d = threadIdx.x;
         uint32_t run = 0;
         for (int w = 0; w < kSortWarps; ++w) {
-            uint32_t c = cnt[w][d];
+            const uint32_t c = cnt[w][d];
             cnt[w][d] = run;
             run += c;
         }
-        // stash the 64-bit global base of the digit in shared memory next to the cursors
-        __shared__ unsigned long long gbase[256];
-        gbase[d] = base;
-        __syncthreads();
-        // phase C: stable scatter, round by round
-        for (int r = 0; r < kSortChunk / kSortWarps / 32; ++r) {
-            int64_t i = wbase + r * 32 + lane;
-            int dg = i < n ? (int)((keys[i] >> shift) & 255u) : -1;
-            uint32_t grp = __match_any_sync(0xFFFFFFFFu, dg);
-            uint32_t rank = __popc(grp & ((1u << lane) - 1));
-            if (dg >= 0) {
-                unsigned long long dst = gbase[dg] + cnt[warp][dg] + rank;
-                out_keys[dst] = keys[i];
-                out_vals[dst] = vals[i];
-            }
-            __syncwarp();
-            if (dg >= 0 && rank == 0) cnt[warp][dg] += __popc(grp);
-            __syncwarp();
+        uint32_t incl = run;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t x = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if (lane >= o) incl += x;
         }
+        if (lane == 31) wsum[warp] = incl;
+        __syncthreads();
+        uint32_t before = 0;
+        for (int w = 0; w < warp; ++w) before += wsum[w];
+        dstart[d] = before + incl - run;
+        gbase[d] = offsets[(size_t)d * gridDim.x + blockIdx.x];
+    }
+    __syncthreads();
+    // phase C: stable placement in shared memory, round by round (rank within the round = lower lanes with the same digit)
+#pragma unroll
+    for (int r = 0; r < kSortRounds; ++r) {
+        const int64_t i = wbase + r * 32 + lane;
+        const int dg = i < n ? (int)((key[r] >> shift) & 255u) : -1;
+        const uint32_t grp = same_digit_lanes(dg);
+        const uint32_t rank = __popc(grp & ((1u << lane) - 1));
+        if (dg >= 0) {
+            const uint32_t pos = dstart[dg] + cnt[warp][dg] + rank;
+            s_key[pos] = key[r];
+            s_val[pos] = vals[i];
+        }
+        __syncwarp();
+        if (dg >= 0 && rank == 0) cnt[warp][dg] += __popc(grp);
+        __syncwarp();
+    }
+    __syncthreads();
+    // phase D: copy out in sorted order: consecutive threads write consecutive addresses inside every digit's run
+    for (int j = threadIdx.x; j < nblk; j += kSortThreads) {
+        const uint32_t k = s_key[j];
+        const uint32_t d = (k >> shift) & 255u;
+        const unsigned long long dst = gbase[d] + (uint32_t)j - dstart[d];
+        out_keys[dst] = k;
+        out_vals[dst] = s_val[j];
     }
 }
 
@@ -218,13 +259,18 @@ int32_t radix_sort_pairs(mbc_ctx* ctx, uint32_t* d_keys, uint32_t* d_vals, int64
     MBC_TRY(dev_alloc(ctx, (void**)&tv, (size_t)n * 4, false));
     MBC_TRY(dev_alloc(ctx, (void**)&hist, (size_t)256 * nblocks * 4, false));
     MBC_TRY(dev_alloc(ctx, (void**)&offs, ((size_t)256 * nblocks + 1) * 8, false));
+    static bool configured = false;
+    if (!configured) {
+        MBC_CUDA(cudaFuncSetAttribute(rsort_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSortChunk * 8));
+        configured = true;
+    }
     uint32_t *sk = d_keys, *sv = d_vals, *dk = tk, *dv = tv;
     int passes = std::max(1, (key_bits + 7) / 8);
     for (int p = 0; p < passes; ++p) {
         rsort_hist_kernel<<<(unsigned)nblocks, kSortThreads, 0, ctx->stream>>>(sk, n, p * 8, hist);
         ctx->launches++;
         MBC_TRY(exclusive_scan_u32(ctx, hist, 256 * nblocks, offs));
-        rsort_scatter_kernel<<<(unsigned)nblocks, kSortThreads, 0, ctx->stream>>>(sk, sv, n, p * 8, offs, dk, dv);
+        rsort_scatter_kernel<<<(unsigned)nblocks, kSortThreads, kSortChunk * 8, ctx->stream>>>(sk, sv, n, p * 8, offs, dk, dv);
         ctx->launches++;
         std::swap(sk, dk);
         std::swap(sv, dv);
