@@ -132,10 +132,22 @@ class Columnarfile:
     def _push_deleted(self, bits: BitSet) -> None:
         self.table.set_deleted(bits.words if bits.words.size else np.zeros(1, dtype=np.uint64))
 
-    def markTupleDeleted(self, position: int) -> bool:
-        """Columnarfile.java:812: only the GPU-resident deleted bitmap is maintained here."""
-        self._deleted.set(position)
+    def markTupleDeleted(self, position) -> bool:
+        """Columnarfile.java:812 markTupleDeleted(TID) (a bare position is accepted too): only the GPU-resident deleted
+        bitmap is maintained here."""
+        self._deleted.set(position.position if isinstance(position, TID) else int(position))
         return True
+
+    def markTuplesDeleted(self, positions) -> int:
+        """The delete drivers' loop `while ((tid = scan.get_next_tid()) != null) markTupleDeleted(tid)` in one step: all
+        bits are set on the host BitSet, the device copy is refreshed once."""
+        bits = self._deleted.getBitSet()
+        n = 0
+        for p in positions:
+            bits.set(p.position if isinstance(p, TID) else int(p))
+            n += 1
+        self._push_deleted(bits)
+        return n
 
     # ---- scans ---------------------------------------------------------------------------------------------------------------
     def openTupleScan(self) -> "TupleScan":

@@ -340,3 +340,65 @@ class ColumnarSort:
         self.resultCount = res.count
         res.close()
         return lines
+
+
+class DeleteQuery:
+    """input/DeleteQuery.java:27-205: `delete_query DB CF {col,op,val} NUMBUF FILESCAN|COLUMNSCAN|BITMAP md|pd`.
+    The qualifying TIDs come from the tid-only constructors of ColumnarFileScan / ColumnarColumnScan / ColumnIndexScan
+    (`get_next_tid`), every one is marked deleted (Columnarfile.markTupleDeleted, :812) and every later scan skips those
+    rows.  `pd` (purge: rewrite the heap files without the rows) is a mutation of the storage engine and stays in Java."""
+
+    def execute(self, args: Sequence[str], echo: bool = True) -> list[str]:
+        if len(args) < 6:
+            raise Exception("Invalid number of attributes.")
+        cfname, constraint, access, delete_type = args[1], args[2], args[4], args[5]
+        if not (constraint.startswith("{") and constraint.endswith("}")):
+            raise Exception("VALUECONSTRAINT format invalid.")
+        try:
+            if int(args[3]) < 1:
+                raise Exception("NUMBUF is not more than 1.")
+        except ValueError:
+            raise Exception("NUMBUF is not integer.")
+        if access.upper() not in ("FILESCAN", "COLUMNSCAN", "BTREE", "BITMAP"):
+            raise Exception("access type invalid.")
+        if delete_type.lower() not in ("md", "pd"):
+            raise Exception("delete type invalid.")
+        if access.upper() == "BTREE":
+            raise Exception("BTREE access stays in Java (out of scope for the GPU path)")
+        if delete_type.lower() == "pd":
+            raise Exception("purge (pd) rewrites the heap files: stays in Java; use md")
+        cf = Columnarfile(cfname)
+        parts = constraint[1:-1].strip().split(",")
+        if len(parts) != 3:
+            raise Exception("Invalid VALUECONSTRAINT elements")
+        exprs, itypes, fnums, inames = build_cnf_condexpr("{(" + ",".join(parts) + ")}", cf)
+        col = cf.colNameToIndex(parts[0].strip())
+        if access.upper() == "FILESCAN":                           # executeFileScan (:119-133)
+            it = ColumnarFileScan(cfname, cf.getAttributeTypes(), cf.getStringSizes(), cf.getFieldCount(), exprs)
+        elif access.upper() == "COLUMNSCAN":                       # executeColumnScan (:135-153)
+            import copy
+            colscan = copy.deepcopy(exprs)
+            for e in colscan:
+                if e is not None and e.type1.attrType == AttrType.attrSymbol:
+                    e.operand1.symbol = FldSpec(RelSpec(RelSpec.outer), 1)
+            it = ColumnarColumnScan(cf, col, colscan)
+        else:                                                      # executeBitmapScan (:181-205)
+            if not cf.bitmapIndexExists(col):
+                raise Exception("Bitmap index does not exist on column " + parts[0])
+            it = ColumnarIndexScan(cf, fnums, itypes, inames, cf.getAttributeTypes(), cf.getStringSizes(), cf.getFieldCount(), exprs)
+        tids = []
+        if isinstance(it, ColumnarIndexScan):
+            tids = [int(p) for p in it.getOutputPositions().positions()]
+        else:
+            while True:
+                tid = it.get_next_tid()
+                if tid is None:
+                    break
+                tids.append(tid)
+        it.close()
+        self.deletedCount = cf.markTuplesDeleted(tids)
+        lines: list[str] = []
+        _emit(lines, "=======================EXTRA METAINFO===============================", echo)
+        _emit(lines, str(cf.getTupleCnt()), echo)
+        _emit(lines, repr(cf.getMarkedDeleted().getBitSet()), echo)  # Columnarfile.printDeleteBitset (:573)
+        return lines

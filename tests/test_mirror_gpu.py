@@ -12,7 +12,7 @@ from mbcol import _native as N
 from mbcol.columnar import Columnarfile
 from mbcol.global_ import AttrOperator, AttrType, IndexType, IntegerValue, StringValue, SystemDefs, TID
 from mbcol.index import ColumnarIndexScan, ColumnIndexScan
-from mbcol.input import BitMapQuery, Index, MultiIndexQuery, NljQuery, Query, build_cnf_condexpr
+from mbcol.input import BitMapQuery, DeleteQuery, Index, MultiIndexQuery, NljQuery, Query, build_cnf_condexpr
 from mbcol.iterator import ColumnarColumnScan, ColumnarColumnsScan, ColumnarFileScan, CondExpr, FldSpec, RelSpec
 
 pytestmark = pytest.mark.gpu
@@ -320,3 +320,33 @@ def test_mark_deleted_is_seen_by_every_scan(db, oracle, minidata):
     for p in victims:
         cf.getMarkedDeleted().clear(p)
     assert "Total Results Count By Query: %d" % int((cols[2] == 6).sum()) in Query().execute(["db", "cf2", "[C]", "{C,=,6}", "10", "FILESCAN"], echo=False)
+
+
+def test_delete_query_marks_rows_for_every_later_scan(db, oracle, minidata):
+    """input.DeleteQuery (`delete_query DB CF {constraint} NUMBUF access md`): the TIDs come from get_next_tid of the
+    tid-only scan constructors, markTupleDeleted hides the rows from every scan that follows -- through each access path,
+    on a private copy of the table so the other tests keep theirs."""
+    names, descs, cols = minidata
+    from mbcol.global_ import AttrType as AT
+    cf = Columnarfile("delq", 4, [AT(t) for t, _ in descs], [w for _, w in descs], names)
+    cf.load_columns(cols)
+    Index().createIndex(["db", "delq", "C", "bitmap"])
+    gone = np.zeros(500, dtype=bool)
+    for cons, access in (("{C,=,6}", "FILESCAN"), ("{A,<,Colorado}", "COLUMNSCAN"), ("{C,=,0}", "BITMAP")):
+        col, op, lit = cons[1:-1].split(",")
+        ci = names.index(col)
+        term = oracle.Term(oracle.OPS[op], ("col", ci), ("int", int(lit)) if descs[ci][0] == 1 else ("str", lit), 0)
+        hit = np.zeros(500, dtype=bool)
+        hit[oracle.scan(descs, cols, [term])["positions"]] = True
+        q = DeleteQuery()
+        lines = q.execute(["db", "delq", cons, "100", access, "md"], echo=False)
+        assert q.deletedCount == int((hit & ~gone).sum()) > 0                # rows deleted earlier are not seen again
+        gone |= hit
+        assert lines[1] == "500"
+        assert cf.getMarkedDeleted().getBitSet().positions().tolist() == np.flatnonzero(gone).tolist()
+        rest = Query().execute(["db", "delq", "[A,C]", "{D,>=,0}", "100", "FILESCAN"], echo=False)
+        assert f"Total Results Count By Query: {int((~gone).sum())}" in rest
+    assert Query().execute(["db", "delq", "[C]", "{C,=,6}", "100", "COLUMNSCAN"], echo=False)[-3].endswith(": 0")
+    with pytest.raises(Exception, match="stays in Java"):
+        DeleteQuery().execute(["db", "delq", "{C,=,1}", "100", "FILESCAN", "pd"], echo=False)
+    cf.close()
