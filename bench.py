@@ -205,6 +205,19 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     counts = {}
 
     views = {}
+    # how the 1% result reaches rank 0: NCCL all-gather of padded blocks (default), grouped send/recv ("p2p"), or copies into
+    # rank 0's IPC-exported buffer ("peer": measured 10.3 ms per step at N=2 on this pool -- the cross-process peer copies
+    # ran at ~5 GB/s, i.e. staged through the host, not NVLink DMA -- so it is opt-in)
+    gather_mode = [os.environ.get("MBC_BENCH_GATHER", "allgather")]
+    peer = [None]
+    if world > 1 and gather_mode[0] == "peer":
+        from mbcol import sharding as _sh
+        try:                                                    # 3 % of the whole table's rows x 36 B: three times the 1 % result
+            peer[0] = _sh.PeerGather(int(0.03 * rows * world) * ROW_BYTES_OUT, dev)
+        except Exception as e:                                  # every rank raises alike (agreed by an all-reduce inside)
+            if rank == 0:
+                print(f"[bench] peer-memory gather unavailable ({e}); using the NCCL all-gather form", file=sys.stderr)
+            gather_mode[0] = "allgather"
 
     def dev_bytes(ptr, nbytes):
         """uint8 view of device memory owned by the library.  The pool hands the same buffers back step after step, so
@@ -219,7 +232,8 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         """mbcol.sharding over NCCL, once per step: ONE all-gather of every rank's [aggregates..., count] blocks of the
         three scans (each rank then folds COUNT/SUM/MIN/MAX on the host, which is the all-reduce), then the 1% query's
         positions + projected values are gathered on rank 0 in rank (= position) order through one all-gather of
-        padded blocks (mbcol.sharding.allgather_rows; MBC_BENCH_GATHER=p2p selects the grouped send/recv form)."""
+        padded blocks (mbcol.sharding.allgather_rows); MBC_BENCH_GATHER=p2p selects the grouped send/recv form, =peer the
+        copies into rank 0's IPC-exported buffer (mbcol.sharding.PeerGather)."""
         from mbcol import sharding
         mine = torch.cat([dev_bytes(r.device_pointers()["aggs"], 9 * 8) for r in results]).view(torch.int64)
         blocks = sharding.allgather_blocks(mine).view(world, len(results), 9).cpu().numpy()   # every rank sees every rank's partials
@@ -228,9 +242,12 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         cnts = [int(c) for c in blocks[:, 0, 8]]
         bufs = [(res.device_pointers()["positions"], 8)] + [res.column_device(i) for i in range(4)]
         locals_ = [(dev_bytes(ptr, rows * stride)[:res.count * stride], stride) for ptr, stride in bufs]
-        if os.environ.get("MBC_BENCH_GATHER") == "p2p":
+        mode = gather_mode[0]
+        if mode == "peer":                                      # rank 0: the whole table's 1% result, in position order
+            gathered = peer[0].gather(locals_, cnts)            # DMA into rank 0's IPC-exported buffer over NVLink
+        elif mode == "p2p":
             gathered = sharding.gather_rows_multi(locals_, cnts)
-        else:                                                   # rank 0: the whole table's 1% result, in position order
+        else:
             gathered = sharding.allgather_rows(locals_, cnts)
         return folded, gathered
 
