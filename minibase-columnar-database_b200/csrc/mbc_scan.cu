@@ -361,7 +361,9 @@ static int32_t launch_job(ScanJob* job, int tile_base, bool first) {
     job->launches++;
     ctx->launches += 2;
     if (job->r->ev_mid[1]) cudaEventRecord(job->r->ev_mid[1], ctx->stream);
-    if (p.out_pos || p.nproj > 0 || p.nagg > 0) {
+    bool need_write = p.out_pos || p.nproj > 0;
+    for (int a = 0; a < p.nagg; ++a) need_write |= p.aggs[a].kind != MBC_AGG_COUNT;   // COUNT comes from the tile offsets
+    if (need_write) {
         const char* pt = getenv("MBC_WRITE_PERSISTENT_TILES");          // tests force either form
         const int persistent_min_tiles = pt ? atoi(pt) : 49152;
         if (p.ntiles >= persistent_min_tiles) {
@@ -388,10 +390,16 @@ static int32_t finish_job_device(ScanJob* job, int64_t tiles_done, bool deferred
     mbc_result* r = job->r;
     if (job->launches == 0) MBC_CUDA(cudaMemsetAsync(job->w.count, 0, 16, ctx->stream));   // nothing was scanned
     if (p.nagg > 0) {
-        AggList list;
-        memcpy(list.g, p.aggs, sizeof(list.g));
-        agg_finish_kernel<<<p.nagg, 1024, 0, ctx->stream>>>(job->w.partials, (int)job->total_tiles, (int)tiles_done, list,
-                                                           job->w.agg_out, job->count_slot());
+        bool count_only = true;
+        for (int a = 0; a < p.nagg; ++a) count_only &= p.aggs[a].kind == MBC_AGG_COUNT;
+        if (count_only) {
+            agg_count_only_kernel<<<1, 32, 0, ctx->stream>>>(p.nagg, job->w.agg_out, job->count_slot());
+        } else {
+            AggList list;
+            memcpy(list.g, p.aggs, sizeof(list.g));
+            agg_finish_kernel<<<p.nagg, 1024, 0, ctx->stream>>>(job->w.partials, (int)job->total_tiles, (int)tiles_done, list,
+                                                               job->w.agg_out, job->count_slot());
+        }
         ctx->launches++;
         MBC_CUDA(cudaGetLastError());
     }

@@ -895,6 +895,11 @@ __global__ void __launch_bounds__(1024) agg_finish_kernel(const unsigned long lo
     if (threadIdx.x == 0) out[blockIdx.x] = sh[0];
 }
 
+// COUNT is the only aggregate asked for: the running count is the answer, no partials to reduce
+__global__ void agg_count_only_kernel(int nagg, unsigned long long* out, const long long* count) {
+    if (threadIdx.x <= kMaxAgg) out[threadIdx.x] = (threadIdx.x < nagg || threadIdx.x == kMaxAgg) ? (unsigned long long)*count : 0ull;
+}
+
 struct TupleField {
     const void* src;
     int32_t type, width, stride, offset;

@@ -5,7 +5,7 @@ import pytest
 
 import mbcol
 from mbcol import _native as N
-from util import C2_DESCS, c2_columns, check_result, load_table
+from util import C2_DESCS, c2_columns, c2_terms, check_result, load_table
 
 pytestmark = pytest.mark.gpu
 ALL = N.WANT_POSITIONS | N.WANT_COLUMNS | N.WANT_TUPLES | N.WANT_AGG | N.WANT_HOST
@@ -72,7 +72,10 @@ def test_shapes_that_return_nothing_or_everything(ctx, oracle):
     np.testing.assert_array_equal(every.positions(), np.arange(n))
     only_aggs = t.scan([], want=N.WANT_AGG, aggs=[(1, 1), (3, 2)])                    # nothing materialised but aggregates
     assert only_aggs.agg(0)[0] == int(cols[1].astype(np.int64).sum()) and only_aggs.agg(1)[1] == float(cols[2].max())
-    for r in (none, every, only_aggs):
+    counts = t.scan(c2_terms(oracle, 0.1), want=N.WANT_AGG, aggs=[(0, 0), (0, 2)])      # COUNT only: no write pass at all
+    exp = oracle.scan(C2_DESCS, cols, c2_terms(oracle, 0.1))["count"]
+    assert counts.count == exp and counts.agg(0) == (exp, float(exp), True) and counts.agg(1)[0] == exp
+    for r in (none, every, only_aggs, counts):
         r.close()
     t.close()
 
