@@ -179,7 +179,12 @@ int32_t mbc_scan(mbc_table* t, const mbc_term* terms, int32_t nterms,
                  const mbc_aggspec* aggs, int32_t nagg, mbc_result** out);
 /* Same scan over host-resident columns: rows are streamed to the GPU in chunks (H2D on a copy
  * stream overlapped with the scan of the previous chunk) and the result is copied back.
- * host_cols[c] follows the mbc_table_load_column layout.  This is the end-to-end path. */
+ * host_cols[c] follows the mbc_table_load_column layout.  This is the end-to-end path.
+ * Late materialisation: a column that is only projected / aggregated (never compared) whose buffer is pinned
+ * host memory (mbc_host_alloc, cudaHostAlloc, cudaHostRegister), 16-byte aligned and laid out like the device
+ * column is not uploaded when a first 256 Ki-row sample shows that at most 1/5 of the rows qualify: the write
+ * pass then reads the survivors' values in place over PCIe.  Results are identical either way; pageable buffers
+ * always take the upload path.  mbc_h2d_bytes() counts what crossed. */
 int32_t mbc_scan_host(mbc_ctx* ctx, int32_t ncols, const mbc_coldesc* cols, const void* const* host_cols,
                       int64_t nrows, int64_t position_base,
                       const mbc_term* terms, int32_t nterms, const int32_t* proj_cols, int32_t nproj,
