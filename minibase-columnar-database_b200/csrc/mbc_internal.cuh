@@ -192,6 +192,7 @@ struct ScanRequest {
 int32_t run_scan(const ScanRequest& rq, mbc_result** out);
 int32_t finish_result_host(mbc_result* r);     // tuple encode + D2H according to r->want
 // stable LSD radix sort of (key, value) pairs by the low key_bits bits of the keys, in place (mbc_join.cu)
-int32_t radix_sort_pairs(mbc_ctx* ctx, uint32_t* d_keys, uint32_t* d_vals, int64_t n, int key_bits);
+// pass_mask: bit p = run the pass over key bits [8p, 8p+8) (clear it for digits known to be constant)
+int32_t radix_sort_pairs(mbc_ctx* ctx, uint32_t* d_keys, uint32_t* d_vals, int64_t n, int key_bits, uint32_t pass_mask = 0xFu);
 
 }  // namespace mbc

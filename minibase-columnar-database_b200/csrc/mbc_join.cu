@@ -250,8 +250,8 @@ __global__ void __launch_bounds__(kSortThreads) rsort_scatter_kernel(const uint3
 }
 
 // sorts in place (result ends in keys/vals); tmp buffers of the same size are allocated here
-int32_t radix_sort_pairs(mbc_ctx* ctx, uint32_t* d_keys, uint32_t* d_vals, int64_t n, int key_bits) {
-    if (n <= 1) return MBC_OK;
+int32_t radix_sort_pairs(mbc_ctx* ctx, uint32_t* d_keys, uint32_t* d_vals, int64_t n, int key_bits, uint32_t pass_mask) {
+    if (n <= 1 || pass_mask == 0) return MBC_OK;
     uint32_t *tk = nullptr, *tv = nullptr, *hist = nullptr;
     unsigned long long* offs = nullptr;
     int64_t nblocks = (n + kSortChunk - 1) / kSortChunk;
@@ -267,6 +267,7 @@ int32_t radix_sort_pairs(mbc_ctx* ctx, uint32_t* d_keys, uint32_t* d_vals, int64
     uint32_t *sk = d_keys, *sv = d_vals, *dk = tk, *dv = tv;
     int passes = std::max(1, (key_bits + 7) / 8);
     for (int p = 0; p < passes; ++p) {
+        if (!((pass_mask >> p) & 1u)) continue;                 // this digit is the same in every key: a stable pass would change nothing
         rsort_hist_kernel<<<(unsigned)nblocks, kSortThreads, 0, ctx->stream>>>(sk, n, p * 8, hist);
         ctx->launches++;
         MBC_TRY(exclusive_scan_u32(ctx, hist, 256 * nblocks, offs));

@@ -25,6 +25,22 @@ __global__ void __launch_bounds__(256) sort_key_kernel(const uint32_t* __restric
     }
 }
 
+// OR and AND of all keys: a byte in which they agree is the same in every key, and its radix pass can be skipped
+__global__ void __launch_bounds__(256) sort_key_bits_kernel(const uint32_t* __restrict__ keys, int64_t n, uint32_t* or_and /* [2], preset {0, ~0} */) {
+    uint32_t o = 0u, a = ~0u;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t k = keys[i];
+        o |= k;
+        a &= k;
+    }
+    o = __reduce_or_sync(0xFFFFFFFFu, o);
+    a = __reduce_and_sync(0xFFFFFFFFu, a);
+    if ((threadIdx.x & 31) == 0) {
+        atomicOr(or_and, o);
+        atomicAnd(or_and + 1, a);
+    }
+}
+
 __global__ void __launch_bounds__(256) sort_rows_from_positions_kernel(const int64_t* __restrict__ pos, int64_t n, int64_t base,
                                                                       uint32_t* __restrict__ rows) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
@@ -77,10 +93,11 @@ extern "C" int32_t mbc_sort(mbc_table* t, const int32_t* key_cols, int32_t nkeys
     r->nrows = t->nrows;
     r->count = n;
     r->capacity = n;
-    uint32_t *rows = nullptr, *keys = nullptr;
+    uint32_t *rows = nullptr, *keys = nullptr, *bits = nullptr;
     auto fail = [&](int32_t s) {
         dev_free(ctx, rows);
         dev_free(ctx, keys);
+        dev_free(ctx, bits);
         mbc_result_free(all);
         mbc_result_free(r);
         return s;
@@ -91,6 +108,7 @@ extern "C" int32_t mbc_sort(mbc_table* t, const int32_t* key_cols, int32_t nkeys
     if (n > 0) {
         STRY(dev_alloc(ctx, (void**)&rows, (size_t)n * 4, false));
         STRY(dev_alloc(ctx, (void**)&keys, (size_t)n * 4, false));
+        STRY(dev_alloc(ctx, (void**)&bits, 8, false));
         sort_rows_from_positions_kernel<<<grid, 256, 0, ctx->stream>>>(all->d_pos, n, t->pos_base, rows);
         ctx->launches++;
         for (int k = nkeys - 1; k >= 0; --k) {
@@ -98,8 +116,19 @@ extern "C" int32_t mbc_sort(mbc_table* t, const int32_t* key_cols, int32_t nkeys
             const int words = c.type == MBC_ATTR_STRING ? (c.width + 3) / 4 : 1;      // bytes past the width are zero padding
             for (int w = words - 1; w >= 0; --w) {
                 sort_key_kernel<<<grid, 256, 0, ctx->stream>>>(rows, n, c.d, c.stride, w, c.type, descending ? 1 : 0, keys);
-                ctx->launches++;
-                STRY(radix_sort_pairs(ctx, keys, rows, n, 32));
+                // which of the four digits vary at all (small int domains, zero padding and common prefixes of strings do not)
+                const uint32_t preset[2] = {0u, ~0u};
+                uint32_t seen[2];
+                if (cudaMemcpyAsync(bits, preset, 8, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) return fail(MBC_ERR_CUDA);
+                sort_key_bits_kernel<<<grid, 256, 0, ctx->stream>>>(keys, n, bits);
+                ctx->launches += 2;
+                if (cudaMemcpyAsync(seen, bits, 8, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+                    cudaStreamSynchronize(ctx->stream) != cudaSuccess) return fail(MBC_ERR_CUDA);
+                const uint32_t differ = seen[0] ^ seen[1];
+                uint32_t pass_mask = 0;
+                for (int b = 0; b < 4; ++b)
+                    if ((differ >> (8 * b)) & 0xFFu) pass_mask |= 1u << b;
+                STRY(radix_sort_pairs(ctx, keys, rows, n, 32, pass_mask));
             }
         }
     }
@@ -127,6 +156,7 @@ extern "C" int32_t mbc_sort(mbc_table* t, const int32_t* key_cols, int32_t nkeys
     MBC_CUDA(cudaStreamSynchronize(ctx->stream));
     dev_free(ctx, rows);
     dev_free(ctx, keys);
+    dev_free(ctx, bits);
     mbc_result_free(all);
     *out = r;
     return MBC_OK;
