@@ -103,12 +103,38 @@ def c4(ctx, n_r, n_s, reps):
     return out
 
 
+def cpu_baselines(build_rows=2_000_000, n_r=5_000, n_s=250_000):
+    """The oracle (literal CPU restatement of the reference, test infrastructure) timed on bounded samples of the same
+    workloads on this box's host cores, next to the GPU numbers: a reported baseline, not a target."""
+    import time
+    from oracle import oracle as orc
+    orc.build()
+    K = orc.synth_int(SEED, 0, build_rows, 1000)
+    t0 = time.perf_counter()
+    idx = orc.bitmap_build((1, 4), K)
+    tb = time.perf_counter() - t0
+    rng = np.random.default_rng(0)
+    Rd, Sd = [(1, 4), (1, 4)], [(1, 4), (1, 4), (2, 4)]
+    Rc = [orc.synth_perm(n_r, n_r), rng.integers(0, 1000, n_r).astype(np.int32)]
+    Sc = [rng.integers(0, n_r, n_s).astype(np.int32), rng.integers(0, 1000, n_s).astype(np.int32), rng.random(n_s).astype(np.float32)]
+    jt = [orc.Term(orc.OP_EQ, ("col", 0), ("icol", 0), 0)]
+    t0 = time.perf_counter()
+    r = orc.bitmap_join(Rd, Rc, Sd, Sc, jt, [(1, 0), (1, 1), (2, 1), (2, 2)], aggs=[(0, 0), (1, 2), (1, 1), (1, 3)])
+    tj = time.perf_counter() - t0
+    assert len(idx) == 1000 and r["count"] == n_s
+    return {"kind": "port", "cores": orc.max_threads(),
+            "c3_build_K": {"rows_per_s": build_rows / tb, "sample": f"{build_rows} rows, 1000 distinct values; oracle.bitmap_build (numpy, 1 thread)"},
+            "c4_join": {"probe_rows_per_s": n_s / tj, "sample": f"R {n_r} x S {n_s} rows, pair list + tuples + aggregates like BitMapQuery.executeJoin; "
+                                                                 f"oracle/mbc_oracle.cpp orc_bitmap_join"}}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--rows", type=int, default=500_000_000)
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--skip-c3", action="store_true")
     ap.add_argument("--skip-c4", action="store_true")
+    ap.add_argument("--cpu-baseline", action="store_true", help="also time the oracle on bounded samples (host cores)")
     a = ap.parse_args()
     ctx = mbcol.Context(0)
     if not a.skip_c3:
@@ -116,6 +142,8 @@ def main():
     if not a.skip_c4:
         print(json.dumps(c4(ctx, a.rows // 50, a.rows, a.reps)), flush=True)
     ctx.close()
+    if a.cpu_baseline:
+        print(json.dumps({"cpu_baseline": cpu_baselines()}), flush=True)
 
 
 if __name__ == "__main__":
