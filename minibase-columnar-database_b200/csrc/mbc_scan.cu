@@ -479,7 +479,7 @@ int32_t run_scan(const ScanRequest& rq, mbc_result** out) {
 
 // Host-resident columns: stream row chunks through two staging tables.  The copy stream uploads
 // chunk k+1 while the scan of chunk k runs; every chunk appends to the same result buffers (the
-// look-back of a chunk starts from the running output offset left by the previous one).
+// output offsets of a chunk start from the running count left by the previous one).
 static int32_t run_scan_host(mbc_ctx* ctx, int32_t ncols, const mbc_coldesc* cols, const void* const* host_cols,
                              int64_t nrows, int64_t position_base, const ScanRequest& rq_in, mbc_result** out) {
     *out = nullptr;

@@ -17,14 +17,16 @@
 //   * the CNF is a small term program in the kernel parameters; the operator/type switch runs once
 //     per term per 16 rows, the compares themselves are straight-line;
 //   * the filter pass emits the selection bitmap (warp-shuffle assembled words) and one count per tile;
-//     a one-block scan turns the counts into output offsets; the write pass ranks the survivors of a
-//     tile with one packed warp scan (four 8-bit unit counters in one register) and a CTA scan, so
-//     the output is written in ascending position order (the reference emits rows in position order;
-//     bit-exact position lists need order, not atomics) and no CTA ever waits for another;
-//   * survivors are written with one lane per SURVIVOR (a per-warp rank->row list in shared memory):
-//     projection columns that are not predicate columns are only gathered for qualifying rows (late
-//     materialisation: at low selectivity most sectors are never read), stores are coalesced, and the
-//     cost of the output phase is proportional to the selectivity;
+//     independent blocks turn the counts into output offsets (each sums what precedes it itself); the
+//     write pass ranks the survivors of a tile with one packed warp scan (four 8-bit unit counters in
+//     one register) and a CTA scan, so the output is written in ascending position order (the reference
+//     emits rows in position order; bit-exact position lists need order, not atomics) and no CTA ever
+//     waits for another;
+//   * survivors are written with one thread per SURVIVOR (a rank->row list in shared memory):
+//     projection columns are only gathered for qualifying rows (late materialisation), stores are
+//     coalesced, and the cost of the output phase is proportional to the selectivity; groups of 8
+//     tiles with few survivors are written by one CTA so that sparse scans do not pay a CTA's
+//     load -> scan -> gather -> store latency chain per tile;
 //   * COUNT/SUM/MIN/MAX partials are produced per tile and reduced in tile order by a second
 //     tiny kernel, so real-valued sums are reproducible run to run.
 #pragma once
