@@ -99,6 +99,7 @@ struct mbc_ctx {
     cudaStream_t d2h_stream = nullptr;   // results of mbc_scan_host streaming back while later chunks upload
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
     int64_t launches = 0;
+    bool filter_smem_set = false, sort_smem_set = false;   // per-device opt-in to > 48 KB of dynamic shared memory
     int64_t h2d_bytes = 0;            // host -> device bytes moved by mbc_scan_host (copies + rows read in place)
     float last_ms = 0.f;
     bool timing_split = false;

@@ -259,10 +259,9 @@ int32_t radix_sort_pairs(mbc_ctx* ctx, uint32_t* d_keys, uint32_t* d_vals, int64
     MBC_TRY(dev_alloc(ctx, (void**)&tv, (size_t)n * 4, false));
     MBC_TRY(dev_alloc(ctx, (void**)&hist, (size_t)256 * nblocks * 4, false));
     MBC_TRY(dev_alloc(ctx, (void**)&offs, ((size_t)256 * nblocks + 1) * 8, false));
-    static bool configured = false;
-    if (!configured) {
+    if (!ctx->sort_smem_set) {                                    // a function attribute is per device: once per context
         MBC_CUDA(cudaFuncSetAttribute(rsort_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSortChunk * 8));
-        configured = true;
+        ctx->sort_smem_set = true;
     }
     uint32_t *sk = d_keys, *sv = d_vals, *dk = tk, *dv = tv;
     int passes = std::max(1, (key_bits + 7) / 8);

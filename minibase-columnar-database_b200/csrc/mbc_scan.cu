@@ -99,10 +99,9 @@ static int32_t plan_staging(mbc_ctx* ctx, ScanParams* p, size_t* smem_bytes, int
     // ring depth: as deep as ~100 KB of shared memory allows (two CTAs per SM), at least 2
     p->nstages = p->nstaged == 0 ? 2 : std::max(2, std::min(kMaxStages, (int)(200 * 1024 / MBC_FILTER_CTAS / (p->nstaged * kStageColBytes))));
     *smem_bytes = (size_t)p->nstages * p->nstaged * kStageColBytes;
-    static bool configured = false;
-    if (!configured) {
+    if (!ctx->filter_smem_set) {                                  // a function attribute is per device: once per context
         MBC_CUDA(cudaFuncSetAttribute(filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        configured = true;
+        ctx->filter_smem_set = true;
     }
     int blocks_per_sm = 1;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, filter_kernel, kScanThreads, *smem_bytes) != cudaSuccess || blocks_per_sm < 1)
