@@ -5,6 +5,8 @@ from __future__ import annotations
 
 from typing import Optional, Sequence
 
+import numpy as np
+
 from . import _native as N
 from .columnar import Columnarfile
 from .engine import Term, bitmap_join
@@ -231,8 +233,11 @@ class NljQuery:
     """input/NljQuery.java:33-330: `nlj DB OUTER INNER OUTERCONST INNERCONST JOINCONST OUTERACCESS INNERACCESS [targets]
     NUMBUF MEM`.  The reference runs a block nested-loop join over two column scans
     (iterator/ColumnarNestedLoopJoins.java:157-207); here both side constraints are GPU filter scans that leave
-    selection bitmaps and the join is the same K6 as `bmj` (equi path or tiled theta kernel).  Same pair SET as the
-    reference; the pairs come out outer-ascending x inner-ascending, the Java's block order depends on MEM."""
+    selection bitmaps and the join is the same K6 as `bmj` (equi path or tiled theta kernel).  The pair list is then put
+    into the reference's emission order: the qualifying outer rows are taken a block at a time -- (MEM - 1) pages of
+    1024 / outer-tuple-size tuples, :118-121 -- and for every block the inner rows are walked in order, the block's
+    outer rows inside (sort key: outer block, inner position, outer position), so the printed rows match the Java line
+    by line."""
 
     def execute(self, args: Sequence[str], echo: bool = True) -> list[str]:
         if len(args) < 11:
@@ -245,6 +250,12 @@ class NljQuery:
                 raise Exception("BTREE access stays in Java (out of scope for the GPU path)")
         if not (targets.startswith("[") and targets.endswith("]")):
             raise Exception("[TARGETCOLUMNNAMES] format invalid.")
+        try:
+            amt_of_memory = int(args[10])
+        except ValueError:
+            raise Exception("amt_of_memory is not integer.")
+        if amt_of_memory < 2:
+            raise Exception("amt_of_memory is not more than 1.")
         outer, inner = Columnarfile(outer_name), Columnarfile(inner_name)
         osel = self._constraint(outer, ocnf, oacc)
         isel = self._constraint(inner, icnf, iacc)
@@ -270,11 +281,24 @@ class NljQuery:
         res = bitmap_join(outer.table, inner.table, join_terms, proj,
                           N.WANT_POSITIONS | N.WANT_COLUMNS | N.WANT_TUPLES | N.WANT_AGG | N.WANT_HOST, aggs=[(N.AGG_COUNT, 0)],
                           outer_sel=osel, inner_sel=isel)
+        # the outer iterator's tuple (NljQuery.java:84-106,446-470): target columns of the outer file, the join columns,
+        # and -- unless the access is FILESCAN -- the constraint columns of every conjunct after the first (a TreeSet)
+        tcols = {c for side, c in proj if side == N.OPERAND_OUTER} | {t.lhs[1] for t in join_terms}
+        if oacc.upper() != "FILESCAN":
+            for conj in ocnf.split("^")[1:]:
+                tcols |= {outer.colNameToIndex(d[1:-1].split(",")[0].strip()) for d in conj[1:-1].split("|")}
+        sizes, types = outer.getAttrSizes(), outer.getAttributeTypes()
+        tuple_size = (len(tcols) + 2) * 2 + sum(sizes[c] + 2 if types[c].attrType == AttrType.attrString else 4 for c in tcols)
+        block_rows = max(1, (amt_of_memory - 1) * (1024 // tuple_size))
+        po, pi = res.positions(), res.positions2()
+        rank = np.searchsorted(osel.positions(), po)               # rank of the pair's outer row among the qualifying ones
+        order = np.lexsort((po, pi, rank // block_rows))
         lines: list[str] = []
         _emit(lines, ", ".join(names), echo)
         from .heap import Tuple
-        for raw in res.tuples():
-            t = Tuple(bytes(raw))
+        tuples = res.tuples()
+        for k in order:
+            t = Tuple(bytes(tuples[k]))
             t._adopt_header()
             _emit(lines, _fmt(t, out_types), echo)
         count = res.count
@@ -294,7 +318,7 @@ class NljQuery:
             res, scan._result = scan._result, None                 # the selection outlives the scan object
             return res
         from .iterator import flatten_condexpr
-        return cf.table.scan(flatten_condexpr(exprs), want=N.WANT_BITMAP)
+        return cf.table.scan(flatten_condexpr(exprs), want=N.WANT_BITMAP | N.WANT_POSITIONS | N.WANT_HOST)
 
 
 class ColumnarSort:

@@ -278,6 +278,25 @@ def synth_str(seed: int, col: int, nrows: int, width: int, position_base: int = 
 # ---------------------------------------------------------------------------------------------
 # strings <-> fixed-width zero padded byte rows
 # ---------------------------------------------------------------------------------------------
+def nlj_outer_block_rows(outer_coldescs, outer_cols_in_tuple: Sequence[int], amt_of_mem: int) -> int:
+    """Outer tuples per block of iterator/ColumnarNestedLoopJoins.java:118-121: (amt_of_mem - 1) buffer pages of
+    MINIBASE_PAGESIZE / outerItr.getTupleSize() tuples, the tuple holding the columns input/NljQuery.java collects for the
+    outer side (targets, join columns, constraint columns of the conjuncts the scan does not evaluate; a TreeSet)."""
+    cols = sorted(set(outer_cols_in_tuple))
+    size = (len(cols) + 2) * 2 + sum(outer_coldescs[c][1] + 2 if outer_coldescs[c][0] == ATTR_STRING else 4 for c in cols)
+    return (amt_of_mem - 1) * (1024 // size)
+
+
+def nlj_order(outer_qualifying_positions, pair_outer, pair_inner, block_rows: int) -> np.ndarray:
+    """Emission order of ColumnarNestedLoopJoins.get_next (:157-207) as a permutation of the pair list: the qualifying
+    outer rows are taken block_rows at a time (scan order); for every block the whole inner side is walked in order, and
+    for every inner row the block's outer rows in order.  Sort key = (outer block, inner position, outer position)."""
+    oq = np.asarray(outer_qualifying_positions, dtype=np.int64)
+    po, pi = np.asarray(pair_outer, dtype=np.int64), np.asarray(pair_inner, dtype=np.int64)
+    rank = np.searchsorted(oq, po)
+    return np.lexsort((po, pi, rank // max(int(block_rows), 1)))
+
+
 def sort(coldescs, columns, key_cols: Sequence[int], descending: bool = False, deleted_positions=()) -> np.ndarray:
     """input/ColumnarSort.java:163-205 comparator, restated: the live positions ordered by the key columns (first key most
     significant; ints numerically, strings by String.compareTo = byte order of the zero-padded BMP text), all keys

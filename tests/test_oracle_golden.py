@@ -128,29 +128,39 @@ def test_bmj(golden, minidata, oracle):
     assert n >= 8
 
 
-def test_nlj_counts_and_rows(golden, minidata, oracle):
-    """G5, G8: the nested-loop join runs (any access path) give the same pair multiset as the bitmap join."""
+def _nlj_outer_tuple_cols(names, cmd):
+    """input/NljQuery.java:84-106,446-470: the columns of the outer iterator's tuple."""
+    parts = cmd.split()
+    outer, ocnf, jcnf, oacc, targets = parts[2], parts[4], parts[6], parts[7], parts[9]
+    cols = {names.index(t.split(".")[1]) for t in targets[1:-1].split(",") if t.split(".")[0] == outer}
+    if oacc.upper() != "FILESCAN":                                  # findConsTargetCols: conjuncts after the first one
+        for conj in ocnf.split("^")[1:]:
+            cols |= {names.index(d[1:-1].split(",")[0].strip()) for d in conj[1:-1].split("|")}
+    for conj in jcnf.split("^"):                                    # findJoinTargetCols
+        cols |= {names.index(d[1:-1].split(",")[0].strip()) for d in conj[1:-1].split("|")}
+    return sorted(cols), int(parts[11])
+
+
+def test_nlj_rows_in_the_reference_order(golden, minidata, oracle):
+    """G5, G8: every `nlj` run of the transcript (any access path) -- pair count and the printed rows IN ORDER.  The
+    order is ColumnarNestedLoopJoins' block nested loop (outer block, inner row, outer row), restated by
+    oracle.nlj_order with the block size the Java derives from MEM and the outer tuple size."""
     import hashlib
+    names, descs, cols = minidata
     n = 0
-    seen = set()
     for e in golden:
-        if e["kind"] != "nlj" or e.get("failed"):
+        if e["kind"] != "nlj" or e.get("failed") or "ff1." in e["cmd"]:
             continue
-        key = re.sub(r"(FILESCAN|COLUMNSCAN|BTREE|BITMAP) (FILESCAN|COLUMNSCAN|BTREE|BITMAP)", "X X", e["cmd"])
-        key = re.sub(r"\d+ \d+$", "", key)
-        if key in seen or "ff1." in e["cmd"]:
-            continue
-        seen.add(key)
-        _, _, res, rows = _run_join(oracle, minidata, e["cmd"], "nlj")
+        opos, _, res, rows = _run_join(oracle, minidata, e["cmd"], "nlj")
         assert res["count"] == e["count"], e["cmd"]
+        tcols, mem = _nlj_outer_tuple_cols(names, e["cmd"])
+        order = oracle.nlj_order(opos, res["outer_positions"], res["inner_positions"], oracle.nlj_outer_block_rows(descs, tcols, mem))
+        rows = [rows[k] for k in order]
         if "rows" in e:
-            assert sorted(rows) == sorted(e["rows"]), e["cmd"]
-        else:
-            assert e["count"] == 2284 and len(rows) == 2284
-            # block nested loop emits the same pairs in another order: compare as a multiset through sorting
-            assert hashlib.sha256("\n".join(sorted(rows)).encode()).hexdigest() == e["rows_sorted_sha256"], e["cmd"]
+            assert rows == e["rows"], e["cmd"]
+        assert hashlib.sha256("\n".join(rows).encode()).hexdigest() == e["rows_sha256"], e["cmd"]
         n += 1
-    assert n >= 8
+    assert n >= 40
 
 
 def test_duplicate_constraint_cache_is_observable(minidata, oracle):
