@@ -239,9 +239,13 @@ class NljQuery:
     outer rows inside (sort key: outer block, inner position, outer position), so the printed rows match the Java line
     by line."""
 
-    def execute(self, args: Sequence[str], echo: bool = True) -> list[str]:
+    def execute(self, args: Sequence[str], echo: bool = True, via_iterators: bool = False) -> list[str]:
+        """via_iterators=True builds the two input scans and a ColumnarNestedLoopJoins over them exactly like
+        NljQuery.java:139-176 (FILESCAN / COLUMNSCAN access); the default goes to the join kernels directly."""
         if len(args) < 11:
             raise Exception("Invalid number of attributes.")
+        if via_iterators:
+            return self._execute_via_iterators(args, echo)
         outer_name, inner_name, ocnf, icnf, jcnf, oacc, iacc, targets = args[1:9]
         for acc in (oacc, iacc):
             if acc.upper() not in ("FILESCAN", "COLUMNSCAN", "BTREE", "BITMAP"):
@@ -303,6 +307,98 @@ class NljQuery:
             _emit(lines, _fmt(t, out_types), echo)
         count = res.count
         res.close(); osel.close(); isel.close()
+        _footer(lines, count, echo)
+        self.resultCount = count
+        return lines
+
+    def _execute_via_iterators(self, args: Sequence[str], echo: bool) -> list[str]:
+        from .iterator import ColumnarColumnsScan, ColumnarNestedLoopJoins
+        outer_name, inner_name, ocnf, icnf, jcnf, oacc, iacc, targets = args[1:9]
+        amt_of_memory = int(args[10])
+        files = {"o": Columnarfile(outer_name), "i": Columnarfile(inner_name)}
+        names = [t.strip() for t in targets[1:-1].split(",")]
+        tcols = {"o": set(), "i": set()}                            # the TreeSets of NljQuery.java:84-106
+        for n in names:
+            rel, col = n.split(".")
+            side = "o" if rel == outer_name else "i"
+            tcols[side].add(files[side].colNameToIndex(col))
+        for side, cnf, acc in (("o", ocnf, oacc), ("i", icnf, iacc)):   # findConsTargetCols (:446-470)
+            if acc.upper() not in ("FILESCAN", "COLUMNSCAN"):
+                raise Exception("via_iterators serves FILESCAN and COLUMNSCAN access")
+            if acc.upper() != "FILESCAN":
+                for conj in cnf.split("^")[1:]:
+                    tcols[side] |= {files[side].colNameToIndex(d[1:-1].split(",")[0].strip()) for d in conj[1:-1].split("|")}
+        join = []
+        for ci, conj in enumerate(jcnf.split("^")):                 # findJoinTargetCols + buildCNFJoinCondExpr
+            for dis in conj[1:-1].split("|"):
+                a, op, b = [p.strip() for p in dis[1:-1].strip().split(",")]
+                oc, ic = files["o"].colNameToIndex(a), files["i"].colNameToIndex(b)
+                tcols["o"].add(oc); tcols["i"].add(ic)
+                join.append((ci, op, oc, ic))
+        order = {s: sorted(tcols[s]) for s in "oi"}
+        field = {s: {c: k + 1 for k, c in enumerate(order[s])} for s in "oi"}      # findFieldOffset
+
+        def iterator_of(side, cnf, acc):                            # getIterator (:259-300)
+            cf = files[side]
+            exprs, _, _, _ = build_cnf_condexpr(cnf, cf)
+            proj = [FldSpec(RelSpec(RelSpec.outer), c + 1) for c in order[side]]
+            if acc.upper() == "FILESCAN":
+                return ColumnarFileScan(cf._fileName, cf.getAttributeTypes(), cf.getStringSizes(), cf.getFieldCount(), len(proj), proj, exprs)
+            used = sorted({t.operand1.symbol.offset - 1 for e in exprs if e is not None for t in _chain(e)})
+            for e in exprs:
+                if e is not None:
+                    for t in _chain(e):
+                        t.operand1.symbol = FldSpec(RelSpec(RelSpec.outer), used.index(t.operand1.symbol.offset - 1) + 1)
+            return ColumnarColumnsScan(cf, used, len(proj), order[side], proj, exprs)
+
+        def _chain(e):
+            while e is not None:
+                yield e
+                e = e.next
+
+        outer_it, inner_it = iterator_of("o", ocnf, oacc), iterator_of("i", icnf, iacc)
+        join_filter, by_conj = [], {}
+        for ci, op, oc, ic in join:
+            e = CondExpr()
+            e.op = AttrOperator.findOperator(op)
+            e.type1 = e.type2 = AttrType(AttrType.attrSymbol)
+            e.operand1.symbol = FldSpec(RelSpec(RelSpec.outer), field["o"][oc])
+            e.operand2.symbol = FldSpec(RelSpec(RelSpec.innerRel), field["i"][ic])
+            if ci in by_conj:
+                tail = by_conj[ci]
+                while tail.next is not None:
+                    tail = tail.next
+                tail.next = e
+            else:
+                by_conj[ci] = e
+                join_filter.append(e)
+        join_filter.append(None)
+        proj_list, out_types = [], []
+        for n in names:
+            rel, col = n.split(".")
+            side = "o" if rel == outer_name else "i"
+            c = files[side].colNameToIndex(col)
+            proj_list.append(FldSpec(RelSpec(RelSpec.outer if side == "o" else RelSpec.innerRel), field[side][c]))
+            out_types.append(files[side].getAttributeTypes()[c].attrType)
+
+        def tuple_types(side):
+            cf = files[side]
+            types = [cf.getAttributeTypes()[c] for c in order[side]]
+            return types, [cf.getAttrSizes()[c] for c in order[side] if cf.getAttributeTypes()[c].attrType == AttrType.attrString]
+
+        (in1, s1), (in2, s2) = tuple_types("o"), tuple_types("i")
+        nlj = ColumnarNestedLoopJoins(files["o"], files["i"], in1, len(in1), s1, in2, len(in2), s2, outer_it, inner_it,
+                                      None, None, join_filter, proj_list, len(proj_list), amt_of_memory)
+        lines: list[str] = []
+        _emit(lines, ", ".join(names), echo)
+        count = 0
+        while True:
+            t = nlj.get_next()
+            if t is None:
+                break
+            _emit(lines, _fmt(t, out_types), echo)
+            count += 1
+        nlj.close()
         _footer(lines, count, echo)
         self.resultCount = count
         return lines

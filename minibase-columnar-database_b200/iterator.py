@@ -52,6 +52,10 @@ class IndexException(ChainException):
     pass
 
 
+class NestedLoopException(ChainException):
+    pass
+
+
 # ---- predicate / projection structures -----------------------------------------------------------------
 class RelSpec:
     """iterator/RelSpec.java:3-16"""
@@ -261,6 +265,14 @@ class ColumnarFileScan(Iterator):
         pos = self._open().next_position()
         return None if pos is None else TID(self.in1_len, pos)
 
+    # what ColumnarNestedLoopJoins needs from an input iterator: its predicate over TABLE columns and the table column
+    # behind every field of its output tuple
+    def _table_terms(self) -> list:
+        return flatten_condexpr(self.OutputFilter)
+
+    def _tuple_columns(self) -> list:
+        return [fs.offset - 1 for fs in self.perm_mat]
+
     def close(self) -> None:
         if not self.closeFlag:
             if self._result is not None:
@@ -328,18 +340,28 @@ class _ColumnsScan(Iterator):
     def show(self):
         return self.perm_mat
 
+    def _table_terms(self) -> list:
+        terms = []
+        for t in flatten_condexpr(self.OutputFilter):           # field k of the predicate tuple -> table column colNos[k]
+            ops = []
+            for kind, val in (t.lhs, t.rhs):
+                if kind == "col":
+                    if not 0 <= val < len(self.colNos):
+                        raise PredEvalException(None, "FieldNumberOutOfBoundException is caught by PredEval.java")
+                    val = self.colNos[val]
+                ops.append((kind, val))
+            terms.append(Term(t.op, ops[0], ops[1], t.conj))
+        return terms
+
+    def _tuple_columns(self) -> list:
+        return list(self.outIndexes)
+
+    def getTupleSize(self) -> int:
+        return self.Jtuple.size()
+
     def _open(self) -> _ResultCursor:
         if self._cursor is None:
-            terms = []
-            for t in flatten_condexpr(self.OutputFilter):       # field k of the predicate tuple -> table column colNos[k]
-                ops = []
-                for kind, val in (t.lhs, t.rhs):
-                    if kind == "col":
-                        if not 0 <= val < len(self.colNos):
-                            raise PredEvalException(None, "FieldNumberOutOfBoundException is caught by PredEval.java")
-                        val = self.colNos[val]
-                    ops.append((kind, val))
-                terms.append(Term(t.op, ops[0], ops[1], t.conj))
+            terms = self._table_terms()
             try:
                 self._result = self.f.table.scan(terms, proj=self.outIndexes, want=N.WANT_POSITIONS | N.WANT_COLUMNS | N.WANT_HOST)
             except N.MbcError as e:
@@ -388,3 +410,112 @@ class ColumnarColumnsScan(_ColumnsScan):
     def __init__(self, columnarfile, colNos: Sequence[int], *rest):
         super().__init__(columnarfile, colNos, rest,
                          "ColumnarColumnsScan(columnarfile, colNos, [n_out_flds, out_indexes, proj_list,] outFilter)")
+
+
+class ColumnarNestedLoopJoins(Iterator):
+    """iterator/ColumnarNestedLoopJoins.java:45-231.
+
+    ColumnarNestedLoopJoins(outerColumnarFile, innerColumnarFile, in1, in1_len, t1_str_sizes, in2, in2_len, t2_str_sizes,
+                            outerItr, innerItr, outFilter, rightFilter, joinFilter, proj_list, n_out_flds, amt_of_mem)
+
+    in1 / in2 describe the tuples the two input iterators produce; outFilter / rightFilter are evaluated on those tuples
+    (outer / inner), joinFilter on the pair (operand1 = outer field, operand2 = innerRel field), proj_list picks the
+    output fields from either tuple.  The input iterators must be this package's scans (ColumnarFileScan,
+    ColumnarColumnScan, ColumnarColumnsScan): their predicates and the pending filters are folded into one GPU filter
+    scan per side, the join runs as K6, and get_next() hands the joined tuples out in the reference's block order --
+    outer blocks of (amt_of_mem - 1) * (1024 / outerItr.getTupleSize()) qualifying tuples, for each block every inner
+    tuple in order, the block's outer tuples inside (:157-207)."""
+
+    def __init__(self, outerColumnarFile, innerColumnarFile, in1, in1_len, t1_str_sizes, in2, in2_len, t2_str_sizes,
+                 outerItr, innerItr, outFilter, rightFilter, joinFilter, proj_list, n_out_flds, amt_of_mem):
+        super().__init__()
+        for it in (outerItr, innerItr):
+            if not hasattr(it, "_table_terms"):
+                raise NestedLoopException(None, "input iterators must be ColumnarFileScan / ColumnarColumn(s)Scan of this package")
+        self.outerColumnarFile, self.innerColumnarFile = outerColumnarFile, innerColumnarFile
+        self.outerItr, self.innerItr = outerItr, innerItr
+        self.OuterFilter, self.RightFilter, self.JoinFilter = outFilter, rightFilter, joinFilter
+        self._in1, self._in2 = list(in1)[:in1_len], list(in2)[:in2_len]
+        self.perm_mat, self.nOutFlds = list(proj_list), n_out_flds
+        self.n_buf_pgs = int(amt_of_mem)
+        # two-relation setup_op_tuple (iterator/TupleUtils.java:343-409)
+        def sizes_of(types, str_sizes):
+            out, k = [], 0
+            for t in types:
+                if t.attrType == AttrType.attrString:
+                    out.append(str_sizes[k]); k += 1
+                else:
+                    out.append(0)
+            return out
+        s1, s2 = sizes_of(self._in1, t1_str_sizes), sizes_of(self._in2, t2_str_sizes)
+        self.Jtypes, jsizes = [], []
+        for fs in self.perm_mat[:n_out_flds]:
+            types, sizes = (self._in1, s1) if fs.relation.key == RelSpec.outer else (self._in2, s2)
+            self.Jtypes.append(AttrType(types[fs.offset - 1].attrType))
+            if types[fs.offset - 1].attrType == AttrType.attrString:
+                jsizes.append(sizes[fs.offset - 1])
+        self.Jtuple = Tuple()
+        try:
+            self.Jtuple.setHdr(n_out_flds, self.Jtypes, jsizes)
+        except Exception as e:
+            raise NestedLoopException(e, "TupleUtilsException is caught by ColumnarNestedLoopsJoins.java")
+        self._rows = None
+        self._i = 0
+
+    @staticmethod
+    def _side_terms(it, pending) -> list:
+        """The iterator's own predicate AND the pending filter (fields of the iterator's tuple), over table columns."""
+        terms = list(it._table_terms())
+        base = 1 + max([t.conj for t in terms], default=-1)
+        cols = it._tuple_columns()
+        for t in flatten_condexpr(pending):
+            ops = [((k, cols[v]) if k == "col" else (k, v)) for k, v in (t.lhs, t.rhs)]
+            terms.append(Term(t.op, ops[0], ops[1], base + t.conj))
+        return terms
+
+    def _run(self) -> None:
+        from .engine import bitmap_join
+        want = N.WANT_BITMAP | N.WANT_POSITIONS | N.WANT_HOST
+        try:
+            osel = self.outerColumnarFile.table.scan(self._side_terms(self.outerItr, self.OuterFilter), want=want)
+            isel = self.innerColumnarFile.table.scan(self._side_terms(self.innerItr, self.RightFilter), want=want)
+            ocols, icols = self.outerItr._tuple_columns(), self.innerItr._tuple_columns()
+            jterms = []
+            for t in flatten_condexpr(self.JoinFilter):           # operand1: outer tuple field, operand2: innerRel field
+                jterms.append(Term(t.op, ("col", ocols[t.lhs[1]]), ("icol", icols[t.rhs[1]]), t.conj))
+            proj = [(N.OPERAND_OUTER, ocols[fs.offset - 1]) if fs.relation.key == RelSpec.outer else (N.OPERAND_INNER, icols[fs.offset - 1])
+                    for fs in self.perm_mat[:self.nOutFlds]]
+            res = bitmap_join(self.outerColumnarFile.table, self.innerColumnarFile.table, jterms, proj,
+                              N.WANT_POSITIONS | N.WANT_COLUMNS | N.WANT_HOST, outer_sel=osel, inner_sel=isel)
+        except N.MbcError as e:
+            raise NestedLoopException(e, "Exceeption is caught by ColumnarNestedLoopsJoins.java")
+        block_rows = max(1, (self.n_buf_pgs - 1) * (1024 // max(self.outerItr.getTupleSize(), 1)))
+        po, pi = res.positions(), res.positions2()
+        rank = np.searchsorted(osel.positions(), po)
+        order = np.lexsort((po, pi, rank // block_rows))
+        self._cols = [np.asarray(res.column(i))[order] for i in range(self.nOutFlds)]
+        self._rows = len(order)
+        res.close(); osel.close(); isel.close()
+
+    def get_next(self) -> Optional[Tuple]:
+        if self._rows is None:
+            self._run()
+        if self._i >= self._rows:
+            return None
+        k = self._i
+        self._i += 1
+        for f, t in enumerate(self.Jtypes):                     # Projection.Join (:40-101) into the reused Jtuple
+            if t.attrType == AttrType.attrInteger:
+                self.Jtuple.setIntFld(f + 1, int(self._cols[f][k]))
+            elif t.attrType == AttrType.attrReal:
+                self.Jtuple.setFloFld(f + 1, float(self._cols[f][k]))
+            else:
+                self.Jtuple.setStrFld(f + 1, bytes(self._cols[f][k]).rstrip(b"\0").decode("utf-8"))
+        return self.Jtuple
+
+    def close(self) -> None:
+        if not self.closeFlag:
+            self.innerItr.close()
+            self.outerItr.close()
+            self._cols, self._rows = None, 0
+            self.closeFlag = True
