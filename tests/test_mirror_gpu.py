@@ -264,6 +264,9 @@ def test_nlj_golden(db, golden):
         if "rows" in e and isinstance(e["rows"], list):
             assert rows == e["rows"], e["cmd"]                                  # line by line, in the Java's order
         assert hashlib.sha256("\n".join(rows).encode()).hexdigest() == e["rows_sha256"], e["cmd"]
+        if "BITMAP" not in e["cmd"]:
+            # the same through two scan iterators and iterator.ColumnarNestedLoopJoins, built like NljQuery.java does
+            assert NljQuery().execute(e["cmd"].split()[1:], echo=False, via_iterators=True) == lines, e["cmd"]
         n += 1
     assert n >= 8
 
