@@ -421,7 +421,8 @@ class ColumnarSort:
     """input/ColumnarSort.java:73-400: `sort DB CF [sort columns] [projected columns] ASC|DSC NUMBUF SORTBUF`
     (SURVEY.md 8f rank 4).  The reference runs an external merge sort over (keys, position) records; here the row ids
     are radix-sorted on the GPU (mbc_sort) and the projected fields gathered in that order.  Same printed lines
-    `<projected values> :<position>`; rows with equal keys come out in ascending position."""
+    `<projected values> :<position>`, equal keys in the order the Java's merge structure leaves them (replayed on the
+    host for results up to REFERENCE_TIE_ORDER_MAX_ROWS rows; ascending position beyond that)."""
 
     def execute(self, args: Sequence[str], echo: bool = True) -> list[str]:
         if len(args) < 7:
@@ -447,12 +448,16 @@ class ColumnarSort:
         keys = [cf.colNameToIndex(n.strip()) for n in sort_cols[1:-1].split(",")]
         proj = [cf.colNameToIndex(n.strip()) for n in proj_cols[1:-1].split(",")]
         types = [cf.getAttributeTypes()[c].attrType for c in proj]
-        res = cf.table.sort(keys, descending=(order == "DSC"), proj=proj,
+        res = cf.table.sort(keys, descending=(order == "DSC"), proj=keys + proj,
                             want=N.WANT_POSITIONS | N.WANT_COLUMNS | N.WANT_HOST)
         _emit(lines, "SORTED COLUMNS", echo)
         pos = res.positions()
-        cols = [res.column(i) for i in range(len(proj))]
-        for k in range(res.count):                                  # printRecordsByPages: values, blank separated, then :position
+        key_cols = [np.asarray(res.column(i)) for i in range(len(keys))]
+        cols = [res.column(len(keys) + i) for i in range(len(proj))]
+        emit = range(res.count)
+        if 0 < res.count <= self.REFERENCE_TIE_ORDER_MAX_ROWS:
+            emit = self._reference_order(cf, keys, key_cols, pos, sortbuf)
+        for k in emit:                                              # printRecordsByPages: values, blank separated, then :position
             vals = [str(int(cols[f][k])) if t == AttrType.attrInteger else repr(float(cols[f][k])) if t == AttrType.attrReal
                     else bytes(cols[f][k]).rstrip(b"\0").decode("utf-8") for f, t in enumerate(types)]
             _emit(lines, " ".join(vals) + " :" + str(int(pos[k])), echo)
@@ -460,6 +465,58 @@ class ColumnarSort:
         self.resultCount = res.count
         res.close()
         return lines
+
+    # The GPU sort leaves equal keys in ascending position.  The Java's external merge sort leaves them in an order that
+    # follows from its page and run structure (ColumnarSort.java:206-352); for tables up to this many rows the mirror
+    # replays that structure on the host over the key groups of the GPU result, so the lines come out exactly as the
+    # reference prints them.  Larger results keep the GPU order (a valid sort either way).
+    REFERENCE_TIE_ORDER_MAX_ROWS = 200_000
+
+    @staticmethod
+    def _reference_order(cf: Columnarfile, keys: Sequence[int], key_cols, pos, sort_buffers: int) -> list:
+        """Indices into the GPU-sorted result, in the order the reference emits the rows."""
+        n = len(pos)
+        group = np.zeros(n, dtype=np.int64)                        # key rank of every row of the sorted result
+        if n > 1:
+            change = np.zeros(n - 1, dtype=bool)
+            for kc in key_cols:
+                a = np.asarray(kc).reshape(n, -1)
+                change |= (a[1:] != a[:-1]).any(axis=1)
+            group[1:] = np.cumsum(change)
+        by_pos = np.argsort(pos, kind="stable")                    # record r of the sort heap file = r-th live row by position
+        sizes, types = cf.getAttrSizes(), cf.getAttributeTypes()
+        rec = sum(sizes[c] + 2 if types[c].attrType == AttrType.attrString else 4 for c in keys) + 4
+        records = _external_sort_replay(group[by_pos].tolist(), 1004 // (rec + 4), sort_buffers - 1)
+        return [int(by_pos[r]) for r in records]
+
+
+def _external_sort_replay(key: list, per_page: int, nbuf: int) -> list:
+    """The pass structure of input/ColumnarSort.java:206-352 on record numbers 0..n-1 with integer keys: P records per
+    heap page, pass 0 reads B pages round-robin and sorts them stably, every later pass merges B runs of B^i pages taking
+    the smallest head, the lowest run among equal heads.  Returns the record numbers in emission order."""
+    import heapq
+    import math
+    n = len(key)
+    npages = (n + per_page - 1) // per_page
+    passes = int(math.ceil(math.log(npages) / math.log(nbuf))) if npages > 1 and nbuf > 1 else 0
+    cur = list(range(n))
+    for i in range(passes):
+        pages = [cur[s:s + per_page] for s in range(0, n, per_page)]
+        run = nbuf ** i
+        runs = [pages[s:s + run] for s in range(0, npages, run)]
+        out = []
+        for k in range(0, len(runs), nbuf):
+            grp = runs[k:k + nbuf]
+            if i == 0:
+                heads = [r[0] for r in grp]
+                lst = [h[s] for s in range(max(len(h) for h in heads)) for h in heads if s < len(h)]
+                lst.sort(key=key.__getitem__)                      # Collections.sort: stable
+                out += lst
+            else:
+                seqs = [[(key[r], j, q, r) for q, r in enumerate(x for pg in rn for x in pg)] for j, rn in enumerate(grp)]
+                out += [t[3] for t in heapq.merge(*seqs)]
+        cur = out
+    return cur
 
 
 class DeleteQuery:

@@ -297,6 +297,58 @@ def nlj_order(outer_qualifying_positions, pair_outer, pair_inner, block_rows: in
     return np.lexsort((po, pi, rank // max(int(block_rows), 1)))
 
 
+def external_sort_order(coldescs, columns, key_cols: Sequence[int], descending: bool, sort_buffers: int) -> list:
+    """input/ColumnarSort.java:206-352 restated on row ids: the ORDER (ties included) in which the reference's external
+    merge sort emits the rows.  (key..., position) records of `rec` bytes go P = 1004 // (rec + 4) to a heap page
+    (:206-210, heap/HFPage.java); B = sort_buffers - 1 input buffers; ceil(log(pages) / log(B)) passes (:214).  Pass 0
+    takes the pages B at a time, reads them round-robin (first record of every page, second record of every page, ...,
+    :293-309) and sorts that list stably (Collections.sort, :310); every later pass merges B runs of B^i pages, always
+    taking the smallest head and, among equal heads, the one of the lowest run (:318-346,664-680: a stable sort of the
+    (run, head) entries).  Every pass appends to a fresh heap file, so a run starts on a page boundary."""
+    import math
+    n = nrows_of(coldescs, columns)
+    ranks = []
+    for c in key_cols:
+        t, w = coldescs[c]
+        col = np.asarray(columns[c])
+        keys = np.ascontiguousarray(col.reshape(n, -1)[:, :w]).view(f"S{w}").reshape(n) if t == ATTR_STRING else col.reshape(n)
+        _, inv = np.unique(keys, return_inverse=True)
+        ranks.append(-inv if descending else inv)
+    key = [tuple(int(r[i]) for r in ranks) for i in range(n)]
+    rec = sum(coldescs[c][1] + 2 if coldescs[c][0] == ATTR_STRING else 4 for c in key_cols) + 4
+    per_page = 1004 // (rec + 4)
+    nbuf = sort_buffers - 1
+    npages = (n + per_page - 1) // per_page
+    passes = int(math.ceil(math.log(npages) / math.log(nbuf))) if npages > 1 else 0
+    cur = list(range(n))
+    for i in range(passes):
+        pages = [cur[s:s + per_page] for s in range(0, n, per_page)]
+        run = nbuf ** i
+        runs = [pages[s:s + run] for s in range(0, npages, run)]
+        out = []
+        for k in range(0, len(runs), nbuf):
+            group = runs[k:k + nbuf]
+            if i == 0:
+                heads = [r[0] for r in group]
+                lst = [h[s] for s in range(max(len(h) for h in heads)) for h in heads if s < len(h)]
+                lst.sort(key=lambda r: key[r])
+                out += lst
+            else:
+                seqs = [[r for p in rn for r in p] for rn in group]
+                ptr = [0] * len(seqs)
+                while True:
+                    best = -1
+                    for j, sq in enumerate(seqs):
+                        if ptr[j] < len(sq) and (best < 0 or key[sq[ptr[j]]] < key[seqs[best][ptr[best]]]):
+                            best = j
+                    if best < 0:
+                        break
+                    out.append(seqs[best][ptr[best]])
+                    ptr[best] += 1
+        cur = out
+    return cur
+
+
 def sort(coldescs, columns, key_cols: Sequence[int], descending: bool = False, deleted_positions=()) -> np.ndarray:
     """input/ColumnarSort.java:163-205 comparator, restated: the live positions ordered by the key columns (first key most
     significant; ints numerically, strings by String.compareTo = byte order of the zero-padded BMP text), all keys

@@ -191,25 +191,30 @@ def test_stale_padding_mode_only_changes_padding(minidata, oracle):
         assert oracle.decode_tuple(bytes(a), descs) == oracle.decode_tuple(bytes(b), descs)
 
 
-def _sort_lines(oracle, minidata, cmd):
+def _sort_lines(oracle, minidata, cmd, order):
     names, descs, cols = minidata
-    parts = cmd.split()
-    keys = [names.index(x) for x in parts[3][1:-1].split(",")]
-    proj = [names.index(x) for x in parts[4][1:-1].split(",")]
-    order = oracle.sort(descs, cols, keys, descending=(parts[5] == "DSC"))
+    proj = [names.index(x) for x in cmd.split()[4][1:-1].split(",")]
     strs = {c: oracle.unpack_strings(cols[c]) for c in proj if descs[c][0] == 0}
-    lines = [" ".join(strs[c][p] if c in strs else str(int(cols[c][p])) for c in proj) + " :" + str(int(p)) for p in order]
-    return lines, len(keys), proj[:len(keys)] == keys
+    return [" ".join(strs[c][p] if c in strs else str(int(cols[c][p])) for c in proj) + " :" + str(int(p)) for p in order]
 
 
 def test_sort_golden(golden, minidata, oracle):
-    """`sort db cf [keys] [projection] ASC|DSC ...` (phase3_output:24-3156): six runs, one and four key columns."""
+    """`sort db cf [keys] [projection] ASC|DSC NUMBUF SORTBUF` (phase3_output:24-3156): six runs, one and four key columns,
+    2 / 5 / 14 merge buffers.  oracle.external_sort_order restates the reference's external merge sort and reproduces the
+    printed rows LINE BY LINE, order of equal keys included; oracle.sort (ties by position, what the GPU produces) gives
+    the same key sequence and row multiset."""
+    names, descs, cols = minidata
     n = 0
     for e in golden:
         if e["kind"] != "sort" or e.get("failed"):
             continue
-        lines, nkeys, lead = _sort_lines(oracle, minidata, e["cmd"])
-        assert e["count"] == len(lines) == 500
-        check_sorted_like_golden(lines, e["rows"], nkeys, lead)
+        parts = e["cmd"].split()
+        keys = [names.index(x) for x in parts[3][1:-1].split(",")]
+        desc = parts[5] == "DSC"
+        exact = _sort_lines(oracle, minidata, e["cmd"], oracle.external_sort_order(descs, cols, keys, desc, int(parts[7])))
+        assert e["count"] == len(exact) == 500 and exact == e["rows"], e["cmd"]
+        stable = _sort_lines(oracle, minidata, e["cmd"], oracle.sort(descs, cols, keys, descending=desc))
+        lead = parts[4][1:-1].split(",")[:len(keys)] == parts[3][1:-1].split(",")
+        check_sorted_like_golden(stable, e["rows"], len(keys), lead)
         n += 1
     assert n == 6
