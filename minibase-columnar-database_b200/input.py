@@ -113,7 +113,7 @@ class Query:
         _emit(lines, ", ".join(names), echo)
         count = 0
         if access.upper() == "BITMAP":                            # Query.executeBitmapScan (:248-297)
-            if not cf.bitmapIndexExists(cols[0] if False else cf.colNameToIndex(parts[0].strip())):
+            if not cf.bitmapIndexExists(cf.colNameToIndex(parts[0].strip())):
                 raise Exception("Bitmap index does not exist on column " + parts[0])
             it = ColumnarIndexScan(cf, fnums, itypes, inames, cf.getAttributeTypes(), cf.getStringSizes(), cf.getFieldCount(),
                                    len(cols), cols, proj, exprs, False)
