@@ -74,6 +74,61 @@ def _fmt(tuple_, types: Sequence[int]) -> str:
     return ", ".join(vals)
 
 
+def parse_datafile(path: str, numcolumns: int):
+    """The data-file format of input/BatchInsert.java:60-103: a header row `name:int` / `name:char(N)` separated by tabs,
+    then one row per record.  Returns (names, [(attrType, size)], column arrays in the mbc_table_load_column layout)."""
+    with open(path, "r", encoding="utf-8") as f:
+        headers = f.readline().rstrip("\r\n").split("\t")
+        if len(headers) != numcolumns or numcolumns == 0:        # (the Java indexes past the header array when NUMCOLUMNS is larger)
+            raise Exception("Number of columns specified does not match the number of columns in data file")
+        names, descs = [], []
+        for h in headers[:numcolumns]:
+            name, typ = h.split(":")
+            names.append(name)
+            if typ == "int":
+                descs.append((AttrType.attrInteger, 4))
+            elif typ.startswith("char"):
+                descs.append((AttrType.attrString, int(typ[len("char("):-1])))
+            else:
+                raise Exception("column attr type is not supported.")
+        rows = [ln.rstrip("\r\n").split("\t") for ln in f if ln.strip("\r\n")]
+    cols = []
+    for c, (t, w) in enumerate(descs):
+        if t == AttrType.attrInteger:
+            cols.append(np.array([int(r[c]) for r in rows], dtype=np.int32))
+        else:
+            a = np.zeros((len(rows), w), dtype=np.uint8)
+            for i, r in enumerate(rows):
+                b = r[c].encode("utf-8")
+                if len(r[c]) > w or len(b) > w:
+                    raise Exception("column value exceeds size limit")
+                a[i, :len(b)] = np.frombuffer(b, dtype=np.uint8)
+            cols.append(a)
+    return names, descs, cols
+
+
+class BatchInsert:
+    """input/BatchInsert.java:21-140: `batchinsert DATAFILE DB CF NUMCOLUMNS`.  The data file is parsed on the host and
+    the columns are loaded into a GPU-resident Columnarfile in one step (the reference inserts row by row into heap
+    files; writing those pages stays in Java).  Together with `query ... FILESCAN` this is BASELINE config C1."""
+
+    def insert(self, args: Sequence[str], echo: bool = True) -> list[str]:
+        if len(args) < 4:
+            raise Exception("Invalid number of attributes.")
+        datafile, cfname = args[0], args[2]
+        try:
+            numcolumns = int(args[3])
+        except ValueError:
+            raise Exception("NUMCOULMNS is not integer.")
+        names, descs, cols = parse_datafile(datafile, numcolumns)
+        cf = Columnarfile(cfname, numcolumns, [AttrType(t) for t, _ in descs], [w for _, w in descs], names)
+        cf.load_columns(cols)
+        lines: list[str] = []
+        _emit(lines, "Record count: " + str(cf.getTupleCnt()), echo)
+        self.recordCount = cf.getTupleCnt()
+        return lines
+
+
 class Index:
     """input/Index.java:16-66: `index DB CF COL bitmap`"""
 

@@ -12,7 +12,7 @@ from mbcol import _native as N
 from mbcol.columnar import Columnarfile
 from mbcol.global_ import AttrOperator, AttrType, IndexType, IntegerValue, StringValue, SystemDefs, TID
 from mbcol.index import ColumnarIndexScan, ColumnIndexScan
-from mbcol.input import BitMapQuery, DeleteQuery, Index, MultiIndexQuery, NljQuery, Query, build_cnf_condexpr
+from mbcol.input import BatchInsert, BitMapQuery, DeleteQuery, Index, MultiIndexQuery, NljQuery, Query, build_cnf_condexpr
 from mbcol.iterator import ColumnarColumnScan, ColumnarColumnsScan, ColumnarFileScan, CondExpr, FldSpec, RelSpec
 
 pytestmark = pytest.mark.gpu
@@ -352,3 +352,18 @@ def test_delete_query_marks_rows_for_every_later_scan(db, oracle, minidata):
     with pytest.raises(Exception, match="stays in Java"):
         DeleteQuery().execute(["db", "delq", "{C,=,1}", "100", "FILESCAN", "pd"], echo=False)
     cf.close()
+
+
+def test_batchinsert_then_query_is_config_c1(db, golden):
+    """BASELINE config C1 end to end through the drivers: `batchinsert minidata.txt db cfb 4` (G1: 500 records), then the
+    same single-column FILESCAN queries as on the table ingested from the reference-format DB image."""
+    bi = BatchInsert()
+    lines = bi.insert([os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "minidata.tsv"), "db", "cfb", "4"], echo=False)
+    rc = [e["record_count"] for e in golden if e["kind"] == "batchinsert" and "record_count" in e]
+    assert lines == ["Record count: 500"] and bi.recordCount == 500 and 500 in rc
+    for cons in ("{C,>=,6}", "{A,=,Colorado}", "{D,<,3}"):
+        for access in ("FILESCAN", "COLUMNSCAN"):
+            a = Query().execute(["db", "cfb", "[A,B,C,D]", cons, "100", access], echo=False)
+            b = Query().execute(["db", "cf", "[A,B,C,D]", cons, "100", access], echo=False)
+            assert a == b and len(a) > 6
+    Columnarfile("cfb").close()

@@ -121,3 +121,18 @@ def test_dbfile_header_reader_against_the_page_writer(oracle, minidata):
     assert read_header(img, "other")["colnames"] == ["K"] and read_header(img, "other")["deleted_bytes"] == b""
     with pytest.raises(Exception, match="Columnar File does not exist"):
         read_header(img, "nope")
+
+
+def test_batchinsert_datafile_parser(oracle, minidata):
+    """input.parse_datafile (BatchInsert.java:60-103) against the fixture the oracle reads: names, types, column arrays."""
+    import os
+    from mbcol.input import parse_datafile
+    names, descs, cols = minidata
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "minidata.tsv")
+    n2, d2, c2 = parse_datafile(path, 4)
+    assert n2 == names and [(int(t), w) for t, w in d2] == descs
+    for a, b in zip(c2, cols):
+        np.testing.assert_array_equal(np.asarray(a).reshape(-1), np.asarray(b).reshape(-1))
+    for bad in (0, 2, 5):                                        # NUMCOLUMNS must be the file's column count
+        with pytest.raises(Exception, match="does not match"):
+            parse_datafile(path, bad)
