@@ -284,6 +284,15 @@ class BitMapQuery:
         return ColumnarIndexScan(cf, fnums, itypes, inames, cf.getAttributeTypes(), cf.getStringSizes(), cf.getFieldCount(), exprs)
 
 
+def nlj_emission_order(outer_qualifying_positions, pair_outer, pair_inner, block_rows: int) -> np.ndarray:
+    """Permutation that puts a pair list into the emission order of iterator/ColumnarNestedLoopJoins.java:157-207: the
+    qualifying outer rows are taken block_rows at a time; per block every inner row in order, the block's outer rows
+    inside.  Sort key = (outer block, inner position, outer position)."""
+    po, pi = np.asarray(pair_outer, dtype=np.int64), np.asarray(pair_inner, dtype=np.int64)
+    rank = np.searchsorted(np.asarray(outer_qualifying_positions, dtype=np.int64), po)
+    return np.lexsort((po, pi, rank // max(int(block_rows), 1)))
+
+
 class NljQuery:
     """input/NljQuery.java:33-330: `nlj DB OUTER INNER OUTERCONST INNERCONST JOINCONST OUTERACCESS INNERACCESS [targets]
     NUMBUF MEM`.  The reference runs a block nested-loop join over two column scans
@@ -349,9 +358,7 @@ class NljQuery:
         sizes, types = outer.getAttrSizes(), outer.getAttributeTypes()
         tuple_size = (len(tcols) + 2) * 2 + sum(sizes[c] + 2 if types[c].attrType == AttrType.attrString else 4 for c in tcols)
         block_rows = max(1, (amt_of_memory - 1) * (1024 // tuple_size))
-        po, pi = res.positions(), res.positions2()
-        rank = np.searchsorted(osel.positions(), po)               # rank of the pair's outer row among the qualifying ones
-        order = np.lexsort((po, pi, rank // block_rows))
+        order = nlj_emission_order(osel.positions(), res.positions(), res.positions2(), block_rows)
         lines: list[str] = []
         _emit(lines, ", ".join(names), echo)
         from .heap import Tuple

@@ -491,7 +491,7 @@ class ColumnarNestedLoopJoins(Iterator):
             raise NestedLoopException(e, "Exceeption is caught by ColumnarNestedLoopsJoins.java")
         block_rows = max(1, (self.n_buf_pgs - 1) * (1024 // max(self.outerItr.getTupleSize(), 1)))
         po, pi = res.positions(), res.positions2()
-        rank = np.searchsorted(osel.positions(), po)
+        rank = np.searchsorted(osel.positions(), po)              # same key as input.nlj_emission_order
         order = np.lexsort((po, pi, rank // block_rows))
         self._cols = [np.asarray(res.column(i))[order] for i in range(self.nOutFlds)]
         self._rows = len(order)

@@ -136,3 +136,36 @@ def test_batchinsert_datafile_parser(oracle, minidata):
     for bad in (0, 2, 5):                                        # NUMCOLUMNS must be the file's column count
         with pytest.raises(Exception, match="does not match"):
             parse_datafile(path, bad)
+
+
+def test_host_orderings_match_the_oracle_restatements(oracle):
+    """The two orderings the mirror applies on the host to GPU results -- the block nested-loop emission order of `nlj` and
+    the reference's external-merge order of equal keys in `sort` -- against the oracle's restatements (which are pinned on
+    the transcript), on random inputs."""
+    from mbcol.input import _external_sort_replay, nlj_emission_order
+    rng = np.random.default_rng(4)
+    for _ in range(20):
+        n_o, n_i = int(rng.integers(1, 300)), int(rng.integers(1, 300))
+        oq = np.sort(rng.choice(1000, n_o, replace=False))
+        npairs = int(rng.integers(0, 2000))
+        po, pi = oq[rng.integers(0, n_o, npairs)], rng.integers(0, n_i, npairs)
+        block = int(rng.integers(1, 400))
+        np.testing.assert_array_equal(nlj_emission_order(oq, po, pi, block), oracle.nlj_order(oq, po, pi, block))
+    for trial in range(12):
+        n = int(rng.integers(1, 4000))
+        descs = [(1, 4), (0, 7)]
+        cols = [rng.integers(0, int(rng.integers(1, 40)), n).astype(np.int32),
+                oracle.pack_strings([["a", "bb", "ccc", ""][i] for i in rng.integers(0, 4, n)], 7)]
+        keys = [[0], [1], [1, 0]][trial % 3]
+        desc, bufs = bool(trial % 2), int(rng.integers(3, 9))
+        exp = oracle.external_sort_order(descs, cols, keys, desc, bufs)
+        stable = oracle.sort(descs, cols, keys, descending=desc)                  # what the GPU returns: ties by position
+        change = np.zeros(max(n - 1, 0), dtype=bool)
+        for c in keys:
+            a = np.asarray(cols[c]).reshape(n, -1)[stable]
+            change |= (a[1:] != a[:-1]).any(axis=1)
+        group = np.concatenate([[0], np.cumsum(change)]) if n else np.zeros(0, dtype=np.int64)
+        by_pos = np.argsort(stable, kind="stable")
+        rec = sum(w + 2 if t == 0 else 4 for t, w in (descs[c] for c in keys)) + 4
+        got = [int(stable[by_pos[r]]) for r in _external_sort_replay(group[by_pos].tolist(), 1004 // (rec + 4), bufs - 1)]
+        assert got == [int(x) for x in exp], (trial, n, keys, desc, bufs)
