@@ -118,10 +118,12 @@ typedef struct {
 } mbc_projspec;
 
 /* ---- context ----------------------------------------------------------------------- */
-/* One context = one GPU (one process per GPU; multi-GPU runs shard rows by position range
- * and exchange results with NCCL outside this library).  Replaces the role of
+/* One context = one GPU.  Multi-GPU runs shard rows by position range, one context per GPU (in one process or in
+ * one process per GPU), and gather their results through the mbc_shard_* calls below.  Replaces the role of
  * global/SystemDefs.java:7-96 (buffer pool + DB singletons): device HBM is the pool. */
 int32_t mbc_init(int32_t device_id, mbc_ctx** out);
+/* SURVEY.md 8(b)'s mbc_init(n_devices, ids): one context per listed device, all or nothing. */
+int32_t mbc_init_devices(int32_t n_devices, const int32_t* device_ids, mbc_ctx** out /* [n_devices] */);
 void    mbc_shutdown(mbc_ctx* ctx);
 /* Run every later launch of this context on `cuda_stream` (a cudaStream_t; NULL = the
  * context's own stream) so callers can time with events on their stream. */
@@ -230,6 +232,48 @@ int32_t mbc_bitmap_join(mbc_table* outer, mbc_table* inner,
  * (MBC_WANT_POSITIONS) and the projected columns / Tuple bytes of those rows (MBC_WANT_COLUMNS / MBC_WANT_TUPLES). */
 int32_t mbc_sort(mbc_table* t, const int32_t* key_cols, int32_t nkeys, int32_t descending,
                  const int32_t* proj_cols, int32_t nproj, uint32_t want, mbc_result** out);
+
+/* ---- sharding: TID-range shards on the GPUs of one node ----------------------------------------
+ * The reference has no partitioning (it is one Java thread); this is what running its ColumnarFileScan
+ * (iterator/ColumnarFileScan.java:156-188) over a table whose position ranges live on several GPUs needs: every rank
+ * scans its slice (mbc_scan on a table created with position_base = first position of the slice), then the ranks'
+ * results are concatenated in rank (= position) order in a WINDOW in the root rank's HBM, and COUNT/SUM/MIN/MAX are
+ * folded.  The rows cross NVLink once, as peer-memory stores from a kernel of this library; there is no NCCL call.
+ *
+ *   every rank:  mbc_shard_create(ctx, rank, world, &sh)
+ *   root:        mbc_shard_window_create(sh, capacity_rows, ncols, strides, handle)      allocates + exports the window
+ *   peers:       mbc_shard_window_open(sh, handle, ...)      another process: the host ships the 64 handle bytes
+ *            or  mbc_shard_window_attach(sh, root_sh)        same process (one JVM, several GPUs): peer access
+ *   per step, every rank (root included), after its mbc_scan:
+ *                mbc_shard_gather(sh, result, beside_next_scan)   asynchronous; then mbc_shard_fence(sh) before the
+ *                                                                 result is freed when beside_next_scan != 0
+ *   root:        mbc_shard_collect(sh, &total, counts)       waits for every rank's rows; mbc_shard_agg folds aggregates;
+ *                mbc_shard_read / mbc_shard_window_device     the gathered rows;   mbc_shard_release(sh) ends the step.
+ * Every rank must call mbc_shard_gather exactly once per step (the calls are matched by a step counter), with results
+ * of the same projection; the root must release a step before the ranks can gather the step after the next one. */
+typedef struct mbc_shard mbc_shard;
+#define MBC_IPC_HANDLE_BYTES 64
+int32_t mbc_shard_create(mbc_ctx* ctx, int32_t rank, int32_t world, mbc_shard** out);
+void    mbc_shard_free(mbc_shard* sh);
+/* col_strides: device row stride of every projected column (mbc_result_column_device). handle_out: 64 bytes or NULL. */
+int32_t mbc_shard_window_create(mbc_shard* sh, int64_t capacity_rows, int32_t ncols, const int32_t* col_strides,
+                                uint8_t* handle_out);
+int32_t mbc_shard_window_open(mbc_shard* sh, const uint8_t* handle, int64_t capacity_rows, int32_t ncols,
+                              const int32_t* col_strides);
+int32_t mbc_shard_window_attach(mbc_shard* sh, const mbc_shard* root);
+/* Push this rank's positions, projected columns, count and aggregates of `r` into the window.  beside_next_scan != 0:
+ * the push runs on a side stream behind r's kernels, so scans queued afterwards overlap it. */
+int32_t mbc_shard_gather(mbc_shard* sh, const mbc_result* r, int32_t beside_next_scan);
+int32_t mbc_shard_fence(mbc_shard* sh);
+int32_t mbc_shard_collect(mbc_shard* root, int64_t* total_rows, int64_t* rank_counts /* [world] or NULL */);
+/* aggregate i of the gathered results folded over the ranks; kind / type as in the scan's mbc_aggspec / column type */
+int32_t mbc_shard_agg(const mbc_shard* root, int32_t i, int32_t kind, int32_t type, int64_t* as_i64, double* as_f64,
+                      int32_t* valid);
+/* device pointers of the last gathered step (root: its own memory; peers: the mapped window) */
+int32_t mbc_shard_window_device(const mbc_shard* sh, void** d_positions, int32_t col, void** d_column);
+/* copy rows [first_row, first_row + nrows) of the gathered positions (col = -1, int64) or of column `col` to the host */
+int32_t mbc_shard_read(mbc_shard* root, int32_t col, int64_t first_row, int64_t nrows, void* host_out);
+int32_t mbc_shard_release(mbc_shard* root);
 
 /* ---- results -------------------------------------------------------------------------- */
 /* A device-resident result of mbc_scan (no MBC_WANT_HOST / MBC_WANT_TUPLES) completes asynchronously:

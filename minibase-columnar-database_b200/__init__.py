@@ -12,6 +12,6 @@ Import as ``import mbcol`` (alias module at the repo root).
 """
 from . import _native
 from ._native import MbcError
-from .engine import Context, Table, Result, Term, bitmap_join
+from .engine import Context, Table, Result, Shard, Term, bitmap_join
 
-__all__ = ["Context", "Table", "Result", "Term", "bitmap_join", "MbcError", "_native"]
+__all__ = ["Context", "Table", "Result", "Shard", "Term", "bitmap_join", "MbcError", "_native"]

@@ -104,7 +104,21 @@ _SIGNATURES = {
     "mbc_result_device": (C.c_int32, [_VP, C.POINTER(_VP), C.POINTER(_VP), C.POINTER(_VP), C.POINTER(_VP)]),
     "mbc_result_column_device": (C.c_int32, [_VP, C.c_int32, C.POINTER(_VP), C.POINTER(C.c_int32)]),
     "mbc_result_free": (None, [_VP]),
+    "mbc_init_devices": (C.c_int32, [C.c_int32, C.POINTER(C.c_int32), C.POINTER(_VP)]),
+    "mbc_shard_create": (C.c_int32, [_VP, C.c_int32, C.c_int32, C.POINTER(_VP)]),
+    "mbc_shard_free": (None, [_VP]),
+    "mbc_shard_window_create": (C.c_int32, [_VP, C.c_int64, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_uint8)]),
+    "mbc_shard_window_open": (C.c_int32, [_VP, C.POINTER(C.c_uint8), C.c_int64, C.c_int32, C.POINTER(C.c_int32)]),
+    "mbc_shard_window_attach": (C.c_int32, [_VP, _VP]),
+    "mbc_shard_gather": (C.c_int32, [_VP, _VP, C.c_int32]),
+    "mbc_shard_fence": (C.c_int32, [_VP]),
+    "mbc_shard_collect": (C.c_int32, [_VP, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "mbc_shard_agg": (C.c_int32, [_VP, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_double), C.POINTER(C.c_int32)]),
+    "mbc_shard_window_device": (C.c_int32, [_VP, C.POINTER(_VP), C.c_int32, C.POINTER(_VP)]),
+    "mbc_shard_read": (C.c_int32, [_VP, C.c_int32, C.c_int64, C.c_int64, _VP]),
+    "mbc_shard_release": (C.c_int32, [_VP]),
 }
+IPC_HANDLE_BYTES = 64
 
 
 def header_functions(path: str = HEADER_PATH) -> list[str]:

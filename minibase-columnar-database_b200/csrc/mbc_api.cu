@@ -190,6 +190,7 @@ void mbc_shutdown(mbc_ctx* ctx) {
     for (auto& b : ctx->pinned_free) cudaFreeHost(b.p);
     for (auto e : ctx->event_free) cudaEventDestroy(e);
     if (ctx->ws) cudaFree(ctx->ws);
+    if (ctx->fused_flags) cudaFree(ctx->fused_flags);
     cudaEventDestroy(ctx->ev_begin);
     cudaEventDestroy(ctx->ev_end);
     cudaStreamDestroy(ctx->own_stream);

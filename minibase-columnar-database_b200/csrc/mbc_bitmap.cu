@@ -219,9 +219,17 @@ __device__ __forceinline__ void fill_few_values(const BuildParams& p, uint32_t* 
     const int base = IDENT ? (int)p.h.kmin + v0 : v0;
 #pragma unroll
     for (int q = 0; q < kMaxPerThread; ++q) {
-        int id = IDENT ? pv[q] - base : (int)__ldg(p.h.id_of + (uint32_t)((long long)pv[q] - p.h.kmin)) - base;
-        bool ok = (unsigned)id < (unsigned)nv;
-        if (!FULL) ok = ok && row0 + threadIdx.x + q * kBuildThreads < p.nrows;
+        // rows past the end of the table hold the column's zero padding: the id table is only read for a row of the table
+        // whose value lies inside [kmin, kmax] (0 may be far outside it)
+        bool ok = FULL || row0 + threadIdx.x + q * kBuildThreads < p.nrows;
+        int id = -1;
+        if (IDENT) {
+            id = pv[q] - base;
+        } else {
+            const uint32_t k = (uint32_t)((long long)pv[q] - p.h.kmin);
+            if (ok && k < (uint32_t)p.h.range) id = (int)__ldg(p.h.id_of + k) - base;
+        }
+        ok = ok && (unsigned)id < (unsigned)nv;
         uint32_t w = __ballot_sync(0xFFFFFFFFu, ok);
 #pragma unroll
         for (int k = 0; k < 5; ++k)

@@ -43,33 +43,69 @@ struct PageRef {
 __device__ __forceinline__ uint32_t be16(const uint8_t* p) { return ((uint32_t)p[0] << 8) | p[1]; }
 
 // one warp per data page; lanes take slots lane, lane+32, ...
+// `present` (bit p = word p/32, bit p%32) receives one bit per OCCUPIED slot: the Java purge deletes the heap records of
+// marked rows and then clears their markedDeleted bits (columnar/Columnarfile.java:874,912-914), so a purged position is an
+// empty slot (or an empty directory slot) that no Scan / TupleScan ever returns -- it must not come back as a live row.
 __global__ void __launch_bounds__(256) decode_pages_kernel(const uint8_t* db, const PageRef* pages, int64_t npages, int per_page,
-                                                           int type, int width, int stride, uint8_t* dst, int64_t nrows) {
+                                                           int type, int width, int stride, uint8_t* dst, int64_t nrows,
+                                                           uint32_t* present) {
     const int lane = threadIdx.x & 31;
     const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (w >= npages) return;
     const PageRef ref = pages[w];
     const uint8_t* pg = db + (int64_t)ref.page_id * kPage;
-    const int slot_cnt = (int)(int16_t)be16(pg);
-    for (int s = lane; s < slot_cnt; s += 32) {
-        const uint8_t* sl = pg + kDpFixed + 4 * s;
-        const int len = (int)(int16_t)be16(sl);
-        const int off = (int)be16(sl + 2);
-        if (len < 0) continue;                                  // EMPTY_SLOT (HFPage.java:300)
+    const int slot_cnt = min((int)(int16_t)be16(pg), per_page);
+    for (int s0 = 0; s0 < slot_cnt; s0 += 32) {                     // warp-uniform trip count
+        const int s = s0 + lane;
         const int64_t pos = (int64_t)ref.page_index * per_page + s;
-        if (pos >= nrows || off + len > kPage) continue;
-        const uint8_t* rec = pg + off;
-        if (type != MBC_ATTR_STRING) {
-            // Convert.getIntValue / getFloValue: 4 bytes big-endian
-            uint32_t v = ((uint32_t)rec[0] << 24) | ((uint32_t)rec[1] << 16) | ((uint32_t)rec[2] << 8) | rec[3];
-            reinterpret_cast<uint32_t*>(dst)[pos] = v;
-        } else {
-            // Convert.getStrValue: [length:2][modified UTF-8 bytes]; the column keeps the bytes zero padded
-            int n = (int)be16(rec);
-            n = min(n, min(width, len - 2));
-            uint8_t* d = dst + pos * stride;
-            for (int k = 0; k < n; ++k) d[k] = rec[2 + k];
+        bool occupied = false;
+        if (s < slot_cnt && pos < nrows) {
+            const uint8_t* sl = pg + kDpFixed + 4 * s;
+            const int len = (int)(int16_t)be16(sl);
+            const int off = (int)be16(sl + 2);
+            if (len >= 0 && off + len <= kPage) {                   // len < 0: EMPTY_SLOT (HFPage.java:300)
+                occupied = true;
+                const uint8_t* rec = pg + off;
+                if (type != MBC_ATTR_STRING) {
+                    // Convert.getIntValue / getFloValue: 4 bytes big-endian
+                    uint32_t v = ((uint32_t)rec[0] << 24) | ((uint32_t)rec[1] << 16) | ((uint32_t)rec[2] << 8) | rec[3];
+                    reinterpret_cast<uint32_t*>(dst)[pos] = v;
+                } else {
+                    // Convert.getStrValue: [length:2][modified UTF-8 bytes]; the column keeps the bytes zero padded
+                    int n = (int)be16(rec);
+                    n = min(n, min(width, len - 2));
+                    uint8_t* d = dst + pos * stride;
+                    for (int k = 0; k < n; ++k) d[k] = rec[2 + k];
+                }
+            }
         }
+        // the warp's 32 consecutive positions straddle at most two words of the presence bitmap
+        const uint32_t m = __ballot_sync(0xFFFFFFFFu, occupied);
+        const int64_t pos0 = (int64_t)ref.page_index * per_page + s0;
+        const int sh = (int)(pos0 & 31);
+        if (lane == 0 && (m << sh)) atomicOr(present + (pos0 >> 5), m << sh);
+        if (lane == 1 && sh && (m >> (32 - sh))) atomicOr(present + (pos0 >> 5) + 1, m >> (32 - sh));
+    }
+}
+
+// deleted |= ~present (rows of the table only); *any is raised when a deleted bit exists
+__global__ void absent_rows_kernel(const uint32_t* present, uint32_t* deleted, int64_t nrows, int* any) {
+    const int64_t nwords = (nrows + 31) >> 5;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nwords; i += (int64_t)gridDim.x * blockDim.x) {
+        uint32_t a = ~present[i];
+        if (i == nwords - 1 && (nrows & 31)) a &= (1u << (nrows & 31)) - 1u;
+        const uint32_t d = deleted[i] | a;
+        deleted[i] = d;
+        if (d) *any = 1;
+    }
+}
+
+// deleted |= extra (the <cf>.md bits)
+__global__ void or_words_kernel(uint32_t* deleted, const uint32_t* extra, int64_t nwords, int* any) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nwords; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t d = deleted[i] | extra[i];
+        deleted[i] = d;
+        if (d) *any = 1;
     }
 }
 
@@ -217,40 +253,49 @@ extern "C" int32_t mbc_table_ingest_dbfile(mbc_ctx* ctx, const uint8_t* db_bytes
     MBC_TRY(mbc_table_create(ctx, ncols, descs.data(), nrows, 0, &t));
 
     // ---- upload the image once, decode every data page on the device ----
+    // A position is live only if EVERY column holds a record for it: each column's decode marks its occupied slots in a
+    // presence bitmap, and the complement (within [0, nrows)) is ORed into the table's deleted mask.
     uint8_t* d_db = nullptr;
     PageRef* d_pages = nullptr;
+    uint32_t* d_present = nullptr;
+    int* d_any = nullptr;
     size_t max_pages = 1;
     for (auto& p : pages) max_pages = std::max(max_pages, p.size());
+    const size_t mask_bytes = (size_t)t->words_pad * 4;
+    const unsigned mask_grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>((t->words_pad + 255) / 256, ctx->sm_count * 8));
     int32_t s = dev_alloc(ctx, (void**)&d_db, (size_t)db_len, false);
     if (s == MBC_OK) s = dev_alloc(ctx, (void**)&d_pages, max_pages * sizeof(PageRef), false);
+    if (s == MBC_OK) s = dev_alloc(ctx, (void**)&d_present, mask_bytes, false);
+    if (s == MBC_OK) s = dev_alloc(ctx, (void**)&d_any, sizeof(int), true);
+    if (s == MBC_OK && !t->d_deleted) s = dev_alloc(ctx, (void**)&t->d_deleted, mask_bytes, true);
     if (s == MBC_OK && cudaMemcpyAsync(d_db, db_bytes, (size_t)db_len, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) s = MBC_ERR_CUDA;
     begin_timing(ctx);
     for (int c = 0; c < ncols && s == MBC_OK; ++c) {
-        if (pages[c].empty()) continue;
         const Column& col = t->cols[c];
         const int rec = col.type == MBC_ATTR_STRING ? col.width + 2 : col.width;
         const int per_page = (kPage - kDpFixed) / (4 + rec);
-        if (cudaMemcpyAsync(d_pages, pages[c].data(), pages[c].size() * sizeof(PageRef), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess ||
-            cudaStreamSynchronize(ctx->stream) != cudaSuccess) { s = MBC_ERR_CUDA; break; }
-        const int64_t np = (int64_t)pages[c].size();
-        const unsigned grid = (unsigned)((np * 32 + 255) / 256);
-        decode_pages_kernel<<<grid, 256, 0, ctx->stream>>>(d_db, d_pages, np, per_page, col.type, col.width, col.stride, (uint8_t*)col.d, nrows);
-        ctx->launches++;
+        if (cudaMemsetAsync(d_present, 0, mask_bytes, ctx->stream) != cudaSuccess) { s = MBC_ERR_CUDA; break; }
+        if (!pages[c].empty()) {
+            if (cudaMemcpyAsync(d_pages, pages[c].data(), pages[c].size() * sizeof(PageRef), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess ||
+                cudaStreamSynchronize(ctx->stream) != cudaSuccess) { s = MBC_ERR_CUDA; break; }
+            const int64_t np = (int64_t)pages[c].size();
+            const unsigned grid = (unsigned)((np * 32 + 255) / 256);
+            decode_pages_kernel<<<grid, 256, 0, ctx->stream>>>(d_db, d_pages, np, per_page, col.type, col.width, col.stride, (uint8_t*)col.d, nrows,
+                                                               d_present);
+            ctx->launches++;
+        }
+        if (nrows > 0) {
+            absent_rows_kernel<<<mask_grid, 256, 0, ctx->stream>>>(d_present, t->d_deleted, nrows, d_any);
+            ctx->launches++;
+        }
         if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) s = MBC_ERR_CUDA;
     }
     end_timing(ctx);
     if (s == MBC_OK && cudaGetLastError() != cudaSuccess) s = MBC_ERR_CUDA;
-    dev_free(ctx, d_db);
-    dev_free(ctx, d_pages);
-    if (s != MBC_OK) {
-        set_error("mbc_table_ingest_dbfile: device decode failed");
-        mbc_table_free(t);
-        return s;
-    }
 
-    // ---- markedDeleted (BM.readBitSet :179-215): first record of every page of the <cf>.md chain ----
+    // ---- markedDeleted (BM.readBitSet :179-215): first record of every page of the <cf>.md chain, ORed in ----
     auto md = files.find(name + ".md");
-    if (md != files.end()) {
+    if (s == MBC_OK && md != files.end()) {
         std::vector<uint8_t> bytes;
         int64_t pid = md->second;
         int guard = 0;
@@ -262,14 +307,34 @@ extern "C" int32_t mbc_table_ingest_dbfile(mbc_ctx* ctx, const uint8_t* db_bytes
             }
             pid = rd32(pg + 12);
         }
-        bytes.resize((bytes.size() + 7) / 8 * 8, 0);
-        if (!bytes.empty()) {
-            std::vector<uint64_t> words(bytes.size() / 8);
-            memcpy(words.data(), bytes.data(), bytes.size());        // BitSet.valueOf(byte[]) is little-endian
-            s = mbc_table_set_deleted(t, words.data(), (int64_t)words.size());
-            if (s != MBC_OK) { mbc_table_free(t); return s; }
+        // BitSet.valueOf(byte[]) is little-endian: byte k = bits 8k..8k+7, the same numbering as the uint32 words; bits at
+        // or beyond nrows are irrelevant (every scan masks rows >= nrows)
+        bytes.resize(std::min(bytes.size(), mask_bytes));
+        bool any = false;
+        for (uint8_t b : bytes) any |= b != 0;
+        if (any) {
+            bytes.resize(mask_bytes, 0);
+            if (cudaMemcpyAsync(d_present, bytes.data(), mask_bytes, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) s = MBC_ERR_CUDA;
+            if (s == MBC_OK) {
+                or_words_kernel<<<mask_grid, 256, 0, ctx->stream>>>(t->d_deleted, d_present, t->words_pad, d_any);
+                ctx->launches++;
+                if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) s = MBC_ERR_CUDA;   // `bytes` is pageable host memory
+            }
         }
     }
+    int any_deleted = 0;
+    if (s == MBC_OK && (cudaMemcpyAsync(&any_deleted, d_any, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+                        cudaStreamSynchronize(ctx->stream) != cudaSuccess)) s = MBC_ERR_CUDA;
+    dev_free(ctx, d_db);
+    dev_free(ctx, d_pages);
+    dev_free(ctx, d_present);
+    dev_free(ctx, d_any);
+    if (s != MBC_OK) {
+        set_error("mbc_table_ingest_dbfile: device decode failed");
+        mbc_table_free(t);
+        return s;
+    }
+    t->has_deleted = any_deleted != 0;
     *out = t;
     return MBC_OK;
 }

@@ -100,6 +100,12 @@ struct mbc_ctx {
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
     int64_t launches = 0;
     bool filter_smem_set = false, sort_smem_set = false;   // per-device opt-in to > 48 KB of dynamic shared memory
+    // single-residency scan (mbc_scan_fused.cuh): published tile counts, tagged with the launch epoch so the buffer is
+    // never cleared between launches (zeroed when it is allocated and when the 20-bit epoch wraps)
+    uint32_t* fused_flags = nullptr;
+    int64_t   fused_flags_cap = 0;
+    uint32_t  fused_epoch = 0;
+    int       fused_smem_budget = -1;    // dynamic shared memory the fused kernel may use (-1: not probed, 0: unusable)
     int64_t h2d_bytes = 0;            // host -> device bytes moved by mbc_scan_host (copies + rows read in place)
     float last_ms = 0.f;
     bool timing_split = false;

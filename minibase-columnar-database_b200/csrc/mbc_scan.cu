@@ -7,6 +7,7 @@
 
 #include "mbc_internal.cuh"
 #include "mbc_scan_kernels.cuh"
+#include "mbc_scan_fused.cuh"
 
 namespace mbc {
 
@@ -242,11 +243,11 @@ struct Workspace {
     unsigned long long* agg_out;  // [kMaxAgg] aggregates, [kMaxAgg] = the count (agg_finish_kernel)
 };
 
-static int32_t carve_workspace(mbc_ctx* ctx, int64_t launch_tiles, int64_t total_tiles, int nagg, Workspace* w) {
+static int32_t carve_workspace(mbc_ctx* ctx, int64_t launch_tiles, int64_t part_slots, int nagg, Workspace* w) {
     const size_t head = 64 + round_up((kMaxAgg + 1) * 8, 64);
     size_t counts_bytes = (size_t)round_up(launch_tiles * 4, 64);
     size_t out_bytes = (size_t)round_up((launch_tiles + 1) * 8, 64);
-    size_t partial_bytes = (size_t)std::max(nagg, 1) * total_tiles * 8;
+    size_t partial_bytes = (size_t)std::max(nagg, 1) * part_slots * 8;
     size_t total = head + counts_bytes + out_bytes + partial_bytes + 64;
     MBC_TRY(ensure_workspace(ctx, total));
     char* b = (char*)ctx->ws;
@@ -261,17 +262,134 @@ static int32_t carve_workspace(mbc_ctx* ctx, int64_t launch_tiles, int64_t total
 // A scan job: the parameter block, the result that owns the output buffers, and the workspace.
 // `schema` supplies column types/strides; bind_table() points the job at the table whose rows the
 // next launch reads (the resident table, or one of the staging tables of mbc_scan_host).
+constexpr int kPartScale = kTileRows / kFR;   // partial slots per 4096-row tile: the fused engine's tiles are smaller
+
 struct ScanJob {
     ScanParams p;
     mbc_result* r = nullptr;
     Workspace w;
-    int64_t total_tiles = 0;
+    int64_t part_slots = 0;       // capacity (= stride) of the per-tile aggregate partials: one slot per tile of either engine
+    int64_t part_done = 0;        // slots written by the launches so far
     size_t smem_bytes = 0;
     int max_grid = 1;
     int launches = 0;             // launches so far: the running count is in slot launches & 1
+    // single-residency engine (mbc_scan_fused.cuh): planned once per job, chosen per launch
+    bool fused_ok = false;
+    bool fused_off = false;       // a launch whose projected columns are read in place from host memory stays two-pass
+    FusedParams f;
+    size_t fused_smem = 0;
+    int fused_ctas_per_sm = 1;
     long long* count_slot() const { return w.count + (launches & 1); }
     int grid_per_tiles(int ntiles) const { return std::max(1, std::min(ntiles, max_grid)); }
 };
+
+
+// Plan the single-residency engine (mbc_scan_fused.cuh) for this job: payload columns, ring depths, shared memory.
+// Leaves job->fused_ok false when the scan does not fit it; every launch then takes the two-pass engine.
+static void plan_fused(mbc_ctx* ctx, ScanJob* job) {
+    job->fused_ok = false;
+    const char* path = getenv("MBC_SCAN_PATH");                   // "twopass" / "fused": tests and profiles force either engine
+    if (path && !strcmp(path, "twopass")) return;
+    ScanParams& p = job->p;
+    FusedParams& f = job->f;
+    memset(&f, 0, sizeof(f));
+    bool need_write = p.out_pos || p.nproj > 0;
+    for (int a = 0; a < p.nagg; ++a) need_write |= p.aggs[a].kind != MBC_AGG_COUNT;
+    if (!need_write) return;                                       // COUNT alone: pass 1 + the offsets kernel is all there is to do
+    if (ctx->fused_smem_budget < 0) {                              // once per context: opt in to the large shared memory carve-out
+        ctx->fused_smem_budget = 0;
+        int per_sm = 0, reserved = 0, optin = 0, coop = 0;
+        cudaFuncAttributes fa;
+        if (cudaDeviceGetAttribute(&per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, ctx->device) == cudaSuccess &&
+            cudaDeviceGetAttribute(&reserved, cudaDevAttrReservedSharedMemoryPerBlock, ctx->device) == cudaSuccess &&
+            cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device) == cudaSuccess &&
+            cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device) == cudaSuccess && coop &&
+            cudaFuncGetAttributes(&fa, fused_scan_kernel) == cudaSuccess) {
+            // kFCtasPerSm CTAs share the SM's shared memory; each also pays its static arrays and the per-block reserve
+            int budget = std::min(optin, per_sm / kFCtasPerSm - reserved) - (int)fa.sharedSizeBytes;
+            budget = budget / 1024 * 1024;
+            if (budget > 0 && cudaFuncSetAttribute(fused_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, budget) == cudaSuccess)
+                ctx->fused_smem_budget = budget;
+        }
+        cudaGetLastError();
+    }
+    const int budget = ctx->fused_smem_budget;
+    if (budget <= 0) return;
+    // payload = the distinct projected / aggregated columns, laid out back to back in a payload stage
+    int pay_col[kFMaxPay];
+    auto pay_of = [&](int col, int stride) -> int {
+        for (int k = 0; k < f.npay; ++k) if (pay_col[k] == col) return k;
+        if (f.npay == kFMaxPay || (stride & 3)) return -1;
+        pay_col[f.npay] = col;
+        f.pay_stride[f.npay] = stride;
+        f.pay_off[f.npay] = f.pay_stage_bytes;
+        f.pay_stage_bytes += stride * kFR;
+        return f.npay++;
+    };
+    for (int c = 0; c < p.nproj; ++c) {
+        const int k = pay_of(p.proj[c].col, p.proj[c].stride);
+        if (k < 0) return;
+        f.proj_pay[c] = (int8_t)k;
+    }
+    for (int a = 0; a < p.nagg; ++a) {
+        f.agg_pay[a] = -1;
+        if (p.aggs[a].kind == MBC_AGG_COUNT) continue;
+        const int k = pay_of(p.aggs[a].col, 4);
+        if (k < 0) return;
+        f.agg_pay[a] = (int8_t)k;
+    }
+    const int pred_stage = p.nstaged * kFPredColBytes, pay_stage = f.pay_stage_bytes;
+    // Ring depths.  The payload ring needs 2 stages (one tile loading while another is written); the predicate ring takes the
+    // rest: a sparse scan streams the predicate columns alone and wants as many of them in flight as the filter pass has.
+    int P = 2, S = 0;
+    if (f.npay) {
+        S = std::min(2, (budget - 2 * pred_stage) / pay_stage);
+        if (S < 1) return;                                         // rows too wide for a shared-memory tile
+    }
+    if (const char* e = getenv("MBC_FUSED_PAY_STAGES")) S = f.npay ? std::max(1, std::min(kFMaxPayStages, atoi(e))) : 0;
+    if (pred_stage) P = std::max(2, std::min(kFMaxPredStages, (budget - S * pay_stage) / pred_stage));
+    if (const char* e = getenv("MBC_FUSED_PRED_STAGES")) P = std::max(2, std::min(kFMaxPredStages, atoi(e)));
+    if ((size_t)P * pred_stage + (size_t)S * pay_stage > (size_t)budget) return;
+    f.pred_stages = P;
+    f.pay_stages = S;
+    f.ahead = 2;                                                   // tiles between a count's publication and its use
+    if (const char* e = getenv("MBC_FUSED_AHEAD")) f.ahead = std::max(0, std::min(kFMaxAhead, atoi(e)));
+    f.dense_min = kFR / 16;                                        // below 1 survivor in 16 rows a batched gather moves fewer bytes
+    if (const char* e = getenv("MBC_FUSED_DENSE_MIN")) f.dense_min = atoi(e);
+    f.dense_min = std::max(1, std::min(f.dense_min, kFPendCap / 2));
+    job->fused_smem = (size_t)P * pred_stage + (size_t)S * pay_stage;
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fused_scan_kernel, kFThreads, job->fused_smem) != cudaSuccess || per_sm < 1) {
+        cudaGetLastError();
+        return;
+    }
+    job->fused_ctas_per_sm = std::min(per_sm, kFCtasPerSm);
+    job->fused_ok = true;
+}
+
+// published-count buffer of the fused engine: grown (zero filled) on demand, never cleared between launches
+static int32_t fused_flags_for(mbc_ctx* ctx, int64_t ntiles, uint32_t** flags, uint32_t* epoch) {
+    if (ctx->fused_flags_cap < ntiles) {
+        if (ctx->fused_flags) {
+            MBC_CUDA(cudaStreamSynchronize(ctx->stream));
+            MBC_CUDA(cudaFree(ctx->fused_flags));
+            ctx->fused_flags = nullptr;
+            ctx->fused_flags_cap = 0;
+        }
+        const int64_t cap = std::max<int64_t>(round_up(ntiles, 4096), 65536);
+        MBC_CUDA(cudaMalloc((void**)&ctx->fused_flags, (size_t)cap * 4));
+        MBC_CUDA(cudaMemsetAsync(ctx->fused_flags, 0, (size_t)cap * 4, ctx->stream));
+        ctx->fused_flags_cap = cap;
+        ctx->fused_epoch = 0;
+    }
+    if (++ctx->fused_epoch >= (1u << (32 - kFCountBits))) {       // the tag wrapped: stale words could match again
+        MBC_CUDA(cudaMemsetAsync(ctx->fused_flags, 0, (size_t)ctx->fused_flags_cap * 4, ctx->stream));
+        ctx->fused_epoch = 1;
+    }
+    *flags = ctx->fused_flags;
+    *epoch = ctx->fused_epoch;
+    return MBC_OK;
+}
 
 static int32_t prepare_job(const mbc_table* schema, const ScanRequest& rq, int64_t capacity_rows, int64_t launch_tiles,
                            int64_t total_tiles, ScanJob* job) {
@@ -310,15 +428,17 @@ static int32_t prepare_job(const mbc_table* schema, const ScanRequest& rq, int64
         p.nproj = rq.nproj;
     }
     MBC_TRY(dev_alloc(ctx, (void**)&r->d_aggs, (kMaxAgg + 1) * 8, false));
-    MBC_TRY(carve_workspace(ctx, launch_tiles, total_tiles, p.nagg, &job->w));
-    job->total_tiles = total_tiles;
-    p.total_tiles = (int)total_tiles;
+    if (total_tiles * kPartScale > INT32_MAX) MBC_FAIL(MBC_ERR_UNSUPPORTED, "table too large for one device scan");
+    job->part_slots = total_tiles * kPartScale;
+    MBC_TRY(carve_workspace(ctx, launch_tiles, job->part_slots, p.nagg, &job->w));
+    p.total_tiles = (int)job->part_slots;
     p.tile_counts = job->w.tile_counts;
     p.tile_out = job->w.tile_out;
     p.partials = job->w.partials;
     p.out_pos = r->d_pos;
     p.ntiles = INT32_MAX;                         // the grid bound comes from the device; bind_table sets the real count
     MBC_TRY(plan_staging(ctx, &p, &job->smem_bytes, &job->max_grid));
+    plan_fused(ctx, job);
     return MBC_OK;
 }
 
@@ -338,16 +458,52 @@ static void bind_table(ScanJob* job, const mbc_table* t) {
     p.ntiles = (int)((t->nrows + kTileRows - 1) / kTileRows);
 }
 
-// the three launches over the bound table; its tiles occupy [tile_base, tile_base + ntiles) of the partials
-static int32_t launch_job(ScanJob* job, int tile_base, bool first) {
+// the launches over the bound table; its tiles take the next slots of the partials array
+static int32_t launch_job(ScanJob* job, bool first) {
     mbc_ctx* ctx = job->r->ctx;
     ScanParams& p = job->p;
-    p.tile_base = tile_base;
-    if (first) job->launches = 0;
+    if (first) { job->launches = 0; job->part_done = 0; }
+    p.tile_base = (int)job->part_done;
     if (p.ntiles == 0) return MBC_OK;
     p.count_in = job->launches == 0 ? nullptr : job->count_slot();   // later launches append at the running offset
     p.count_out = job->w.count + ((job->launches + 1) & 1);
     p.work_counter = reinterpret_cast<unsigned int*>(job->w.count + 4);
+    if (job->fused_ok && !job->fused_off && !(p.nterms == 0 && p.sel_bitmap)) {
+        // single residency: count warps ahead, offsets from the published counts, compaction out of shared memory
+        FusedParams& f = job->f;
+        const int64_t ntiles = (p.nrows + kFR - 1) / kFR;
+        f.ntiles = (int32_t)ntiles;
+        MBC_TRY(fused_flags_for(ctx, ntiles, &f.flags, &f.epoch));
+        for (int c = 0; c < p.nproj; ++c) f.pay_src[f.proj_pay[c]] = p.proj[c].src;
+        for (int a = 0; a < p.nagg; ++a)
+            if (f.agg_pay[a] >= 0) f.pay_src[f.agg_pay[a]] = p.aggs[a].src;
+        const int grid = (int)std::min<int64_t>(ntiles, std::min(ctx->sm_count * job->fused_ctas_per_sm, 32 * kFWaveRegs));
+        const bool prof = getenv("MBC_FUSED_PROF") != nullptr;      // per-role wait cycles of every CTA, averaged, on stderr
+        f.prof = nullptr;
+        if (prof) MBC_TRY(dev_alloc(ctx, (void**)&f.prof, (size_t)grid * 16 * 8, true));
+        void* args[] = {(void*)&p, (void*)&f};
+        MBC_CUDA(cudaLaunchCooperativeKernel((const void*)fused_scan_kernel, dim3(grid), dim3(kFThreads), args, job->fused_smem, ctx->stream));
+        if (prof) {
+            std::vector<long long> h((size_t)grid * 16);
+            MBC_CUDA(cudaMemcpyAsync(h.data(), f.prof, h.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+            MBC_CUDA(cudaStreamSynchronize(ctx->stream));
+            dev_free(ctx, f.prof);
+            double m[16] = {0};
+            for (int c = 0; c < grid; ++c)
+                for (int k = 0; k < 16; ++k) m[k] += (double)h[(size_t)c * 16 + k] / grid;
+            fprintf(stderr,
+                    "[fused prof] tiles/cta %.1f grid %d P %d S %d ahead %d dense_min %d | total %.0f: pred-wait %.0f count %.0f flags %.0f ctl %.0f "
+                    "rank %.0f payfull-wait %.0f dense+other %.0f sparse %.0f flush %.0f | dense tiles/cta %.1f (cycles of thread 0, mean over CTAs)\n",
+                    (double)ntiles / grid, grid, f.pred_stages, f.pay_stages, f.ahead, f.dense_min, m[0], m[1], m[2], m[3], m[4], m[5], m[6], m[7],
+                    m[8], m[9], m[10]);
+        }
+        job->launches++;
+        ctx->launches++;
+        job->part_done += grid;                                     // one aggregate partial per CTA
+        for (int i = 0; i < 3; ++i)
+            if (job->r->ev_mid[i]) cudaEventRecord(job->r->ev_mid[i], ctx->stream);
+        return MBC_OK;
+    }
     if (p.nterms == 0 && p.sel_bitmap) {
         const int grid = std::max(1, std::min((p.ntiles + kWarpsPerCta - 1) / kWarpsPerCta, ctx->sm_count * 8));
         select_bitmap_kernel<<<grid, kScanThreads, 0, ctx->stream>>>(p.sel_bitmap, p.deleted, p.nrows, p.ntiles, p.out_bitmap, p.tile_counts);
@@ -359,6 +515,7 @@ static int32_t launch_job(ScanJob* job, int tile_base, bool first) {
                                                                                                       p.count_in, p.count_out, p.work_counter);
     job->launches++;
     ctx->launches += 2;
+    job->part_done += p.ntiles;
     if (job->r->ev_mid[1]) cudaEventRecord(job->r->ev_mid[1], ctx->stream);
     bool need_write = p.out_pos || p.nproj > 0;
     for (int a = 0; a < p.nagg; ++a) need_write |= p.aggs[a].kind != MBC_AGG_COUNT;   // COUNT comes from the tile offsets
@@ -383,7 +540,7 @@ static int32_t launch_job(ScanJob* job, int tile_base, bool first) {
 
 // aggregate finish + count/aggregate readback.  Synchronous form: the device work of the job is complete after this.
 // Deferred form: everything is queued, the result carries the event and mbc::result_finalize() completes it.
-static int32_t finish_job_device(ScanJob* job, int64_t tiles_done, bool deferred = false) {
+static int32_t finish_job_device(ScanJob* job, bool deferred = false) {
     mbc_ctx* ctx = job->r->ctx;
     ScanParams& p = job->p;
     mbc_result* r = job->r;
@@ -396,7 +553,7 @@ static int32_t finish_job_device(ScanJob* job, int64_t tiles_done, bool deferred
         } else {
             AggList list;
             memcpy(list.g, p.aggs, sizeof(list.g));
-            agg_finish_kernel<<<p.nagg, 1024, 0, ctx->stream>>>(job->w.partials, (int)job->total_tiles, (int)tiles_done, list,
+            agg_finish_kernel<<<p.nagg, 1024, 0, ctx->stream>>>(job->w.partials, (int)job->part_slots, (int)job->part_done, list,
                                                                job->w.agg_out, job->count_slot());
         }
         ctx->launches++;
@@ -430,8 +587,8 @@ static int32_t finish_job_device(ScanJob* job, int64_t tiles_done, bool deferred
     return MBC_OK;
 }
 
-static int32_t finish_job(ScanJob* job, int64_t tiles_done) {
-    MBC_TRY(finish_job_device(job, tiles_done));
+static int32_t finish_job(ScanJob* job) {
+    MBC_TRY(finish_job_device(job));
     return finish_result_host(job->r);
 }
 
@@ -464,10 +621,10 @@ int32_t run_scan(const ScanRequest& rq, mbc_result** out) {
         job.r->ev_t1 = event_get(ctx);
         for (auto& e : job.r->ev_mid) e = event_get(ctx);      // per-kernel times of a resident scan (mbc_result_phase_ms)
         if (job.r->ev_t0) cudaEventRecord(job.r->ev_t0, ctx->stream);
-        s = launch_job(&job, 0, true);
+        s = launch_job(&job, true);
     }
     const bool deferred = rq.allow_deferred && !(rq.want & (MBC_WANT_HOST | MBC_WANT_TUPLES)) && !getenv("MBC_SYNC_RESULTS");
-    if (s == MBC_OK) s = deferred ? finish_job_device(&job, ntiles, true) : finish_job(&job, ntiles);
+    if (s == MBC_OK) s = deferred ? finish_job_device(&job, true) : finish_job(&job);
     if (s != MBC_OK) {
         if (job.r) mbc_result_free(job.r);
         return s;
@@ -611,7 +768,6 @@ static int32_t run_scan_host(mbc_ctx* ctx, int32_t ncols, const mbc_coldesc* col
     };
 
     begin_timing(ctx);
-    int64_t tiles_done = 0;
     bool late_mode = false;
     int64_t late_row_bytes = 0;                                           // bytes per survivor read from host memory
     for (int64_t k = 0; k < nchunks && s == MBC_OK; ++k) {
@@ -637,6 +793,7 @@ static int32_t run_scan_host(mbc_ctx* ctx, int32_t ncols, const mbc_coldesc* col
         st->nrows = n;
         st->pos_base = position_base + row0;
         bind_table(&job, st);
+        job.fused_off = late_mode;
         if (late_mode) {                                                  // survivors of these columns come from host memory
             ScanParams& p = job.p;
             for (int c = 0; c < p.nproj; ++c)
@@ -644,8 +801,7 @@ static int32_t run_scan_host(mbc_ctx* ctx, int32_t ncols, const mbc_coldesc* col
             for (int a = 0; a < p.nagg; ++a)
                 if (p.aggs[a].col >= 0 && late_ok[p.aggs[a].col]) p.aggs[a].src = host_dev[p.aggs[a].col] + (size_t)row0 * 4;
         }
-        s = launch_job(&job, (int)tiles_done, k == 0);
-        tiles_done += job.p.ntiles;
+        s = launch_job(&job, k == 0);
         if (h_counts && s == MBC_OK &&
             cudaMemcpyAsync(&h_counts[k], job.count_slot(), 8, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) s = MBC_ERR_CUDA;
         cudaEventRecord(ev_done[b], ctx->stream);
@@ -662,7 +818,7 @@ static int32_t run_scan_host(mbc_ctx* ctx, int32_t ncols, const mbc_coldesc* col
         if (stream_out && s == MBC_OK && k >= 1) s = drain(k - 1);
     }
     if (s == MBC_OK && stream_out) {
-        s = finish_job_device(&job, tiles_done);
+        s = finish_job_device(&job);
         if (s == MBC_OK) {
             if (out_cap >= 0 && !out_overflow && r->count <= out_cap) {
                 s = copy_rows(copied, r->count);                          // the tail, then everything has landed
@@ -681,7 +837,7 @@ static int32_t run_scan_host(mbc_ctx* ctx, int32_t ncols, const mbc_coldesc* col
             }
         }
     } else if (s == MBC_OK) {
-        s = finish_job(&job, tiles_done);
+        s = finish_job(&job);
     }
     cudaStreamSynchronize(ctx->copy_stream);
     cudaStreamSynchronize(ctx->d2h_stream);

@@ -140,18 +140,19 @@ __device__ __forceinline__ uint32_t mask_op(int op, uint32_t lt, uint32_t eq) {
     }
 }
 
-// load the 16 raw 32-bit values this thread owns (4 units x one 128-bit load), or broadcast a literal
+// load the raw 32-bit values this thread owns (U units x one 128-bit load; U = 4 -> 16 rows), or broadcast a literal
+template <int U = kUnits>
 __device__ __forceinline__ void load_operand32(const DevOperand& o, int64_t thread_row0, const uint32_t* stage, int tile_off,
-                                               uint32_t v[kRowsPerThread]) {
+                                               uint32_t (&v)[U * kVec], const int stage_rows = kTileRows) {
     if (o.kind == 0) {
 #pragma unroll
-        for (int i = 0; i < kRowsPerThread; ++i) v[i] = o.bits;
+        for (int i = 0; i < U * kVec; ++i) v[i] = o.bits;
     } else if (o.staged >= 0) {
         // the tile's slice of this column was brought into shared memory by the TMA engine; lanes read
         // consecutive 16-byte chunks (conflict-free LDS.128)
-        const uint32_t* base = stage + o.staged * kTileRows + tile_off;
+        const uint32_t* base = stage + o.staged * stage_rows + tile_off;
 #pragma unroll
-        for (int u = 0; u < kUnits; ++u) {
+        for (int u = 0; u < U; ++u) {
             uint4 q = *reinterpret_cast<const uint4*>(base + u * kUnitRows);
             v[u * 4 + 0] = q.x;
             v[u * 4 + 1] = q.y;
@@ -161,7 +162,7 @@ __device__ __forceinline__ void load_operand32(const DevOperand& o, int64_t thre
     } else {
         const uint32_t* base = reinterpret_cast<const uint32_t*>(o.ptr) + thread_row0;
 #pragma unroll
-        for (int u = 0; u < kUnits; ++u) {
+        for (int u = 0; u < U; ++u) {
             uint4 q = ldg128(base + u * kUnitRows);
             v[u * 4 + 0] = q.x;
             v[u * 4 + 1] = q.y;
@@ -171,11 +172,11 @@ __device__ __forceinline__ void load_operand32(const DevOperand& o, int64_t thre
     }
 }
 
-// 16 rows of one relation: bit i = rel(a[i], b[i])
+// U * 4 rows of one relation: bit i = rel(a[i], b[i])
 #define MBC_CMP16(T, CONV, REL)                                                           \
     {                                                                                      \
         uint32_t m = 0;                                                                    \
-        _Pragma("unroll") for (int i = 0; i < kRowsPerThread; ++i) {                       \
+        _Pragma("unroll") for (int i = 0; i < U * kVec; ++i) {                             \
             T x = CONV(a[i]), y = CONV(b[i]);                                              \
             m |= (uint32_t)(x REL y) << i;                                                 \
         }                                                                                  \
@@ -186,10 +187,12 @@ __device__ __forceinline__ int32_t as_i32(uint32_t v) { return (int32_t)v; }
 
 // TupleUtils.java:48-57 (int) and :59-68 (float): 16 rows at once.  Bit u*4+j = row u*128+lane*4+j.
 // The operator switch is outside the row loop: one compare + one bit insert per row.
-__device__ __forceinline__ uint32_t eval_term32(const DevTerm& t, int64_t thread_row0, const uint32_t* stage, int tile_off) {
-    uint32_t a[kRowsPerThread], b[kRowsPerThread];
-    load_operand32(t.lhs, thread_row0, stage, tile_off, a);
-    load_operand32(t.rhs, thread_row0, stage, tile_off, b);
+template <int U = kUnits>
+__device__ __forceinline__ uint32_t eval_term32(const DevTerm& t, int64_t thread_row0, const uint32_t* stage, int tile_off,
+                                                const int stage_rows = kTileRows) {
+    uint32_t a[U * kVec], b[U * kVec];
+    load_operand32<U>(t.lhs, thread_row0, stage, tile_off, a, stage_rows);
+    load_operand32<U>(t.rhs, thread_row0, stage, tile_off, b, stage_rows);
     if (t.cmp_type == MBC_ATTR_INTEGER) {
         switch (t.op) {
             case MBC_OP_EQ: MBC_CMP16(int32_t, as_i32, ==)
@@ -227,6 +230,7 @@ __device__ __forceinline__ uint32_t str_word(const DevOperand& o, const uint32_t
 // without NUL bytes (the contract) unsigned byte order over the padded width is compareTo's order.
 // Rows are taken lane-contiguously (row = u*128 + k*32 + lane) and the 128 result bits of a unit
 // are transposed into the 4-rows-per-lane layout through ballots.
+template <int U = kUnits>
 __device__ __forceinline__ uint32_t eval_term_str(const DevTerm& t, int64_t warp_row0, int lane) {
     int wl = t.lhs.kind == 0 ? t.lit_words : (t.lhs.stride >> 2);
     int wr = t.rhs.kind == 0 ? t.lit_words : (t.rhs.stride >> 2);
@@ -235,7 +239,7 @@ __device__ __forceinline__ uint32_t eval_term_str(const DevTerm& t, int64_t warp
                         (t.lhs.kind != 0 ? t.lhs.stride : t.rhs.stride) == 16 && t.lit_words <= 4;
     uint32_t mask = 0;
 #pragma unroll
-    for (int u = 0; u < kUnits; ++u) {
+    for (int u = 0; u < U; ++u) {
         uint32_t bal[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -271,11 +275,12 @@ __device__ __forceinline__ uint32_t eval_term_str(const DevTerm& t, int64_t warp
 }
 
 // the 16 bits this thread owns out of a row bitmap (bit p = word p/32, bit p%32)
+template <int U = kUnits>
 __device__ __forceinline__ uint32_t load_bits(const uint32_t* bm, int64_t warp_row0, int lane) {
     uint32_t mask = 0;
     const uint32_t* w = bm + (warp_row0 >> 5) + (lane >> 3);
 #pragma unroll
-    for (int u = 0; u < kUnits; ++u) {
+    for (int u = 0; u < U; ++u) {
         uint32_t word = __ldg(w + u * (kUnitRows / 32));
         mask |= ((word >> ((lane & 7) * 4)) & 0xFu) << (u * 4);
     }

@@ -352,3 +352,98 @@ class Result:
         p, s = C.c_void_p(), C.c_int32()
         N.check(N.lib().mbc_result_column_device(self._h, i, C.byref(p), C.byref(s)))
         return int(p.value or 0), int(s.value)
+
+
+def device_stride(desc: tuple) -> int:
+    """Device row stride of a column (csrc/mbc_internal.cuh str_stride): 4 for int / real; char(W) rounded up to 4 below 16
+    bytes, to 16 above."""
+    t, w = desc
+    if t != N.ATTR_STRING:
+        return 4
+    return (w + 3) // 4 * 4 if w < 16 else (w + 15) // 16 * 16
+
+
+class Shard:
+    """One rank of a table sharded by position (TID) range over the GPUs of a node, through the mbc_shard_*
+    ABI: every rank scans its slice, then `gather` pushes its positions / projected columns / count / aggregates into the
+    root rank's window over NVLink peer memory (a kernel of libmbcol.so; no NCCL).  The root `collect`s.
+
+    Same process (one host driving several GPUs):    root = Shard(ctx0, 0, n); root.create_window(...);
+                                                     peer = Shard(ctx1, 1, n); peer.attach(root)
+    One process per GPU: the root's `create_window` returns 64 handle bytes that the host ships to the peers by any
+    channel (torch.distributed broadcast in bench.py; a socket or a file in a JVM), and the peers `open_window(handle)`."""
+
+    def __init__(self, ctx: Context, rank: int, world: int):
+        self.ctx, self.rank, self.world = ctx, rank, world
+        self._h = C.c_void_p()
+        N.check(N.lib().mbc_shard_create(ctx._h, rank, world, C.byref(self._h)))
+        self.proj_descs: list = []
+        self.capacity = 0
+
+    def close(self) -> None:
+        if self._h:
+            N.lib().mbc_shard_free(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _strides(self, proj_descs):
+        st = [device_stride(d) for d in proj_descs]
+        return (C.c_int32 * max(len(st), 1))(*st), len(st)
+
+    def create_window(self, capacity_rows: int, proj_descs: Sequence[tuple]) -> bytes:
+        arr, n = self._strides(proj_descs)
+        handle = (C.c_uint8 * N.IPC_HANDLE_BYTES)()
+        N.check(N.lib().mbc_shard_window_create(self._h, capacity_rows, n, arr, handle))
+        self.proj_descs, self.capacity = list(proj_descs), capacity_rows
+        return bytes(handle)
+
+    def open_window(self, handle: bytes, capacity_rows: int, proj_descs: Sequence[tuple]) -> None:
+        arr, n = self._strides(proj_descs)
+        h = (C.c_uint8 * N.IPC_HANDLE_BYTES)(*handle)
+        N.check(N.lib().mbc_shard_window_open(self._h, h, capacity_rows, n, arr))
+        self.proj_descs, self.capacity = list(proj_descs), capacity_rows
+
+    def attach(self, root: "Shard") -> None:
+        N.check(N.lib().mbc_shard_window_attach(self._h, root._h))
+        self.proj_descs, self.capacity = list(root.proj_descs), root.capacity
+
+    def gather(self, result: "Result", beside_next_scan: bool = False) -> None:
+        N.check(N.lib().mbc_shard_gather(self._h, result._h, 1 if beside_next_scan else 0))
+
+    def fence(self) -> None:
+        N.check(N.lib().mbc_shard_fence(self._h))
+
+    def collect(self) -> tuple:
+        """Root: wait for every rank's rows of the last gathered step -> (total rows, [rows per rank])."""
+        total = C.c_int64()
+        counts = (C.c_int64 * self.world)()
+        N.check(N.lib().mbc_shard_collect(self._h, C.byref(total), counts))
+        return int(total.value), [int(x) for x in counts]
+
+    def agg(self, i: int, kind: int, col_type: int):
+        """Aggregate i folded over the ranks -> (int64 value, float64 value, valid)."""
+        a, f, v = C.c_int64(), C.c_double(), C.c_int32()
+        N.check(N.lib().mbc_shard_agg(self._h, i, kind, col_type, C.byref(a), C.byref(f), C.byref(v)))
+        return int(a.value), float(f.value), bool(v.value)
+
+    def positions(self, first: int, n: int) -> np.ndarray:
+        out = np.empty(n, dtype=np.int64)
+        N.check(N.lib().mbc_shard_read(self._h, -1, first, n, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def column(self, i: int, first: int, n: int) -> np.ndarray:
+        t, w = self.proj_descs[i]
+        st = device_stride((t, w))
+        raw = np.empty(n * st, dtype=np.uint8)
+        N.check(N.lib().mbc_shard_read(self._h, i, first, n, raw.ctypes.data_as(C.c_void_p)))
+        if t == N.ATTR_STRING:
+            return raw.reshape(n, st)[:, :w]
+        return raw.view(np.int32 if t == N.ATTR_INTEGER else np.float32)
+
+    def release(self) -> None:
+        N.check(N.lib().mbc_shard_release(self._h))

@@ -153,3 +153,19 @@ def test_bitmap_scan_without_index_fails_loudly(ctx, oracle):
         t.bitmap_scan([oracle.Term(0, ("col", 0), ("int", 5), 0)], want=N.WANT_POSITIONS)
     assert ei.value.status == N.ERR_NOINDEX
     t.close()
+
+
+@pytest.mark.parametrize("nrows", [8191, 8193, 20_001, 100_003])
+def test_few_values_away_from_zero_ragged_tail(ctx, oracle, nrows):
+    """<= 32 distinct values that do not include 0 and do not fill their range, no deleted rows, nrows not a multiple of the
+    8192-row build chunk: the ragged last chunk sees the column's zero padding, which lies outside [kmin, kmax] and must
+    not be looked up in the value -> id table (round 1 read ~16 GB past it)."""
+    rng = np.random.default_rng(nrows)
+    for values in ([10, 20, 30], [-70000 + 65535, -70000], [5, 6, 9, 1000, 40000]):
+        col = rng.choice(np.array(values, dtype=np.int32), nrows).astype(np.int32)
+        other = rng.integers(0, 3, nrows).astype(np.int32)
+        descs = [(1, 4), (1, 4)]
+        t = load_table(ctx, descs, [col, other])
+        t.bitmap_build(0)
+        _check_index(oracle, t, 0, descs[0], col)
+        t.close()
