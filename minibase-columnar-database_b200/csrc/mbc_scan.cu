@@ -298,16 +298,13 @@ static void plan_fused(mbc_ctx* ctx, ScanJob* job) {
     if (!need_write) return;                                       // COUNT alone: pass 1 + the offsets kernel is all there is to do
     if (ctx->fused_smem_budget < 0) {                              // once per context: opt in to the large shared memory carve-out
         ctx->fused_smem_budget = 0;
-        int per_sm = 0, reserved = 0, optin = 0, coop = 0;
+        int reserved = 0, optin = 0, coop = 0;
         cudaFuncAttributes fa;
-        if (cudaDeviceGetAttribute(&per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, ctx->device) == cudaSuccess &&
-            cudaDeviceGetAttribute(&reserved, cudaDevAttrReservedSharedMemoryPerBlock, ctx->device) == cudaSuccess &&
+        if (cudaDeviceGetAttribute(&reserved, cudaDevAttrReservedSharedMemoryPerBlock, ctx->device) == cudaSuccess &&
             cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device) == cudaSuccess &&
             cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device) == cudaSuccess && coop &&
             cudaFuncGetAttributes(&fa, fused_scan_kernel) == cudaSuccess) {
-            // kFCtasPerSm CTAs share the SM's shared memory; each also pays its static arrays and the per-block reserve
-            int budget = std::min(optin, per_sm / kFCtasPerSm - reserved) - (int)fa.sharedSizeBytes;
-            budget = budget / 1024 * 1024;
+            const int budget = (optin - (int)fa.sharedSizeBytes) / 1024 * 1024;   // one CTA per SM: everything the SM has
             if (budget > 0 && cudaFuncSetAttribute(fused_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, budget) == cudaSuccess)
                 ctx->fused_smem_budget = budget;
         }
@@ -339,21 +336,22 @@ static void plan_fused(mbc_ctx* ctx, ScanJob* job) {
         f.agg_pay[a] = (int8_t)k;
     }
     const int pred_stage = p.nstaged * kFPredColBytes, pay_stage = f.pay_stage_bytes;
-    // Ring depths.  The payload ring needs 2 stages (one tile loading while another is written); the predicate ring takes the
-    // rest: a sparse scan streams the predicate columns alone and wants as many of them in flight as the filter pass has.
+    // Ring depths.  The payload ring takes 3 stages when they fit (one tile being written, two loading: ~110 KB in flight
+    // per SM for the C2 row), the predicate ring the rest; a scan that fetches nothing per row gives it all to the predicates.
     int P = 2, S = 0;
     if (f.npay) {
-        S = std::min(2, (budget - 2 * pred_stage) / pay_stage);
-        if (S < 1) return;                                         // rows too wide for a shared-memory tile
+        S = std::min(3, (budget - 2 * pred_stage) / pay_stage);
+        if (S < 2) return;                                         // rows too wide for a double-buffered shared-memory tile
     }
-    if (const char* e = getenv("MBC_FUSED_PAY_STAGES")) S = f.npay ? std::max(1, std::min(kFMaxPayStages, atoi(e))) : 0;
+    if (const char* e = getenv("MBC_FUSED_PAY_STAGES")) S = f.npay ? std::max(2, std::min(kFMaxPayStages, atoi(e))) : 0;
     if (pred_stage) P = std::max(2, std::min(kFMaxPredStages, (budget - S * pay_stage) / pred_stage));
     if (const char* e = getenv("MBC_FUSED_PRED_STAGES")) P = std::max(2, std::min(kFMaxPredStages, atoi(e)));
-    if ((size_t)P * pred_stage + (size_t)S * pay_stage > (size_t)budget) return;
+    // every predicate stage belongs to ONE count group (tile i -> stage i % P, group i % kFGroups): a waiter never sees a stage
+    // whose previous phase was another group's (mbarrier parity waits cannot tell "two phases behind" from "done")
+    P = P / kFGroups * kFGroups;
+    if (P < kFGroups || (size_t)P * pred_stage + (size_t)S * pay_stage > (size_t)budget) return;
     f.pred_stages = P;
     f.pay_stages = S;
-    f.ahead = 2;                                                   // tiles between a count's publication and its use
-    if (const char* e = getenv("MBC_FUSED_AHEAD")) f.ahead = std::max(0, std::min(kFMaxAhead, atoi(e)));
     f.dense_min = kFR / 16;                                        // below 1 survivor in 16 rows a batched gather moves fewer bytes
     if (const char* e = getenv("MBC_FUSED_DENSE_MIN")) f.dense_min = atoi(e);
     f.dense_min = std::max(1, std::min(f.dense_min, kFPendCap / 2));
@@ -363,12 +361,13 @@ static void plan_fused(mbc_ctx* ctx, ScanJob* job) {
         cudaGetLastError();
         return;
     }
-    job->fused_ctas_per_sm = std::min(per_sm, kFCtasPerSm);
+    job->fused_ctas_per_sm = 1;
     job->fused_ok = true;
 }
 
 // published-count buffer of the fused engine: grown (zero filled) on demand, never cleared between launches
 static int32_t fused_flags_for(mbc_ctx* ctx, int64_t ntiles, uint32_t** flags, uint32_t* epoch) {
+    ntiles += kFMaxGrid;                                           // the control warps bulk-copy whole waves: one wave of padding
     if (ctx->fused_flags_cap < ntiles) {
         if (ctx->fused_flags) {
             MBC_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -436,6 +435,7 @@ static int32_t prepare_job(const mbc_table* schema, const ScanRequest& rq, int64
     p.tile_out = job->w.tile_out;
     p.partials = job->w.partials;
     p.out_pos = r->d_pos;
+    p.out_cap = capacity_rows;
     p.ntiles = INT32_MAX;                         // the grid bound comes from the device; bind_table sets the real count
     MBC_TRY(plan_staging(ctx, &p, &job->smem_bytes, &job->max_grid));
     plan_fused(ctx, job);
@@ -477,25 +477,42 @@ static int32_t launch_job(ScanJob* job, bool first) {
         for (int c = 0; c < p.nproj; ++c) f.pay_src[f.proj_pay[c]] = p.proj[c].src;
         for (int a = 0; a < p.nagg; ++a)
             if (f.agg_pay[a] >= 0) f.pay_src[f.agg_pay[a]] = p.aggs[a].src;
-        const int grid = (int)std::min<int64_t>(ntiles, std::min(ctx->sm_count * job->fused_ctas_per_sm, 32 * kFWaveRegs));
+        int grid = (int)std::min<int64_t>(ntiles, std::min(ctx->sm_count, kFMaxGrid));
+        if (grid >= 4) grid &= ~3;                                  // a wave of published counts is a 16-byte multiple
         const bool prof = getenv("MBC_FUSED_PROF") != nullptr;      // per-role wait cycles of every CTA, averaged, on stderr
         f.prof = nullptr;
-        if (prof) MBC_TRY(dev_alloc(ctx, (void**)&f.prof, (size_t)grid * 16 * 8, true));
+        if (prof) MBC_TRY(dev_alloc(ctx, (void**)&f.prof, (size_t)grid * 24 * 8, true));
+        f.dbg = nullptr;
+#ifdef MBC_FUSED_DEBUG
+        static long long* h_dbg = nullptr;                          // host-mapped: survives a faulting kernel
+        if (!h_dbg && cudaHostAlloc((void**)&h_dbg, 64, cudaHostAllocMapped) == cudaSuccess) memset(h_dbg, 0, 64);
+        if (h_dbg) {
+            if (h_dbg[0]) fprintf(stderr, "[fused check] EARLIER launch: line %lld cta %lld thread %lld values %lld %lld %lld %lld\n", h_dbg[0], h_dbg[1],
+                                  h_dbg[2], h_dbg[3], h_dbg[4], h_dbg[5], h_dbg[6]);
+            cudaHostGetDevicePointer((void**)&f.dbg, h_dbg, 0);
+        }
+#endif
         void* args[] = {(void*)&p, (void*)&f};
         MBC_CUDA(cudaLaunchCooperativeKernel((const void*)fused_scan_kernel, dim3(grid), dim3(kFThreads), args, job->fused_smem, ctx->stream));
+#ifdef MBC_FUSED_DEBUG
+        if (cudaStreamSynchronize(ctx->stream) != cudaSuccess && h_dbg)
+            fprintf(stderr, "[fused check] line %lld cta %lld thread %lld values %lld %lld %lld %lld (grid %d P %d S %d ntiles %lld)\n", h_dbg[0], h_dbg[1], h_dbg[2],
+                    h_dbg[3], h_dbg[4], h_dbg[5], h_dbg[6], grid, f.pred_stages, f.pay_stages, (long long)ntiles);
+#endif
         if (prof) {
-            std::vector<long long> h((size_t)grid * 16);
+            std::vector<long long> h((size_t)grid * 24);
             MBC_CUDA(cudaMemcpyAsync(h.data(), f.prof, h.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
             MBC_CUDA(cudaStreamSynchronize(ctx->stream));
             dev_free(ctx, f.prof);
-            double m[16] = {0};
+            double m[24] = {0};
             for (int c = 0; c < grid; ++c)
-                for (int k = 0; k < 16; ++k) m[k] += (double)h[(size_t)c * 16 + k] / grid;
+                for (int k = 0; k < 24; ++k) m[k] += (double)h[(size_t)c * 24 + k] / grid;
             fprintf(stderr,
-                    "[fused prof] tiles/cta %.1f grid %d P %d S %d ahead %d dense_min %d | total %.0f: pred-wait %.0f count %.0f flags %.0f ctl %.0f "
-                    "rank %.0f payfull-wait %.0f dense+other %.0f sparse %.0f flush %.0f | dense tiles/cta %.1f (cycles of thread 0, mean over CTAs)\n",
-                    (double)ntiles / grid, grid, f.pred_stages, f.pay_stages, f.ahead, f.dense_min, m[0], m[1], m[2], m[3], m[4], m[5], m[6], m[7],
-                    m[8], m[9], m[10]);
+                    "[fused prof] tiles/cta %.1f grid %d P %d S %d dense_min %d | control: total %.0f flag-wait %.0f sum+stale %.0f payfree-wait %.0f "
+                    "dense %.1f stale waves %.1f | count(g0): total %.0f maskfree-wait %.0f pred-wait %.0f eval %.0f | write: total %.0f "
+                    "maskready-wait %.0f ctl-wait %.0f rank %.0f payfull-wait %.0f dense+other %.0f sparse %.0f flush %.0f (cycles, mean over CTAs)\n",
+                    (double)ntiles / grid, grid, f.pred_stages, f.pay_stages, f.dense_min, m[0], m[1], m[2], m[3], m[4], m[5], m[8], m[9], m[10],
+                    m[11], m[12], m[13], m[14], m[15], m[16], m[17], m[18], m[19]);
         }
         job->launches++;
         ctx->launches++;

@@ -79,6 +79,7 @@ constexpr int kStageColBytes = kTileRows * 4;    // one column of one tile: 16 K
 struct ScanParams {
     int64_t nrows;
     int64_t pos_base;
+    int64_t out_cap;              // rows the output buffers hold (debug checks)
     int32_t ntiles;
     int32_t nterms;
     int32_t nproj;

@@ -725,6 +725,11 @@ class DBWriter:
         out = bytearray(top * PAGE)
         for pid, b in self.pages.items():
             out[pid * PAGE:(pid + 1) * PAGE] = b
+        # the space map (pages 1..): bit p of the map = page p allocated, least significant bit first (DB.java:739-822);
+        # openDB marks page 0 and the map pages (:104-106), allocate_page every page handed out since
+        for pid in range(top):
+            at = PAGE * (1 + pid // (PAGE * 8)) + (pid % (PAGE * 8)) // 8
+            out[at] |= 1 << (pid % 8)
         return bytes(out)
 
 
@@ -747,7 +752,7 @@ class HeapfileWriter:
             data = _HFPage(self.db.alloc())
             self.db.pages[data.pid] = data.b
             d = self.dirs[-1]
-            info = struct.pack(">hhi", data.free, 0, data.pid)
+            info = struct.pack(">hhi", data.free - 4, 0, data.pid)      # DataPageInfo.availspace = HFPage.available_space() (Heapfile.java:89)
             slot = d.insert(info)
             if slot is None:
                 nd = _HFPage(self.db.alloc())
@@ -761,7 +766,7 @@ class HeapfileWriter:
         slot = self.cur_data.insert(rec)
         self.recct += 1
         d, s = self.cur_info
-        d.update(s, struct.pack(">hhi", self.cur_data.free, self.recct, self.cur_data.pid))
+        d.update(s, struct.pack(">hhi", self.cur_data.free - 4, self.recct, self.cur_data.pid))
         return self.cur_data.pid, slot
 
 
