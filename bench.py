@@ -536,6 +536,13 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         dist.destroy_process_group()
 
 
+class _CudaArray:
+    """__cuda_array_interface__ view of library-owned device memory (tests and scripts wrap it with torch.as_tensor)."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3}
+
+
 def scan_host_rows(ctx, mbcol, wl, host_cols, rows, terms, want, position_base):
     """Context.scan_host with the row count given explicitly (untouched columns are passed as a dummy buffer)."""
     import ctypes as C

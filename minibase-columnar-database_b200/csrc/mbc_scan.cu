@@ -271,6 +271,8 @@ struct ScanJob {
     int64_t part_slots = 0;       // capacity (= stride) of the per-tile aggregate partials: one slot per tile of either engine
     int64_t part_done = 0;        // slots written by the launches so far
     size_t smem_bytes = 0;
+    size_t write_smem = 0;        // dynamic shared memory of the write pass (staging of the streaming dense path)
+    bool stream_forced = false;   // MBC_STREAM_MIN_PCT set: the streaming path is armed whatever the density hint says
     int max_grid = 1;
     int launches = 0;             // launches so far: the running count is in slot launches & 1
     // single-residency engine (mbc_scan_fused.cuh): planned once per job, chosen per launch
@@ -284,12 +286,50 @@ struct ScanJob {
 };
 
 
+// Streaming dense write path (write_dense_tile_stream): the compacted values of 1024 rows of every projected field are
+// staged in shared memory, back to back.  Falls back to the gather path when a projected row is too wide.
+static void plan_stream(mbc_ctx* ctx, ScanJob* job) {
+    ScanParams& p = job->p;
+    p.stream_dense = 0;
+    job->write_smem = 0;
+    const char* e = getenv("MBC_WRITE_STREAM");                    // "0": the gather path of round 1 (tests, profiles)
+    if (e && !strcmp(e, "0")) return;
+    size_t off = 0;
+    for (int c = 0; c < p.nproj; ++c) {
+        if (p.proj[c].stride & 3) return;
+        p.stage_off[c] = (int32_t)off;
+        off += (size_t)p.proj[c].stride * kSubRows;
+    }
+    if (off > (size_t)kStreamStageMax) return;
+    if (!ctx->write_smem_set) {                                    // per device: opt in to > 48 KB of dynamic shared memory
+        if (cudaFuncSetAttribute(write_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStreamStageMax) != cudaSuccess ||
+            cudaFuncSetAttribute(write_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStreamStageMax) != cudaSuccess) {
+            cudaGetLastError();
+            return;
+        }
+        ctx->write_smem_set = true;
+    }
+    p.stream_dense = 1;
+    // measured on B200 (100 M C2 rows): the gather path wins up to ~3/4 filled groups (0.93 vs 1.24 ms at 50 %), streaming
+    // above (1.42 vs 1.66 ms at 90 %): it moves exactly the algorithmic bytes but pays two barriers per 1024 rows
+    p.stream_min = kGroupRows * 3 / 4;
+    if (const char* m = getenv("MBC_STREAM_MIN_PCT")) {
+        p.stream_min = (int)((long long)kGroupRows * std::max(0, std::min(100, atoi(m))) / 100);
+        job->stream_forced = true;
+    }
+    job->write_smem = off;
+}
+
 // Plan the single-residency engine (mbc_scan_fused.cuh) for this job: payload columns, ring depths, shared memory.
 // Leaves job->fused_ok false when the scan does not fit it; every launch then takes the two-pass engine.
 static void plan_fused(mbc_ctx* ctx, ScanJob* job) {
     job->fused_ok = false;
-    const char* path = getenv("MBC_SCAN_PATH");                   // "twopass" / "fused": tests and profiles force either engine
-    if (path && !strcmp(path, "twopass")) return;
+    // MBC_SCAN_PATH=fused opts in (tests, profiles).  Measured on B200 (profiles/README.md): the two-pass engine with the
+    // streaming dense write path is faster at every selectivity so far -- the fused kernel's three roles each sit close to
+    // the per-tile HBM time (term-program interpretation in the count warps, the ~2 us L2 round trip of the published
+    // counts while HBM is saturated, ~800 instructions per tile and warp in the write warps), so it is not the default.
+    const char* path = getenv("MBC_SCAN_PATH");
+    if (!path || strcmp(path, "fused")) return;
     ScanParams& p = job->p;
     FusedParams& f = job->f;
     memset(&f, 0, sizeof(f));
@@ -438,6 +478,7 @@ static int32_t prepare_job(const mbc_table* schema, const ScanRequest& rq, int64
     p.out_cap = capacity_rows;
     p.ntiles = INT32_MAX;                         // the grid bound comes from the device; bind_table sets the real count
     MBC_TRY(plan_staging(ctx, &p, &job->smem_bytes, &job->max_grid));
+    plan_stream(ctx, job);
     plan_fused(ctx, job);
     return MBC_OK;
 }
@@ -537,6 +578,13 @@ static int32_t launch_job(ScanJob* job, bool first) {
     bool need_write = p.out_pos || p.nproj > 0;
     for (int a = 0; a < p.nagg; ++a) need_write |= p.aggs[a].kind != MBC_AGG_COUNT;   // COUNT comes from the tile offsets
     if (need_write) {
+        // The streaming dense path costs every CTA of the write pass 28 KB of shared memory (and the SM that much L1): it is
+        // armed only when the last completed scan of this context was dense (>= 60 % of its rows qualified) or when the
+        // threshold is forced.  Either way the result is the same; a wrong guess leaves dense groups to the gather path.
+        const bool stream_now = p.stream_dense && (job->stream_forced || ctx->density_hint >= 0.6f);
+        const int stream_saved = p.stream_dense;
+        const size_t write_smem = stream_now ? job->write_smem : 0;
+        if (!stream_now) p.stream_dense = 0;
         const char* pt = getenv("MBC_WRITE_PERSISTENT_TILES");          // tests force either form
         const int persistent_min_tiles = pt ? atoi(pt) : 49152;
         if (p.ntiles >= persistent_min_tiles) {
@@ -544,10 +592,15 @@ static int32_t launch_job(ScanJob* job, bool first) {
             if (!ctas_per_sm &&
                 (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, write_kernel<true>, kScanThreads, 0) != cudaSuccess || ctas_per_sm < 1))
                 ctas_per_sm = 1;
-            write_kernel<true><<<std::min(p.ntiles, ctx->sm_count * ctas_per_sm), kScanThreads, 0, ctx->stream>>>(p);
+            int per_sm = ctas_per_sm;
+            if (write_smem &&
+                (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, write_kernel<true>, kScanThreads, write_smem) != cudaSuccess || per_sm < 1))
+                per_sm = 1;
+            write_kernel<true><<<std::min(p.ntiles, ctx->sm_count * per_sm), kScanThreads, write_smem, ctx->stream>>>(p);
         } else {
-            write_kernel<false><<<p.ntiles, kScanThreads, 0, ctx->stream>>>(p);
+            write_kernel<false><<<p.ntiles, kScanThreads, write_smem, ctx->stream>>>(p);
         }
+        p.stream_dense = stream_saved;
         ctx->launches++;
     }
     if (job->r->ev_mid[2]) cudaEventRecord(job->r->ev_mid[2], ctx->stream);
@@ -598,6 +651,7 @@ static int32_t finish_job_device(ScanJob* job, bool deferred = false) {
     MBC_CUDA(cudaMemcpyAsync(host_small, r->d_aggs, sizeof(host_small), cudaMemcpyDeviceToHost, ctx->stream));
     MBC_CUDA(cudaStreamSynchronize(ctx->stream));
     r->count = (int64_t)host_small[kMaxAgg];
+    if (r->nrows > 0) ctx->density_hint = (float)((double)r->count / (double)r->nrows);
     decode_aggs(r, p.aggs, p.nagg, host_small);
     if (r->ev_t0 && r->ev_t1 && cudaEventElapsedTime(&r->kernel_ms, r->ev_t0, r->ev_t1) != cudaSuccess) r->kernel_ms = -1.f;
     result_phase_times(r);
@@ -811,6 +865,7 @@ static int32_t run_scan_host(mbc_ctx* ctx, int32_t ncols, const mbc_coldesc* col
         st->pos_base = position_base + row0;
         bind_table(&job, st);
         job.fused_off = late_mode;
+        if (late_mode) job.p.stream_dense = 0;                            // whole-tile loads would pull every row over PCIe
         if (late_mode) {                                                  // survivors of these columns come from host memory
             ScanParams& p = job.p;
             for (int c = 0; c < p.nproj; ++c)

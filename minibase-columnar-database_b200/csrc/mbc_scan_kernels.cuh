@@ -80,6 +80,9 @@ struct ScanParams {
     int64_t nrows;
     int64_t pos_base;
     int64_t out_cap;              // rows the output buffers hold (debug checks)
+    int32_t stream_dense;         // 1: the tiles of well-filled groups are streamed through the staging of write_dense_tile_stream
+    int32_t stream_min;           // ... groups of kGroupTiles tiles with at least this many survivors; sparser dense groups are gathered
+    int32_t stage_off[kMaxProj];  // byte offset of every projected field's compacted values in that staging
     int32_t ntiles;
     int32_t nterms;
     int32_t nproj;
@@ -724,6 +727,185 @@ __device__ __forceinline__ void write_dense_tile(const ScanParams& p, const int 
     }
 }
 
+// One tile of a dense group, STREAMED: the tile is taken 1024 rows at a time; every thread loads the values of its 4
+// consecutive rows with 128-bit coalesced loads (each projected column is read whole, once: no gathers, no 64..128-byte
+// DRAM fetch around a 4-byte value), ranks its survivors with a block scan of the selection nibbles, drops the survivors'
+// values at their ranks in a shared-memory staging area, and the CTA copies the compacted rows out with coalesced stores.
+// Aggregates are folded from the registers that hold the loaded values.  Replaces the rank -> row list + per-survivor
+// gather of write_dense_tile for scans whose projected row fits the staging area (<= kStreamStageMax bytes per 1024 rows).
+constexpr int kSubRows = kScanThreads * kVec;                      // 1024 rows per step
+constexpr int kStreamStageMax = 64 * 1024;
+
+__device__ __forceinline__ void agg_fold4(const DevAgg& g, unsigned long long& acc, const uint4 v, uint32_t bits) {
+    const uint32_t x[4] = {v.x, v.y, v.z, v.w};
+    if (g.type == MBC_ATTR_INTEGER) {
+        long long a = (long long)acc;
+        if (g.kind == MBC_AGG_SUM) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) a += ((bits >> j) & 1u) ? (long long)(int32_t)x[j] : 0ll;
+        } else if (g.kind == MBC_AGG_MIN) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) if ((bits >> j) & 1u) a = min(a, (long long)(int32_t)x[j]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) if ((bits >> j) & 1u) a = max(a, (long long)(int32_t)x[j]);
+        }
+        acc = (unsigned long long)a;
+    } else {
+        double a = __longlong_as_double((long long)acc);
+        if (g.kind == MBC_AGG_SUM) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) if ((bits >> j) & 1u) a += (double)__uint_as_float(x[j]);
+        } else if (g.kind == MBC_AGG_MIN) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) if ((bits >> j) & 1u) a = fmin(a, (double)__uint_as_float(x[j]));
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) if ((bits >> j) & 1u) a = fmax(a, (double)__uint_as_float(x[j]));
+        }
+        acc = (unsigned long long)__double_as_longlong(a);
+    }
+}
+
+__device__ __forceinline__ void write_dense_tile_stream(const ScanParams& p, const int tile, uint8_t* s_stage, uint16_t* s_list, uint32_t* s_wtot,
+                                                        unsigned long long (*s_aggw)[kWarpsPerCta]) {
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    const int T = (int)p.tile_counts[tile];
+    if (T == 0) {                                                  // block-uniform: nothing qualifies in this tile
+        if (tid < p.nagg) p.partials[(size_t)tid * p.total_tiles + p.tile_base + tile] = agg_identity(p.aggs[tid]);
+        return;
+    }
+    long long base = (long long)p.tile_out[tile];
+    unsigned long long acc[kMaxAgg];
+#pragma unroll
+    for (int a = 0; a < kMaxAgg; ++a) acc[a] = a < p.nagg ? agg_identity(p.aggs[a]) : 0ull;
+    for (int sub = 0; sub < kTileRows / kSubRows; ++sub) {
+        const int64_t row0 = (int64_t)tile * kTileRows + sub * kSubRows;   // rows past the table hold no set bits
+        const int64_t my_row = row0 + tid * kVec;
+        const uint32_t bits = (__ldg(p.out_bitmap + (row0 >> 5) + (tid >> 3)) >> ((tid & 7) * 4)) & 0xFu;
+        // rank of this thread's first survivor among the step's survivors
+        const int cnt = __popc(bits);
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int n = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if (lane >= o) incl += n;
+        }
+        if (lane == 31) s_wtot[warp] = (uint32_t)incl;
+        __syncthreads();                                           // also: the previous step's copy-out is complete
+        uint32_t below = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < kWarpsPerCta; ++w) {
+            const uint32_t t = s_wtot[w];
+            total += t;
+            if (w < warp) below += t;
+        }
+        const int Ts = (int)total;
+        if (Ts == 0) { __syncthreads(); continue; }                // block-uniform
+        const int r0 = (int)below + incl - cnt;
+        if (p.out_pos) {
+            int r = r0;
+#pragma unroll
+            for (int j = 0; j < kVec; ++j)
+                if ((bits >> j) & 1u) s_list[r++] = (uint16_t)(tid * kVec + j);
+        }
+        for (int c = 0; c < p.nproj; ++c) {                        // iterator/Projection.java:103-144
+            const DevProj& pr = p.proj[c];
+            uint8_t* st = s_stage + p.stage_off[c];
+            if (pr.stride == 4) {
+                const uint4 v = ldg128(reinterpret_cast<const uint32_t*>(pr.src) + my_row);
+                const uint32_t x[4] = {v.x, v.y, v.z, v.w};
+                int r = r0;
+#pragma unroll
+                for (int j = 0; j < kVec; ++j)
+                    if ((bits >> j) & 1u) reinterpret_cast<uint32_t*>(st)[r++] = x[j];
+            } else if (pr.stride == 16) {
+                uint4 v[kVec];
+#pragma unroll
+                for (int j = 0; j < kVec; ++j) v[j] = ldg128(reinterpret_cast<const uint4*>(pr.src) + my_row + j);
+                int r = r0;
+#pragma unroll
+                for (int j = 0; j < kVec; ++j)
+                    if ((bits >> j) & 1u) reinterpret_cast<uint4*>(st)[r++] = v[j];
+            } else {
+                const int words = pr.stride >> 2;
+                int r = r0;
+                for (int j = 0; j < kVec; ++j) {
+                    if (!((bits >> j) & 1u)) continue;
+                    const uint32_t* src = reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(pr.src) + (my_row + j) * pr.stride);
+                    uint32_t* d = reinterpret_cast<uint32_t*>(st + (size_t)r * pr.stride);
+                    for (int w = 0; w < words; ++w) d[w] = __ldg(src + w);
+                    ++r;
+                }
+            }
+        }
+#pragma unroll
+        for (int a = 0; a < kMaxAgg; ++a) {                        // folded from the loaded values (a projected column's lines are in L1)
+            if (a >= p.nagg) break;
+            const DevAgg& g = p.aggs[a];
+            if (g.kind == MBC_AGG_COUNT) continue;
+            agg_fold4(g, acc[a], ldg128(reinterpret_cast<const uint32_t*>(g.src) + my_row), bits);
+        }
+        __syncthreads();                                           // the step's survivors are staged
+        // copy-out: thread t takes ranks t, t + 256, t + 512, t + 768 (Ts <= 1024): four predicated, coalesced stores per field
+        if (p.out_pos) {
+            int64_t* dst = p.out_pos + base + tid;
+            const int64_t pos0 = p.pos_base + row0;
+#pragma unroll
+            for (int i = 0; i < kVec; ++i)
+                if (tid + i * kScanThreads < Ts) dst[i * kScanThreads] = pos0 + s_list[tid + i * kScanThreads];
+        }
+        for (int c = 0; c < p.nproj; ++c) {
+            const DevProj& pr = p.proj[c];
+            const uint8_t* st = s_stage + p.stage_off[c];
+            if (pr.stride == 4) {
+                uint32_t* dst = reinterpret_cast<uint32_t*>(pr.dst) + base + tid;
+                const uint32_t* src = reinterpret_cast<const uint32_t*>(st) + tid;
+#pragma unroll
+                for (int i = 0; i < kVec; ++i)
+                    if (tid + i * kScanThreads < Ts) dst[i * kScanThreads] = src[i * kScanThreads];
+            } else if (pr.stride == 16) {
+                uint4* dst = reinterpret_cast<uint4*>(pr.dst) + base + tid;
+                const uint4* src = reinterpret_cast<const uint4*>(st) + tid;
+#pragma unroll
+                for (int i = 0; i < kVec; ++i)
+                    if (tid + i * kScanThreads < Ts) dst[i * kScanThreads] = src[i * kScanThreads];
+            } else {
+                const int words = Ts * (pr.stride >> 2);
+                uint32_t* dst = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(pr.dst) + base * pr.stride);
+                for (int k = tid; k < words; k += kScanThreads) dst[k] = reinterpret_cast<const uint32_t*>(st)[k];
+            }
+        }
+        base += Ts;
+    }
+    // the tile's aggregate partial: lanes butterflied, warps combined in order
+    if (p.nagg > 0) {
+#pragma unroll
+        for (int a = 0; a < kMaxAgg; ++a) {
+            if (a >= p.nagg) break;
+            const DevAgg& g = p.aggs[a];
+            unsigned long long v = acc[a];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v = agg_merge(g, v, __shfl_xor_sync(0xFFFFFFFFu, v, o));
+            if (lane == 0) s_aggw[a][warp] = v;
+        }
+        __syncthreads();
+        if (tid < p.nagg) {
+            const DevAgg& g = p.aggs[tid];
+            unsigned long long v;
+            if (g.kind == MBC_AGG_COUNT) {
+                v = (unsigned long long)T;
+            } else {
+                v = s_aggw[tid][0];
+                for (int x = 1; x < kWarpsPerCta; ++x) v = agg_merge(g, v, s_aggw[tid][x]);
+            }
+            p.partials[(size_t)tid * p.total_tiles + p.tile_base + tile] = v;
+        }
+    }
+}
+
 // A sparse group (0 < total <= kSparseMax survivors in ntl tiles from tile0), written by one CTA.
 __device__ __forceinline__ void write_sparse_group(const ScanParams& p, const int tile0, const int ntl, const long long base, const int total,
                                                    uint16_t* s_list, uint32_t* s_wtot) {
@@ -799,6 +981,7 @@ __device__ __forceinline__ void write_sparse_group(const ScanParams& p, const in
 
 template <bool kPersistent>
 __global__ void __launch_bounds__(kScanThreads, MBC_WRITE_MIN_CTAS) write_kernel(const __grid_constant__ ScanParams p) {
+    extern __shared__ __align__(16) uint8_t s_stage[];             // staging of write_dense_tile_stream (p.stream_dense)
     __shared__ uint16_t s_list[kListCap];                          // survivor rows within the group / tile, by rank
     __shared__ uint32_t s_wtot[kWarpsPerCta];
     __shared__ unsigned long long s_aggw[kMaxAgg][kWarpsPerCta];
@@ -851,7 +1034,11 @@ __global__ void __launch_bounds__(kScanThreads, MBC_WRITE_MIN_CTAS) write_kernel
         for (int j = 0; j < n; ++j) {
             if (!((s_flags[j >> 5] >> (j & 31)) & 1u)) continue;   // block-uniform
             __syncthreads();                                       // the shared arrays are reused from tile to tile
-            write_dense_tile(p, blockIdx.x + (it0 + j) * gridDim.x, s_list, s_wtot, s_aggw);
+            const int tl = blockIdx.x + (it0 + j) * gridDim.x;
+            const int g0 = tl & ~(kGroupTiles - 1);
+            const long long gtot = (long long)(p.tile_out[g0 + min(kGroupTiles, p.ntiles - g0)] - p.tile_out[g0]);
+            if (p.stream_dense && gtot >= p.stream_min) write_dense_tile_stream(p, tl, s_stage, s_list, s_wtot, s_aggw);
+            else write_dense_tile(p, tl, s_list, s_wtot, s_aggw);
         }
     }
   } else {
@@ -862,7 +1049,8 @@ __global__ void __launch_bounds__(kScanThreads, MBC_WRITE_MIN_CTAS) write_kernel
     const long long base = (long long)p.tile_out[tile0];
     const int total = (int)((long long)p.tile_out[tile0 + ntl] - base);
     if (total > kSparseMax) {                                      // block-uniform: dense group, every CTA writes its own tile
-        write_dense_tile(p, tile, s_list, s_wtot, s_aggw);
+        if (p.stream_dense && total >= p.stream_min) write_dense_tile_stream(p, tile, s_stage, s_list, s_wtot, s_aggw);
+        else write_dense_tile(p, tile, s_list, s_wtot, s_aggw);
         return;
     }
     // sparse group: its first CTA writes all of it; one partial for the group, the other tiles carry the identity

@@ -1,9 +1,9 @@
-"""Both scan engines of libmbcol.so against the CPU oracle, through the C ABI.
+"""Every scan engine of libmbcol.so against the CPU oracle, through the C ABI.
 
-`mbc_scan` has two engines: the single-residency one (mbc_scan_fused.cuh: count warps ahead, offsets from published
-tile counts, compaction out of shared memory; default when the projected columns fit a shared-memory tile ring) and the
-two-pass one (filter -> offsets -> write).  `MBC_SCAN_PATH` forces either.  Every case here runs under both and is
-compared with the oracle: bit-exact positions / values / Tuple bytes / integer aggregates, real SUM 1e-6 relative.
+`mbc_scan` has the two-pass engine (filter -> offsets -> write; dense tiles streamed through shared memory, or gathered
+per survivor when MBC_WRITE_STREAM=0 / the projected row is too wide) and the opt-in single-residency engine
+(mbc_scan_fused.cuh, MBC_SCAN_PATH=fused: count warps ahead, offsets from published tile counts, compaction out of shared
+memory).  Every case here runs under all three and is compared with the oracle: bit-exact positions / values / Tuple bytes / integer aggregates, real SUM 1e-6 relative.
 Needs a B200.
 """
 import numpy as np
@@ -16,12 +16,18 @@ from util import C2_AGGS, C2_DESCS, c2_columns, c2_device_table, c2_terms, check
 pytestmark = pytest.mark.gpu
 
 ALL = N.WANT_POSITIONS | N.WANT_COLUMNS | N.WANT_TUPLES | N.WANT_AGG | N.WANT_HOST
-ENGINES = ["fused", "twopass"]
+ENGINES = ["twopass", "stream", "gather", "fused"]
 
 
 @pytest.fixture(params=ENGINES)
 def engine(request, monkeypatch):
-    monkeypatch.setenv("MBC_SCAN_PATH", request.param)
+    """twopass: filter -> offsets -> write, dense groups streamed through shared memory when at least 3/4 full, else their
+    survivors gathered through a rank -> row list (the default engine); stream / gather: every dense group through the one
+    or the other path; fused: the single-residency kernel (opt-in)."""
+    monkeypatch.setenv("MBC_SCAN_PATH", "fused" if request.param == "fused" else "twopass")
+    monkeypatch.setenv("MBC_WRITE_STREAM", "0" if request.param == "gather" else "1")
+    if request.param == "stream":
+        monkeypatch.setenv("MBC_STREAM_MIN_PCT", "0")
     return request.param
 
 
