@@ -38,10 +38,14 @@ class Columnarfile:
                 raise Exception(e.message)
             from .dbfile import read_header
             hdr = read_header(sd.db_bytes, name)
+            self._from_image = True
             self.attrNames = hdr["colnames"]
             self._init_schema([(t, w) for t, w in self.table.coldescs])
             if hdr["deleted_bytes"]:                               # the device copy was set by the ingest; mirror it
                 self._deleted.bitSet = BitSet(np.frombuffer(hdr["deleted_bytes"], dtype=np.uint64).copy())
+            for c, flag in enumerate(hdr["bitmapExist"]):          # Columnarfile.java:288-323: the catalogued indexes are
+                if flag == 1:                                      # available again; the device copy is rebuilt from the column
+                    self.table.bitmap_build(c)                     # (K3 takes less time than decoding the BM pages would)
         else:
             if any(len(n) > 15 for n in attrNames):
                 raise Exception("Attribute name too long.")        # Columnarfile.java:68-70 (MAXATTRNAME)
@@ -106,8 +110,21 @@ class Columnarfile:
 
     # ---- bitmap indexes ------------------------------------------------------------------------------------------
     def createBitMapIndex(self, columnNo: int) -> bool:
-        """Columnarfile.java:698-753 -> K3 on the device."""
+        """Columnarfile.java:698-753 -> K3 on the device.  When the file was opened from a DB image, the index is also
+        PERSISTED into that image in the reference's own format (one `<cf>.bm.<col>.<value>` BMIndexPage chain per value,
+        the "<col>.<value>" catalogue records and bitmapExist in `<cf>.hdr`; dbfile.persist_bitmap_index), so the unmodified
+        Java opens it with BitMapFile(String); SystemDefs.flush() writes the image back to the DB file."""
         self.table.bitmap_build(columnNo)
+        sd = SystemDefs.current()
+        if getattr(self, "_from_image", False) and sd.db_bytes is not None:
+            from .dbfile import persist_bitmap_index
+            vals = self.table.bitmap_values(columnNo)
+            if self.attrTypes[columnNo].attrType == AttrType.attrString:
+                values = [bytes(v).rstrip(b"\0").decode("utf-8") for v in vals]
+            else:
+                values = [int(v) for v in vals]
+            bitsets = [self.table.bitmap_get(columnNo, v).view(np.uint8).tobytes() for v in values]
+            sd.db_bytes = persist_bitmap_index(sd.db_bytes, self._fileName, columnNo, values, bitsets)
         return True
 
     def bitmapIndexExists(self, colNo: int) -> bool:

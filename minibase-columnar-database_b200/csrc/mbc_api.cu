@@ -29,6 +29,30 @@ int32_t dev_alloc(mbc_ctx* ctx, void** p, size_t bytes, bool zero) {
     return MBC_OK;
 }
 
+}  // namespace mbc
+static void ctx_destroy(mbc_ctx* ctx) {
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (auto& b : ctx->pinned_free) cudaFreeHost(b.p);
+    for (auto e : ctx->event_free) cudaEventDestroy(e);
+    if (ctx->ws) cudaFree(ctx->ws);
+    if (ctx->fused_flags) cudaFree(ctx->fused_flags);
+    if (ctx->ev_begin) cudaEventDestroy(ctx->ev_begin);
+    if (ctx->ev_end) cudaEventDestroy(ctx->ev_end);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->d2h_stream) cudaStreamDestroy(ctx->d2h_stream);
+    delete ctx;
+}
+
+namespace mbc {
+
+void ctx_retain(mbc_ctx* ctx) { ++ctx->live_objects; }
+
+void ctx_release(mbc_ctx* ctx) {
+    if (--ctx->live_objects <= 0 && ctx->shutdown_pending) ctx_destroy(ctx);
+}
+
 void dev_free(mbc_ctx* ctx, void* p) {
     if (p) cudaFreeAsync(p, ctx->stream);
 }
@@ -168,36 +192,35 @@ int32_t mbc_init(int32_t device_id, mbc_ctx** out) {
     mbc_ctx* ctx = new mbc_ctx();
     ctx->device = device_id;
     ctx->sm_count = prop.multiProcessorCount;
-    MBC_CUDA(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
-    MBC_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
-    MBC_CUDA(cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking));
-    ctx->stream = ctx->own_stream;
-    MBC_CUDA(cudaEventCreate(&ctx->ev_begin));
-    MBC_CUDA(cudaEventCreate(&ctx->ev_end));
-    // keep freed device memory in the stream-ordered pool: result buffers are re-used
-    // across scans without going back to the driver
     cudaMemPool_t pool;
-    MBC_CUDA(cudaDeviceGetDefaultMemPool(&pool, device_id));
     uint64_t thr = UINT64_MAX;
-    MBC_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+    // keep freed device memory in the stream-ordered pool: result buffers are re-used across scans without going back to
+    // the driver
+    cudaError_t e2 = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
+    if (e2 == cudaSuccess) e2 = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
+    if (e2 == cudaSuccess) e2 = cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking);
+    ctx->stream = ctx->own_stream;
+    if (e2 == cudaSuccess) e2 = cudaEventCreate(&ctx->ev_begin);
+    if (e2 == cudaSuccess) e2 = cudaEventCreate(&ctx->ev_end);
+    if (e2 == cudaSuccess) e2 = cudaDeviceGetDefaultMemPool(&pool, device_id);
+    if (e2 == cudaSuccess) e2 = cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    if (e2 != cudaSuccess) {                   // nothing half-built is left behind
+        set_error("mbc_init: %s", cudaGetErrorString(e2));
+        ctx->stream = ctx->own_stream ? ctx->own_stream : nullptr;
+        if (ctx->stream) ctx_destroy(ctx); else delete ctx;
+        return MBC_ERR_CUDA;
+    }
     *out = ctx;
     return MBC_OK;
 }
 
 void mbc_shutdown(mbc_ctx* ctx) {
     if (!ctx) return;
-    cudaSetDevice(ctx->device);
-    cudaStreamSynchronize(ctx->stream);
-    for (auto& b : ctx->pinned_free) cudaFreeHost(b.p);
-    for (auto e : ctx->event_free) cudaEventDestroy(e);
-    if (ctx->ws) cudaFree(ctx->ws);
-    if (ctx->fused_flags) cudaFree(ctx->fused_flags);
-    cudaEventDestroy(ctx->ev_begin);
-    cudaEventDestroy(ctx->ev_end);
-    cudaStreamDestroy(ctx->own_stream);
-    cudaStreamDestroy(ctx->copy_stream);
-    cudaStreamDestroy(ctx->d2h_stream);
-    delete ctx;
+    if (ctx->live_objects > 0) {               // tables / results are still open: the last one to close destroys the context
+        ctx->shutdown_pending = true;
+        return;
+    }
+    ctx_destroy(ctx);
 }
 
 int32_t mbc_set_stream(mbc_ctx* ctx, void* cuda_stream) {
@@ -245,6 +268,7 @@ int32_t mbc_table_create(mbc_ctx* ctx, int32_t ncols, const mbc_coldesc* cols, i
     MBC_CUDA(cudaSetDevice(ctx->device));
     mbc_table* t = new mbc_table();
     t->ctx = ctx;
+    ctx_retain(ctx);
     t->nrows = nrows;
     t->nrows_pad = std::max<int64_t>(round_up(nrows, kPadRows), kPadRows);
     t->words_pad = t->nrows_pad / 32;
@@ -291,7 +315,9 @@ void mbc_table_free(mbc_table* t) {
         dev_free(t->ctx, b.d_ids);
     }
     dev_free(t->ctx, t->d_deleted);
+    mbc_ctx* ctx = t->ctx;
     delete t;
+    ctx_release(ctx);
 }
 
 int64_t mbc_table_nrows(const mbc_table* t) { return t ? t->nrows : -1; }
@@ -447,6 +473,7 @@ void mbc_result_free(mbc_result* r) {
     dev_free(ctx, r->d_tuples);
     for (auto& b : r->pinned) pinned_release(ctx, b.first, b.second);
     delete r;
+    ctx_release(ctx);
 }
 
 }  // extern "C"

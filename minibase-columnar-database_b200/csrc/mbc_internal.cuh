@@ -107,6 +107,10 @@ struct mbc_ctx {
     uint32_t  fused_epoch = 0;
     int       fused_smem_budget = -1;    // dynamic shared memory the fused kernel may use (-1: not probed, 0: unusable)
     int64_t h2d_bytes = 0;            // host -> device bytes moved by mbc_scan_host (copies + rows read in place)
+    // tables, results and shards alive on this context: mbc_shutdown with live objects only marks the context, the last
+    // free destroys it (a handle closed after its context must not touch freed memory)
+    int64_t live_objects = 0;
+    bool shutdown_pending = false;
     float density_hint = 0.f;         // qualifying fraction of the last completed scan: picks the dense write path of the next
     float last_ms = 0.f;
     bool timing_split = false;
@@ -171,6 +175,8 @@ struct mbc_result {
 namespace mbc {
 
 // ---- helpers implemented in mbc_api.cu ----------------------------------------------------
+void    ctx_retain(mbc_ctx* ctx);            // a table / result / shard now lives on the context
+void    ctx_release(mbc_ctx* ctx);           // ... and is gone: destroys the context if mbc_shutdown was called meanwhile
 int32_t dev_alloc(mbc_ctx* ctx, void** p, size_t bytes, bool zero);
 void    dev_free(mbc_ctx* ctx, void* p);
 int32_t pinned_alloc(mbc_ctx* ctx, void** p, size_t bytes, size_t* actual);

@@ -910,6 +910,7 @@ extern "C" int32_t mbc_bitmap_join(mbc_table* outer, mbc_table* inner, const mbc
 
     mbc_result* r = new mbc_result();
     r->ctx = ctx;
+    ctx_retain(ctx);
     r->want = want;
     r->nrows = 0;
     std::vector<void*> temps;

@@ -450,6 +450,7 @@ static int32_t prepare_job(const mbc_table* schema, const ScanRequest& rq, int64
     mbc_result* r = new mbc_result();
     job->r = r;
     r->ctx = ctx;
+    ctx_retain(ctx);
     r->want = rq.want;
     r->capacity = capacity_rows;
     const bool want_cols = (rq.want & (MBC_WANT_COLUMNS | MBC_WANT_TUPLES)) != 0 && rq.nproj > 0;

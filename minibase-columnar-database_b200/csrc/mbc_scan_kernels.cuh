@@ -576,7 +576,7 @@ constexpr int kGroupWords = kGroupRows / 32;
 constexpr int kThreadWords = kGroupWords / kScanThreads;           // 4 (or 8) -> one (two) 128-bit loads per thread
 constexpr int kListCap = MBC_SPARSE_MAX > kTileRows ? MBC_SPARSE_MAX : kTileRows;
 constexpr int kSparseMax = MBC_SPARSE_MAX;                         // survivors per group handled item-per-warp
-static_assert(kGroupRows <= 65536 && kThreadWords % 4 == 0 && kSparseMax <= kListCap, "group geometry");
+static_assert(kGroupRows <= 65536 && kThreadWords % 4 == 0 && kSparseMax <= kListCap && kWarpsPerCta <= 32, "group geometry");
 
 template <typename V>
 __device__ __forceinline__ void gather_store(const V* __restrict__ src, V* __restrict__ dst, const uint16_t* list, int first,
@@ -676,11 +676,8 @@ __device__ __forceinline__ void write_dense_tile(const ScanParams& p, const int 
         uoff[3] = uoff[2] + ((tot >> 16) & 0xFFu);
         if (lane == 0) s_wtot[warp] = uoff[3] + (tot >> 24);
         __syncthreads();
-        uint32_t wbase = (lane < warp) ? s_wtot[lane & (kWarpsPerCta - 1)] : 0u;
-        wbase += __shfl_xor_sync(0xFFFFFFFFu, wbase, 1);
-        wbase += __shfl_xor_sync(0xFFFFFFFFu, wbase, 2);
-        wbase += __shfl_xor_sync(0xFFFFFFFFu, wbase, 4);
-        wbase = __shfl_sync(0xFFFFFFFFu, wbase, 0);
+        uint32_t wbase = (lane < warp) ? s_wtot[lane & (kWarpsPerCta - 1)] : 0u;   // warp < kWarpsPerCta <= 32 lanes hold the totals below
+        wbase = __reduce_add_sync(0xFFFFFFFFu, wbase);
         if (mask) {
             uint16_t* list = s_list + wbase;
 #pragma unroll

@@ -209,6 +209,7 @@ int32_t mbc_shard_create(mbc_ctx* ctx, int32_t rank, int32_t world, mbc_shard** 
     MBC_CUDA(cudaSetDevice(ctx->device));
     mbc_shard* s = new mbc_shard();
     s->ctx = ctx;
+    ctx_retain(ctx);
     s->rank = rank;
     s->world = world;
     s->counts.assign(world, 0);
@@ -241,7 +242,9 @@ void mbc_shard_free(mbc_shard* s) {
     if (s->ev_scan) cudaEventDestroy(s->ev_scan);
     if (s->ev_push) cudaEventDestroy(s->ev_push);
     if (s->side) cudaStreamDestroy(s->side);
+    mbc_ctx* ctx = s->ctx;
     delete s;
+    ctx_release(ctx);
 }
 
 int32_t mbc_shard_window_create(mbc_shard* s, int64_t capacity_rows, int32_t ncols, const int32_t* col_strides, uint8_t* handle_out) {

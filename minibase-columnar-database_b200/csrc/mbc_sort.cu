@@ -89,6 +89,7 @@ extern "C" int32_t mbc_sort(mbc_table* t, const int32_t* key_cols, int32_t nkeys
 
     mbc_result* r = new mbc_result();
     r->ctx = ctx;
+    ctx_retain(ctx);
     r->want = want;
     r->nrows = t->nrows;
     r->count = n;

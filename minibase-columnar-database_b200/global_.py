@@ -137,6 +137,13 @@ class SystemDefs:
         SystemDefs.JavabaseDB = self
         SystemDefs.JavabaseBM = self.ctx
 
+    def flush(self) -> None:
+        """Write the (possibly edited: persisted bitmap indexes) DB image back to the DB file -- the reference's buffer
+        manager does this page by page on flushAllPages (bufmgr/BufMgr.java)."""
+        if self.dbname is not None and self.db_bytes is not None:
+            with open(self.dbname, "wb") as f:
+                f.write(self.db_bytes)
+
     @classmethod
     def current(cls) -> "SystemDefs":
         if cls.JavabaseDB is None:

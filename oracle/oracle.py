@@ -903,3 +903,61 @@ def read_columnar_file(db: bytes, name: str) -> dict:
     dbytes = dbytes.ljust(((len(dbytes) + 7) // 8) * 8, b"\0")
     deleted = np.frombuffer(dbytes, dtype=np.uint64).copy() if dbytes else np.zeros(0, np.uint64)
     return {"colnames": colnames, "coldescs": coldescs, "columns": columns, "deleted": deleted}
+
+
+# ---- persisted bitmap indexes (reader side; the writer under test is the product's dbfile.persist_bitmap_index) --------
+def read_bitmap_file(db: bytes, filename: str) -> np.ndarray:
+    """bitmap/BitMapFile.java:43-60 BitMapFile(String) -> bitmap/BM.java:179-215 readBitSet: the first record of the header
+    page and of every page chained behind it, concatenated, BitSet.valueOf (little-endian).  Returns uint64 words."""
+    files = _file_entries(db)
+    if filename not in files:
+        raise KeyError(f"The file {filename} does not exist. Please provide a vaild BitMap file name.")
+    data, pid = b"", files[filename]
+    while pid != INVALID_PAGE:
+        base = pid * PAGE
+        cnt = struct.unpack_from(">h", db, base)[0]
+        first = None
+        for s in range(cnt):                                                  # HFPage.firstRecord: the first non-empty slot
+            ln, off = struct.unpack_from(">hH", db, base + DPFIXED + 4 * s)
+            if ln >= 0:
+                first = (ln, off)
+                break
+        if first is None:
+            raise ValueError(f"bitmap page {pid} of {filename} holds no record")
+        data += bytes(db[base + first[1]:base + first[1] + first[0]])
+        pid = struct.unpack_from(">i", db, base + 12)[0]
+    data = data.rstrip(b"\0")
+    data = data.ljust((len(data) + 7) // 8 * 8, b"\0")
+    return np.frombuffer(data, dtype=np.uint64).copy() if data else np.zeros(0, np.uint64)
+
+
+def read_bitmap_catalogue(db: bytes, name: str) -> dict:
+    """columnar/Columnarfile.java:288-323: bitmapExist (the header's sixth record) and the "<col>.<value>" records behind
+    it -> {"bitmapExist": [...], "values": {col: [value, ...]}} with values typed like the column."""
+    files = _file_entries(db)
+    recs = [r for _, _, r in _heap_records(db, files[name + ".hdr"])]
+    n = struct.unpack(">i", recs[0][:4])[0]
+    types = [struct.unpack_from(">i", recs[1], 4 * i)[0] for i in range(n)]
+    values: dict = {c: [] for c in range(n)}
+    for r in recs[6:]:
+        ln = struct.unpack(">H", r[:2])[0]
+        col, val = r[2:2 + ln].decode("utf-8").split(".", 1)                  # the Java splits on every dot: dotted strings break it
+        values[int(col)].append(val if types[int(col)] == ATTR_STRING else int(val))
+    return {"bitmapExist": list(recs[5][:n]), "values": values}
+
+
+def read_bitmap_index(db: bytes, name: str, col: int) -> dict:
+    """{value: BitSet words} of a persisted index: every catalogued value's file `<name>.bm.<col>.<value>`."""
+    cat = read_bitmap_catalogue(db, name)
+    return {v: read_bitmap_file(db, f"{name}.bm.{col}.{v}") for v in cat["values"][col]}
+
+
+def space_map_pages(db: bytes) -> set:
+    """Pages marked allocated in the space map (diskmgr/DB.java:739-822: bit p of the map, least significant bit first)."""
+    num_pages = struct.unpack_from(">i", db, PAGE - 4)[0]
+    out = set()
+    for pid in range(min(num_pages, len(db) // PAGE)):
+        at = PAGE * (1 + pid // (PAGE * 8)) + (pid % (PAGE * 8)) // 8
+        if at < len(db) and (db[at] >> (pid % 8)) & 1:
+            out.add(pid)
+    return out

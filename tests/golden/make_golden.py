@@ -32,6 +32,12 @@ def main():
         body = [ln.rstrip("\r") for ln in lines[a + 1:b]]
         kind = cmd.split(" ")[0] if cmd else ""
         e = {"line": a + 1, "cmd": cmd, "kind": kind}
+        if kind in ("batchinsert", "index"):
+            # "Wrote Pages: {0=2, 1=2, 129=1, ...}": page id -> times written, as the buffer manager flushed them
+            for ln in body:
+                if ln.startswith("Wrote Pages: {"):
+                    e["wrote_pages"] = {k: int(v) for k, v in re.findall(r"(\d+)=(\d+)", ln)}
+                    break
         if kind == "batchinsert":
             m = [re.match(r"Record count: (\d+)", ln) for ln in body]
             m = [x for x in m if x]

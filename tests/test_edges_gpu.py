@@ -156,3 +156,35 @@ def test_both_write_pass_forms(ctx, oracle, monkeypatch):
         check_result(oracle, res, exp, [descs[2], descs[1], descs[0]])
         res.close()
     t.close()
+
+
+def test_multibyte_utf8_strings_compare_like_string_compareto(ctx, oracle):
+    """TupleUtils.java:79-81 compares Java Strings (UTF-16 code units); the columns hold the bytes Convert.setStrValue wrote
+    (modified UTF-8).  For text without U+0000 the byte order of modified UTF-8 IS the UTF-16 code-unit order (2- and 3-byte
+    sequences sort by code point; the BMP has no surrogates), so the kernel's byte compare over the zero-padded width equals
+    compareTo -- checked against the oracle, which decodes to UTF-16 and compares like the Java."""
+    rng = np.random.default_rng(11)
+    words = ["abc", "abd", "ab", "é", "ébc", "eb", "z", "Zürich", "zürich", "日本", "日本語", "中", "ß", "straße", "strasse", "~", "߿", "ࠀ",
+             "￮", "aé", "á", "€uro", "ñandú", "nandu"]
+    n = 9001
+    pick = rng.integers(0, len(words), n)
+    col = oracle.pack_strings([words[i] for i in pick], 16)
+    other = oracle.pack_strings([words[i] for i in rng.integers(0, len(words), n)], 16)
+    ints = rng.integers(0, 5, n).astype(np.int32)
+    descs = [(0, 16), (0, 16), (1, 4)]
+    t = load_table(ctx, descs, [col, other, ints])
+    want = N.WANT_POSITIONS | N.WANT_COLUMNS | N.WANT_TUPLES | N.WANT_AGG | N.WANT_HOST
+    for lit in ("é", "z", "日本", "straße", "á", "ࠀ", "abc"):
+        for op in range(7):
+            terms = [oracle.Term(op, ("col", 0), ("str", lit), 0)]
+            exp = oracle.scan(descs, [col, other, ints], terms, proj=[0, 2], aggs=[(0, 0)])
+            res = t.scan(terms, proj=[0, 2], want=want, aggs=[(0, 0)])
+            check_result(oracle, res, exp, [descs[0], descs[2]])
+            res.close()
+    for op in (0, 1, 5):                                        # column against column, literal on the left
+        terms = [oracle.Term(op, ("col", 0), ("col", 1), 0), oracle.Term(op, ("str", "ñandú"), ("col", 1), 1)]
+        exp = oracle.scan(descs, [col, other, ints], terms, proj=[1, 0])
+        res = t.scan(terms, proj=[1, 0], want=N.WANT_POSITIONS | N.WANT_COLUMNS | N.WANT_TUPLES | N.WANT_HOST)
+        check_result(oracle, res, exp, [descs[1], descs[0]])
+        res.close()
+    t.close()
