@@ -122,9 +122,9 @@ class Context:
         if len(host_cols) != ncols:
             raise ValueError(f"{len(host_cols)} host columns for {ncols} column descriptors")
         for c, ((t, w), a) in enumerate(zip(coldescs, host_cols)):     # the library reads nrows * width bytes from every pointer
-            want = np.int32 if t == N.ATTR_INTEGER else np.float32 if t == N.ATTR_REAL else np.uint8
-            if not isinstance(a, np.ndarray) or a.dtype != want or not a.flags["C_CONTIGUOUS"]:
-                raise ValueError(f"host column {c}: a C-contiguous {np.dtype(want).name} array is required "
+            dt = np.int32 if t == N.ATTR_INTEGER else np.float32 if t == N.ATTR_REAL else np.uint8
+            if not isinstance(a, np.ndarray) or a.dtype != dt or not a.flags["C_CONTIGUOUS"]:
+                raise ValueError(f"host column {c}: a C-contiguous {np.dtype(dt).name} array is required "
                                  f"(got {getattr(a, 'dtype', type(a))}); buffers are not copied, so pinned memory stays pinned")
             if a.size != nrows * (w if t == N.ATTR_STRING else 1):
                 raise ValueError(f"host column {c}: {a.size} elements for {nrows} rows of width {w}")
