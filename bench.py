@@ -220,8 +220,9 @@ def workload_config(wl: Workload, args, rows_per_gpu, world):
            "l2": f"inputs ({rows_per_gpu * wl.row_bytes_in / 1e9:.1f} GB of referenced columns per GPU) are larger than the 126 MB L2; no flush needed"}
     if world > 1:
         cfg["sharding"] = ("TID range per rank, no data-path collective; per step every rank pushes the gathered query's positions + "
-                           "projected values + count + aggregates into rank 0's window with peer-memory stores over NVLink "
-                           "(shard_push_kernel of libmbcol.so, mbc_shard_* ABI through ctypes; no NCCL kernel on the data path); the "
+                           "projected values + count + aggregates into rank 0's IPC-mapped window over NVLink (mbc_shard_* ABI of libmbcol.so "
+                           "through ctypes: counts published by a kernel, rows moved by the copy engines at the exclusive-scan offset; no "
+                           "NCCL kernel on the data path); the "
                            "push of step i runs beside the scans of step i+1; the last one is drained inside the timed region")
     else:
         cfg["sharding"] = "single GPU"
@@ -278,10 +279,15 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     rows = args.rows if args.rows > 0 else wl.default_rows
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    real_stdout = None
     if world > 1:
-        # NCCL's INFO lines (the rank check reads them) go to stderr: stdout carries ONE JSON line
-        if os.environ.get("NCCL_DEBUG") and not os.environ.get("NCCL_DEBUG_FILE"):
-            os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"
+        # stdout carries ONE JSON line: NCCL's version banner and INFO lines (NCCL_DEBUG is left as the caller set it: the
+        # driver's rank check reads them) are sent to stderr -- by NCCL_DEBUG_FILE where NCCL honours it, and by pointing
+        # file descriptor 1 at stderr until the JSON line is printed for whatever still writes to stdout
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        sys.stdout.flush()
+        real_stdout = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
     ctx = mbcol.Context(local_rank)
     stream = torch.cuda.current_stream()
@@ -311,40 +317,49 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             shard.open_window(bytes(hbuf.cpu().numpy().tobytes()), cap, proj_descs)
         dist.barrier()
 
+    # rows over the copy engines (default; measured at N=8: 1.26 ms per step against 1.60 ms with SM stores -- 7 ranks' stores
+    # into one GPU reached ~500 GB/s of its NVLink ingress, the DMA engines ~760 GB/s) or as peer-memory stores from a kernel
+    copy_engines = os.environ.get("MBC_BENCH_GATHER", "dma") == "dma"
     pending = []                                                    # results of the previous step: its push may still be running
     collected = {"total": None, "counts": None}
 
-    def finish_previous():
-        """The previous step's gather: rank 0 waits for every rank's rows (on the shard's side stream -- this step's scans are
-        already queued behind nothing), notes the totals and releases the window slot; every rank then frees the results."""
+    def exchange_previous(record=False):
+        """The previous step's exchange, issued while THIS step's scans (already queued) run: every rank publishes its count
+        and pushes its rows into rank 0's window, rank 0 waits for all of them (on the shard's side stream, so the host never
+        waits for the scans just queued), notes the totals and releases the window slot; then the results are freed.  The host
+        reads the previous step's counts here -- they are complete, nothing in the loop waits for the scans in flight."""
         if not pending:
             return
+        results = list(pending)
+        pending.clear()
+        shard.gather(results[wl.gather_query], beside_next_scan=True, copy_engines=copy_engines)
+        for s, res in zip(wl.sels, results):
+            counts[s] = res.count
+            if record:
+                kernel_ms[s].append(res.kernel_ms)
+                phase_ms[s].append(res.phase_ms)
         if rank == 0:
             collected["total"], collected["counts"] = shard.collect()
             shard.release()
         shard.fence()                                               # the frees below are stream-ordered behind the push
-        for res in pending:
+        for res in results:
             res.close()
-        pending.clear()
 
     def step(record=False):
         results = []
         for s in wl.sels:                                           # device-resident results complete asynchronously:
             results.append(table.scan(terms[s], proj=wl.proj, want=want_dev, aggs=wl.aggs))   # the scans queue back to back
         if world > 1:
-            finish_previous()                                       # step i-1's rows land while step i's scans run
-            shard.gather(results[wl.gather_query], beside_next_scan=True)
+            exchange_previous(record)                               # step i-1's rows travel while step i's scans run
             pending.extend(results)
-            if pending and not record:
-                pass
+            return
         for s, res in zip(wl.sels, results):                        # the host reads every count (this is the wait)
             counts[s] = res.count
             if record:
                 kernel_ms[s].append(res.kernel_ms)
                 phase_ms[s].append(res.phase_ms)
-        if world == 1:
-            for res in results:
-                res.close()
+        for res in results:
+            res.close()
 
     def barrier():
         if world > 1:
@@ -354,7 +369,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     for _ in range(args.warmup):
         step()
     if world > 1:
-        finish_previous()
+        exchange_previous()
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -365,7 +380,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     for _ in range(args.steps):
         step(record=True)
     if world > 1:
-        finish_previous()                                           # the last step's gather is inside the timed region
+        exchange_previous(record=True)                              # the last step's exchange is inside the timed region
     e1.record(stream)
     barrier()
     ms = e0.elapsed_time(e1)
@@ -377,6 +392,12 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     nscan = len(wl.sels)
     value = float(nscan) * rows * world * args.steps / (ms_total * 1e-3)
 
+    push_ms = None
+    if world > 1:                                                   # device time of every rank's last push (rank order)
+        pm = torch.tensor([shard.push_ms], dtype=torch.float64, device=dev)
+        allp = [torch.zeros_like(pm) for _ in range(world)]
+        dist.all_gather(allp, pm)
+        push_ms = [round(float(x.item()), 4) for x in allp]
     # ---- scan-only time of the same shard (no gather): what the multi-GPU step is compared with ----------------------
     scan_only_ms = None
     if world > 1:
@@ -399,6 +420,23 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         parity = check_sharded_step(wl, table, terms, shard, rank, world, rows, proj_descs, mbcol, dist, dev, torch)
 
     # ---- end to end: host-resident columns -> mbc_scan_host -> host-resident results -------------------------------
+    if args.no_e2e:
+        if rank == 0:
+            sys.stdout.flush()
+            os.dup2(real_stdout, 1) if real_stdout is not None else None
+            print(json.dumps({"tuning_run": True, "n_gpus": world, "ms_per_step": ms_total / args.steps, "value": value,
+                              "scan_only_ms_per_step": scan_only_ms, "parity_checked": bool(parity and parity.get("ok")),
+                              "push_ms_per_rank": push_ms,
+                              "per_selectivity_kernel_ms": {str(s): statistics.mean(kernel_ms[s]) for s in wl.sels},
+                              "env": {k: v for k, v in os.environ.items() if k.startswith("MBC_")}}))
+        if shard is not None:
+            barrier()
+            shard.close()
+        table.close()
+        ctx.close()
+        if world > 1:
+            dist.destroy_process_group()
+        return
     host_cols = []
     dummy = np.zeros(64, dtype=np.uint8)
     for c, (t, w) in enumerate(wl.descs):
@@ -522,11 +560,16 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             out["multi_gpu"] = {"scan_only_ms_per_step": scan_only_ms, "step_ms": step_ms,
                                 "efficiency_vs_scan_only": scan_only_ms / step_ms if scan_only_ms else None,
                                 "gathered_rows": collected["total"], "rank_counts": collected["counts"],
+                                "push_kernel_ms_per_rank": push_ms,
                                 "gathered_bytes_per_step": (collected["total"] or 0) * wl.row_bytes_out,
-                                "gather": "mbc_shard_gather: peer-memory stores into rank 0's IPC-mapped window (no NCCL on the data path)"}
+                                "gather": "mbc_shard_gather into rank 0's IPC-mapped window, " + ("copy engines (cudaMemcpyAsync peer copies at the offset a one-warp kernel resolves)" if copy_engines else "peer-memory stores from shard_push_kernel") + "; no NCCL on the data path"}
             out["parity_checked"] = bool(parity and parity.get("ok"))
             out["parity"] = parity
+        sys.stdout.flush()
+        if real_stdout is not None:
+            os.dup2(real_stdout, 1)
         print(json.dumps(out))
+        sys.stdout.flush()
     if shard is not None:
         barrier()
         shard.close()
@@ -635,6 +678,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-pageable", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="tuning runs only: skip the end-to-end leg (the line then carries e2e: null)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))

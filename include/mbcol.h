@@ -261,10 +261,16 @@ int32_t mbc_shard_window_create(mbc_shard* sh, int64_t capacity_rows, int32_t nc
 int32_t mbc_shard_window_open(mbc_shard* sh, const uint8_t* handle, int64_t capacity_rows, int32_t ncols,
                               const int32_t* col_strides);
 int32_t mbc_shard_window_attach(mbc_shard* sh, const mbc_shard* root);
-/* Push this rank's positions, projected columns, count and aggregates of `r` into the window.  beside_next_scan != 0:
- * the push runs on a side stream behind r's kernels, so scans queued afterwards overlap it. */
-int32_t mbc_shard_gather(mbc_shard* sh, const mbc_result* r, int32_t beside_next_scan);
+/* Push this rank's positions, projected columns, count and aggregates of `r` into the window.  `mode` bit 0: the push
+ * runs on a side stream behind r's kernels, so scans queued afterwards overlap it.  Bit 1: the rows travel as peer copies on
+ * the copy engines (no SM; the call then waits until r's kernels have finished, to learn the rank's offset) instead of
+ * peer-memory stores from a kernel. */
+#define MBC_GATHER_BESIDE_NEXT_SCAN 1
+#define MBC_GATHER_COPY_ENGINES     2
+int32_t mbc_shard_gather(mbc_shard* sh, const mbc_result* r, int32_t mode);
 int32_t mbc_shard_fence(mbc_shard* sh);
+/* device time of this rank's last push kernel (waits for it), ms; < 0 if none */
+float   mbc_shard_push_ms(mbc_shard* sh);
 int32_t mbc_shard_collect(mbc_shard* root, int64_t* total_rows, int64_t* rank_counts /* [world] or NULL */);
 /* aggregate i of the gathered results folded over the ranks; kind / type as in the scan's mbc_aggspec / column type */
 int32_t mbc_shard_agg(const mbc_shard* root, int32_t i, int32_t kind, int32_t type, int64_t* as_i64, double* as_f64,

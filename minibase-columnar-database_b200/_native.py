@@ -112,6 +112,7 @@ _SIGNATURES = {
     "mbc_shard_window_attach": (C.c_int32, [_VP, _VP]),
     "mbc_shard_gather": (C.c_int32, [_VP, _VP, C.c_int32]),
     "mbc_shard_fence": (C.c_int32, [_VP]),
+    "mbc_shard_push_ms": (C.c_float, [_VP]),
     "mbc_shard_collect": (C.c_int32, [_VP, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "mbc_shard_agg": (C.c_int32, [_VP, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_double), C.POINTER(C.c_int32)]),
     "mbc_shard_window_device": (C.c_int32, [_VP, C.POINTER(_VP), C.c_int32, C.POINTER(_VP)]),

@@ -464,6 +464,7 @@ void mbc_result_free(mbc_result* r) {
     result_finalize(r);                            // the pinned count/aggregate block must have landed before it is recycled
     event_put(ctx, r->ev_t0);
     event_put(ctx, r->ev_t1);
+    event_put(ctx, r->ev_done);
     for (auto& e : r->ev_mid) event_put(ctx, e);
     dev_free(ctx, r->d_pos);
     dev_free(ctx, r->d_pos2);

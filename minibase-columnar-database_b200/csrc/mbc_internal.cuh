@@ -165,6 +165,7 @@ struct mbc_result {
     // count/aggregate copy queued; the first accessor that needs the count waits on ev_ready.  Back-to-back scans
     // then run without host gaps between them.
     cudaEvent_t ev_ready = nullptr;        // non-null while count/aggs are still in flight
+    cudaEvent_t ev_done = nullptr;         // the result's device buffers (rows, count, aggregates) are complete (kept until free)
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;   // device time of this result's kernels
     cudaEvent_t ev_mid[3] = {nullptr, nullptr, nullptr};   // resident scans: after pass 1, after the offsets, after the write pass
     float phase_ms[4] = {-1.f, -1.f, -1.f, -1.f};          // pass 1, tile offsets, write pass, aggregate finish

@@ -638,6 +638,8 @@ static int32_t finish_job_device(ScanJob* job, bool deferred = false) {
     } else {
         MBC_CUDA(cudaMemcpyAsync(r->d_aggs + kMaxAgg, job->count_slot(), 8, cudaMemcpyDeviceToDevice, ctx->stream));
     }
+    r->ev_done = event_get(ctx);                                   // mbc_shard_gather pushes behind this, not behind later scans
+    if (r->ev_done) cudaEventRecord(r->ev_done, ctx->stream);
     if (deferred) {
         r->aggs.resize(p.nagg);
         for (int a = 0; a < p.nagg; ++a) { r->aggs[a].kind = p.aggs[a].kind; r->aggs[a].type = p.aggs[a].type; }

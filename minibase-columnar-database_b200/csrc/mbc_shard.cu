@@ -7,8 +7,9 @@
 // The root rank owns a WINDOW in its HBM (cudaMalloc, exported with cudaIpcGetMemHandle; peers map it with
 // cudaIpcOpenMemHandle, or -- inside one process, the shape a single JVM driving 8 GPUs has -- reach it through
 // cudaDeviceEnablePeerAccess).  One kernel per rank and step (shard_push_kernel) then does the whole exchange:
-//   1. publishes the rank's count and its COUNT/SUM/MIN/MAX block in the window's control area (release, system scope),
-//   2. reads the counts of the lower ranks from the same area (they run the same scan at the same time) -> its offset,
+//   1. (shard_publish_kernel, right behind the scan) the rank's count and its COUNT/SUM/MIN/MAX block are published in the
+//      window's control area (release, system scope),
+//   2. the push reads the counts of the lower ranks from the same area (they ran the same scan at the same time) -> its offset,
 //   3. stores its positions and projected columns straight into the root's buffers at that offset (coalesced stores over
 //      NVLink; nothing is staged, padded or sent to ranks that do not need it),
 //   4. signals completion.
@@ -68,27 +69,49 @@ __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned l
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-template <typename V>
-__device__ __forceinline__ void push_copy(const V* __restrict__ src, V* __restrict__ dst, long long n) {
-    const long long step = (long long)gridDim.x * blockDim.x;
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    for (; i + 3 * step < n; i += 4 * step) {                      // four independent loads in flight per thread
-        const V a = src[i], b = src[i + step], c = src[i + 2 * step], d = src[i + 3 * step];
-        dst[i] = a; dst[i + step] = b; dst[i + 2 * step] = c; dst[i + 3 * step] = d;
+// Copy nbytes (a multiple of 4; src and dst 4-byte aligned) with 128-bit stores wherever dst allows: the destination is the
+// root's HBM behind NVLink, where a 16-byte store per thread (512 bytes per warp instruction) fills the link's packets; the
+// source is local HBM, read with whatever alignment the (arbitrary) output offset leaves it.
+__device__ __forceinline__ void push_copy(const char* __restrict__ src, char* __restrict__ dst, long long nbytes) {
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long nthreads = (long long)gridDim.x * blockDim.x;
+    long long head = (16 - (long long)(reinterpret_cast<uintptr_t>(dst) & 15)) & 15;
+    if (head > nbytes) head = nbytes;
+    if (tid < head / 4) reinterpret_cast<uint32_t*>(dst)[tid] = reinterpret_cast<const uint32_t*>(src)[tid];
+    const char* s = src + head;
+    char* d = dst + head;
+    const long long n16 = (nbytes - head) / 16;
+    if ((reinterpret_cast<uintptr_t>(s) & 15) == 0) {              // grid-uniform: both sides 16-byte aligned
+        const uint4* s4 = reinterpret_cast<const uint4*>(s);
+        uint4* d4 = reinterpret_cast<uint4*>(d);
+        long long i = tid;
+        for (; i + 3 * nthreads < n16; i += 4 * nthreads) {        // four independent loads in flight per thread
+            const uint4 a = s4[i], b = s4[i + nthreads], c = s4[i + 2 * nthreads], e = s4[i + 3 * nthreads];
+            d4[i] = a; d4[i + nthreads] = b; d4[i + 2 * nthreads] = c; d4[i + 3 * nthreads] = e;
+        }
+        for (; i < n16; i += nthreads) d4[i] = s4[i];
+    } else {
+        const uint32_t* s1 = reinterpret_cast<const uint32_t*>(s);
+        uint4* d4 = reinterpret_cast<uint4*>(d);
+        long long i = tid;
+        for (; i + nthreads < n16; i += 2 * nthreads) {
+            const uint4 a = make_uint4(s1[4 * i], s1[4 * i + 1], s1[4 * i + 2], s1[4 * i + 3]);
+            const long long k = i + nthreads;
+            const uint4 b = make_uint4(s1[4 * k], s1[4 * k + 1], s1[4 * k + 2], s1[4 * k + 3]);
+            d4[i] = a; d4[k] = b;
+        }
+        for (; i < n16; i += nthreads) d4[i] = make_uint4(s1[4 * i], s1[4 * i + 1], s1[4 * i + 2], s1[4 * i + 3]);
     }
-    for (; i < n; i += step) dst[i] = src[i];
+    const long long done = head + n16 * 16;
+    const long long tail = (nbytes - done) / 4;
+    if (tid < tail) reinterpret_cast<uint32_t*>(dst + done)[tid] = reinterpret_cast<const uint32_t*>(src + done)[tid];
 }
 
 __global__ void __launch_bounds__(256) shard_push_kernel(const __grid_constant__ PushParams p) {
     __shared__ long long s_off, s_cnt;
     if (threadIdx.x < 32) {
         const int lane = threadIdx.x;
-        const long long count = (long long)p.my_aggs[kMaxAgg];
-        if (blockIdx.x == 0 && lane == 0) {
-            ShardCtl* mine = p.ctl + p.rank;
-            for (int a = 0; a <= kMaxAgg; ++a) mine->aggs[a] = p.my_aggs[a];
-            st_release_sys(&mine->pub, (p.epoch << 40) | ((unsigned long long)count & kCountMask));
-        }
+        const long long count = (long long)p.my_aggs[kMaxAgg];      // published by shard_publish_kernel when the scan finished
         // the slot was last used by step epoch - kShardSlots: the root must have released it
         if (lane == 0)
             while (ld_acquire_sys(&p.hdr->consumed) + kShardSlots < p.epoch) __nanosleep(200);
@@ -109,12 +132,10 @@ __global__ void __launch_bounds__(256) shard_push_kernel(const __grid_constant__
     const long long off = s_off;
     long long n = s_cnt;
     if (off + n > p.cap_rows) n = max(0ll, p.cap_rows - off);       // never write past the window; the loss is reported
-    if (p.src_pos) push_copy(p.src_pos, p.dst_pos + off, n);
+    if (p.src_pos) push_copy(reinterpret_cast<const char*>(p.src_pos), reinterpret_cast<char*>(p.dst_pos + off), n * 8);
     for (int c = 0; c < p.ncols; ++c) {
-        const int st = p.stride[c];
-        if (st == 4) push_copy(reinterpret_cast<const uint32_t*>(p.src[c]), reinterpret_cast<uint32_t*>(p.dst[c]) + off, n);
-        else if (st == 16) push_copy(reinterpret_cast<const uint4*>(p.src[c]), reinterpret_cast<uint4*>(p.dst[c]) + off, n);
-        else push_copy(reinterpret_cast<const uint32_t*>(p.src[c]), reinterpret_cast<uint32_t*>(p.dst[c]) + off * (st >> 2), n * (st >> 2));
+        const long long st = p.stride[c];
+        push_copy(reinterpret_cast<const char*>(p.src[c]), reinterpret_cast<char*>(p.dst[c]) + off * st, n * st);
     }
     __threadfence_system();
     __syncthreads();
@@ -127,6 +148,54 @@ __global__ void __launch_bounds__(256) shard_push_kernel(const __grid_constant__
             __threadfence_system();
             st_release_sys(&mine->done, p.epoch);
         }
+    }
+}
+
+// The rank's count and aggregate block reach the root's control area before any row is pushed: a rank's push only waits
+// for the (80-byte) publications of the lower ranks, never for their rows.
+__global__ void shard_publish_kernel(ShardCtl* ctl, int rank, unsigned long long epoch, const unsigned long long* my_aggs) {
+    if (threadIdx.x == 0) {
+        ShardCtl* mine = ctl + rank;
+        for (int a = 0; a <= kMaxAgg; ++a) mine->aggs[a] = my_aggs[a];
+        __threadfence_system();
+        st_release_sys(&mine->pub, (epoch << 40) | (my_aggs[kMaxAgg] & kCountMask));
+    }
+}
+
+// Copy-engine form of the push: this one-warp kernel only resolves the rank's offset (and waits for the window slot); the
+// rows then travel as cudaMemcpyAsync peer copies (DMA engines, no SM), and shard_done_kernel signals the root behind them.
+__global__ void shard_offset_kernel(const ShardHeader* hdr, const ShardCtl* ctl, int rank, unsigned long long epoch, const unsigned long long* my_aggs,
+                                    long long cap_rows, long long* out /* host-mapped: offset, rows that fit, rows dropped */) {
+    const int lane = threadIdx.x;
+    if (lane == 0)
+        while (ld_acquire_sys(&hdr->consumed) + kShardSlots < epoch) __nanosleep(200);
+    long long off = 0;
+    if (lane < rank) {
+        unsigned long long v = ld_acquire_sys(&ctl[lane].pub);
+        while ((v >> 40) != epoch) {
+            __nanosleep(200);
+            v = ld_acquire_sys(&ctl[lane].pub);
+        }
+        off = (long long)(v & kCountMask);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) off += __shfl_xor_sync(0xFFFFFFFFu, off, o);
+    if (lane == 0) {
+        const long long count = (long long)my_aggs[kMaxAgg];
+        long long n = count;
+        if (off + n > cap_rows) n = max(0ll, cap_rows - off);
+        out[0] = off;
+        out[1] = n;
+        out[2] = count - n;
+        __threadfence_system();
+    }
+}
+
+__global__ void shard_done_kernel(ShardCtl* ctl, int rank, unsigned long long epoch, unsigned long long dropped) {
+    if (threadIdx.x == 0) {
+        ctl[rank].dropped = dropped;
+        __threadfence_system();
+        st_release_sys(&ctl[rank].done, epoch);
     }
 }
 
@@ -163,10 +232,14 @@ struct mbc_shard {
     size_t bytes = 0;
     cudaStream_t side = nullptr;        // pushes may run beside the next step's scans
     cudaEvent_t ev_scan = nullptr, ev_push = nullptr;
+    cudaEvent_t ev_push0 = nullptr, ev_push1 = nullptr;   // device time of the last push (mbc_shard_push_ms)
     unsigned int* d_blocks_done = nullptr;
     unsigned long long epoch = 0;       // steps gathered so far (every rank calls mbc_shard_gather once per step)
     unsigned long long* d_summary = nullptr;
     unsigned long long* h_summary = nullptr;
+    long long* h_off = nullptr;         // host-mapped: offset / rows / dropped of the copy-engine form
+    long long* d_off = nullptr;
+    cudaEvent_t ev_off = nullptr;
     int64_t total = 0, dropped = 0;
     std::vector<int64_t> counts;
     int push_ctas = 0;
@@ -218,6 +291,10 @@ int32_t mbc_shard_create(mbc_ctx* ctx, int32_t rank, int32_t world, mbc_shard** 
     if (cudaStreamCreateWithFlags(&s->side, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&s->ev_scan, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&s->ev_push, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreate(&s->ev_push0) != cudaSuccess || cudaEventCreate(&s->ev_push1) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s->ev_off, cudaEventDisableTiming) != cudaSuccess ||
+        cudaHostAlloc((void**)&s->h_off, 64, cudaHostAllocMapped) != cudaSuccess ||
+        cudaHostGetDevicePointer((void**)&s->d_off, s->h_off, 0) != cudaSuccess ||
         cudaMalloc((void**)&s->d_blocks_done, 64) != cudaSuccess || cudaMemset(s->d_blocks_done, 0, 64) != cudaSuccess) {
         set_error("mbc_shard_create: %s", cudaGetErrorString(cudaGetLastError()));
         mbc_shard_free(s);
@@ -239,8 +316,12 @@ void mbc_shard_free(mbc_shard* s) {
     if (s->d_blocks_done) cudaFree(s->d_blocks_done);
     if (s->d_summary) cudaFree(s->d_summary);
     if (s->h_summary) cudaFreeHost(s->h_summary);
+    if (s->h_off) cudaFreeHost(s->h_off);
+    if (s->ev_off) cudaEventDestroy(s->ev_off);
     if (s->ev_scan) cudaEventDestroy(s->ev_scan);
     if (s->ev_push) cudaEventDestroy(s->ev_push);
+    if (s->ev_push0) cudaEventDestroy(s->ev_push0);
+    if (s->ev_push1) cudaEventDestroy(s->ev_push1);
     if (s->side) cudaStreamDestroy(s->side);
     mbc_ctx* ctx = s->ctx;
     delete s;
@@ -321,17 +402,51 @@ int32_t mbc_shard_gather(mbc_shard* s, const mbc_result* r, int32_t beside_next_
         p.stride[c] = s->strides[c];
     }
     p.blocks_done = s->d_blocks_done;
+    // the exchange follows THIS result's kernels (its completion event), not whatever the context's stream holds by now:
+    // the caller may already have queued the next step's scans
     cudaStream_t st = ctx->stream;
-    if (beside_next_scan) {                                        // the push follows this result's kernels, not later work of the stream
-        MBC_CUDA(cudaEventRecord(s->ev_scan, ctx->stream));
-        MBC_CUDA(cudaStreamWaitEvent(s->side, s->ev_scan, 0));
+    if (beside_next_scan & 1) {
+        if (r->ev_done) {
+            MBC_CUDA(cudaStreamWaitEvent(s->side, r->ev_done, 0));
+        } else {
+            MBC_CUDA(cudaEventRecord(s->ev_scan, ctx->stream));
+            MBC_CUDA(cudaStreamWaitEvent(s->side, s->ev_scan, 0));
+        }
         st = s->side;
     }
-    shard_push_kernel<<<s->push_ctas, 256, 0, st>>>(p);
+    shard_publish_kernel<<<1, 32, 0, st>>>(p.ctl, s->rank, epoch, p.my_aggs);
     ctx->launches++;
-    MBC_CUDA(cudaGetLastError());
+    cudaEventRecord(s->ev_push0, st);
+    if (beside_next_scan & 2) {
+        // copy engines: offset on the host (one small wait), then one peer copy per buffer, then the done flag
+        shard_offset_kernel<<<1, 32, 0, st>>>(p.hdr, p.ctl, s->rank, epoch, p.my_aggs, s->cap_rows, s->d_off);
+        ctx->launches++;
+        MBC_CUDA(cudaGetLastError());
+        MBC_CUDA(cudaEventRecord(s->ev_off, st));
+        MBC_CUDA(cudaEventSynchronize(s->ev_off));
+        const long long off = s->h_off[0], n = s->h_off[1], dropped = s->h_off[2];
+        if (n > 0) {
+            if (p.src_pos) MBC_CUDA(cudaMemcpyAsync(p.dst_pos + off, p.src_pos, (size_t)n * 8, cudaMemcpyDeviceToDevice, st));
+            for (int c = 0; c < s->ncols; ++c)
+                MBC_CUDA(cudaMemcpyAsync((char*)p.dst[c] + (size_t)off * p.stride[c], p.src[c], (size_t)n * p.stride[c], cudaMemcpyDeviceToDevice, st));
+        }
+        shard_done_kernel<<<1, 32, 0, st>>>(p.ctl, s->rank, epoch, (unsigned long long)dropped);
+        ctx->launches++;
+        MBC_CUDA(cudaGetLastError());
+    } else {
+        shard_push_kernel<<<s->push_ctas, 256, 0, st>>>(p);
+        ctx->launches++;
+        MBC_CUDA(cudaGetLastError());
+    }
+    cudaEventRecord(s->ev_push1, st);
     MBC_CUDA(cudaEventRecord(s->ev_push, st));
     return MBC_OK;
+}
+
+float mbc_shard_push_ms(mbc_shard* s) {
+    float ms = -1.f;
+    if (!s || cudaEventSynchronize(s->ev_push1) != cudaSuccess || cudaEventElapsedTime(&ms, s->ev_push0, s->ev_push1) != cudaSuccess) return -1.f;
+    return ms;
 }
 
 int32_t mbc_shard_fence(mbc_shard* s) {

@@ -421,11 +421,16 @@ class Shard:
         N.check(N.lib().mbc_shard_window_attach(self._h, root._h))
         self.proj_descs, self.capacity = list(root.proj_descs), root.capacity
 
-    def gather(self, result: "Result", beside_next_scan: bool = False) -> None:
-        N.check(N.lib().mbc_shard_gather(self._h, result._h, 1 if beside_next_scan else 0))
+    def gather(self, result: "Result", beside_next_scan: bool = False, copy_engines: bool = False) -> None:
+        N.check(N.lib().mbc_shard_gather(self._h, result._h, (1 if beside_next_scan else 0) | (2 if copy_engines else 0)))
 
     def fence(self) -> None:
         N.check(N.lib().mbc_shard_fence(self._h))
+
+    @property
+    def push_ms(self) -> float:
+        """Device time of this rank's last push (waits for it)."""
+        return float(N.lib().mbc_shard_push_ms(self._h))
 
     def collect(self) -> tuple:
         """Root: wait for every rank's rows of the last gathered step -> (total rows, [rows per rank])."""

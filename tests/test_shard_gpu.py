@@ -44,7 +44,7 @@ def test_sharded_scan_gathers_the_whole_tables_result(oracle, world):
         exp = oracle.scan(C2_DESCS, cols, terms, proj=proj, aggs=C2_AGGS, nthreads=oracle.max_threads())
         results = [t.scan(terms, proj=proj, want=want, aggs=C2_AGGS) for t in tables]
         for r in range(world):                                      # rank order; every push has finished before the next starts
-            shards[r].gather(results[r], beside_next_scan=bool(step & 1))
+            shards[r].gather(results[r], beside_next_scan=bool(step & 1), copy_engines=step in (2, 3))
             shards[r].fence()
             ctxs[r].sync()
         tot, counts = shards[0].collect()
