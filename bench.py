@@ -479,6 +479,10 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     if world > 1:
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
     e2e_value = float(nscan) * rows * world * e2e_steps / (float(e2e_t.item()) * 1e-3)
+    if world > 1:                                                   # whole-job bytes: every rank moved its own
+        hb = torch.tensor([h2d, d2h], dtype=torch.int64, device=dev)
+        dist.all_reduce(hb)
+        h2d, d2h = int(hb[0].item()), int(hb[1].item())
     # the same with pageable (unpinned) host columns, one step: what a caller that does not allocate through mbc_host_alloc gets
     e2e_pageable = None
     if world == 1 and not args.no_pageable:
