@@ -21,7 +21,7 @@
 //   position                   recsPerDataPage * (dirPageIndex * 83 + dirSlot) + slotNo  (Heapfile.java:262-273,349-417)
 //
 // The host only follows the (small) directory structure; every data page is decoded on the GPU, one warp
-// per page, straight out of the uploaded file image.
+// per page out of a shared-memory copy of the page, from the uploaded file image.
 #include <algorithm>
 #include <cstring>
 #include <map>
@@ -42,49 +42,71 @@ struct PageRef {
 
 __device__ __forceinline__ uint32_t be16(const uint8_t* p) { return ((uint32_t)p[0] << 8) | p[1]; }
 
-// one warp per data page; lanes take slots lane, lane+32, ...
+// One warp per data page, kDecodeWarps pages per CTA and iteration.  The page is first copied whole into shared memory with
+// two 128-bit coalesced loads per lane (1 KB per warp instruction pair: the slot directory, the record offsets and the
+// records are then read out of shared memory instead of as scattered byte loads from HBM), then lanes take slots lane,
+// lane + 32, ...: consecutive slots are consecutive positions, so the column stores are coalesced.
 // `present` (bit p = word p/32, bit p%32) receives one bit per OCCUPIED slot: the Java purge deletes the heap records of
 // marked rows and then clears their markedDeleted bits (columnar/Columnarfile.java:874,912-914), so a purged position is an
 // empty slot (or an empty directory slot) that no Scan / TupleScan ever returns -- it must not come back as a live row.
-__global__ void __launch_bounds__(256) decode_pages_kernel(const uint8_t* db, const PageRef* pages, int64_t npages, int per_page,
-                                                           int type, int width, int stride, uint8_t* dst, int64_t nrows,
-                                                           uint32_t* present) {
+constexpr int kDecodeWarps = 8;
+
+__device__ __forceinline__ uint32_t sm_be16(const uint8_t* p) { return ((uint32_t)p[0] << 8) | p[1]; }
+
+__global__ void __launch_bounds__(kDecodeWarps * 32) decode_pages_kernel(const uint8_t* __restrict__ db, const PageRef* __restrict__ pages, int64_t npages,
+                                                                        int per_page, int type, int width, int stride, uint8_t* __restrict__ dst,
+                                                                        int64_t nrows, uint32_t* __restrict__ present) {
+    __shared__ __align__(16) uint8_t s_page[kDecodeWarps][kPage];
     const int lane = threadIdx.x & 31;
-    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (w >= npages) return;
-    const PageRef ref = pages[w];
-    const uint8_t* pg = db + (int64_t)ref.page_id * kPage;
-    const int slot_cnt = min((int)(int16_t)be16(pg), per_page);
-    for (int s0 = 0; s0 < slot_cnt; s0 += 32) {                     // warp-uniform trip count
-        const int s = s0 + lane;
-        const int64_t pos = (int64_t)ref.page_index * per_page + s;
-        bool occupied = false;
-        if (s < slot_cnt && pos < nrows) {
-            const uint8_t* sl = pg + kDpFixed + 4 * s;
-            const int len = (int)(int16_t)be16(sl);
-            const int off = (int)be16(sl + 2);
-            if (len >= 0 && off + len <= kPage) {                   // len < 0: EMPTY_SLOT (HFPage.java:300)
-                occupied = true;
-                const uint8_t* rec = pg + off;
-                if (type != MBC_ATTR_STRING) {
-                    // Convert.getIntValue / getFloValue: 4 bytes big-endian
-                    uint32_t v = ((uint32_t)rec[0] << 24) | ((uint32_t)rec[1] << 16) | ((uint32_t)rec[2] << 8) | rec[3];
-                    reinterpret_cast<uint32_t*>(dst)[pos] = v;
-                } else {
-                    // Convert.getStrValue: [length:2][modified UTF-8 bytes]; the column keeps the bytes zero padded
-                    int n = (int)be16(rec);
-                    n = min(n, min(width, len - 2));
-                    uint8_t* d = dst + pos * stride;
-                    for (int k = 0; k < n; ++k) d[k] = rec[2 + k];
+    const int warp = threadIdx.x >> 5;
+    uint8_t* pg = s_page[warp];
+    for (int64_t w = (int64_t)blockIdx.x * kDecodeWarps + warp; w < npages; w += (int64_t)gridDim.x * kDecodeWarps) {
+        const PageRef ref = pages[w];
+        const uint4* src = reinterpret_cast<const uint4*>(db + (int64_t)ref.page_id * kPage);   // the image is 256-byte aligned, pages 1 KB
+        const uint4 a = __ldg(src + lane), b = __ldg(src + 32 + lane);
+        __syncwarp();                                               // the previous page of this warp has been decoded
+        reinterpret_cast<uint4*>(pg)[lane] = a;
+        reinterpret_cast<uint4*>(pg)[32 + lane] = b;
+        __syncwarp();
+        const int slot_cnt = min((int)(int16_t)sm_be16(pg), per_page);
+        for (int s0 = 0; s0 < slot_cnt; s0 += 32) {                 // warp-uniform trip count
+            const int s = s0 + lane;
+            const int64_t pos = (int64_t)ref.page_index * per_page + s;
+            bool occupied = false;
+            if (s < slot_cnt && pos < nrows) {
+                const uint8_t* sl = pg + kDpFixed + 4 * s;
+                const int len = (int)(int16_t)sm_be16(sl);
+                const int off = (int)sm_be16(sl + 2);
+                if (len >= 0 && off + len <= kPage) {               // len < 0: EMPTY_SLOT (HFPage.java:300)
+                    occupied = true;
+                    const uint8_t* rec = pg + off;
+                    if (type != MBC_ATTR_STRING) {
+                        // Convert.getIntValue / getFloValue: 4 bytes big-endian
+                        const uint32_t v = (off & 3) == 0 ? __byte_perm(*reinterpret_cast<const uint32_t*>(rec), 0, 0x0123)
+                                                          : ((uint32_t)rec[0] << 24) | ((uint32_t)rec[1] << 16) | ((uint32_t)rec[2] << 8) | rec[3];
+                        reinterpret_cast<uint32_t*>(dst)[pos] = v;
+                    } else {
+                        // Convert.getStrValue: [length:2][modified UTF-8 bytes]; the column keeps the bytes zero padded
+                        int n = (int)sm_be16(rec);
+                        n = min(n, min(width, len - 2));
+                        uint32_t* d = reinterpret_cast<uint32_t*>(dst + pos * stride);       // stride is a multiple of 4
+                        for (int k = 0; k < n; k += 4) {
+                            uint32_t word = 0;
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                if (k + j < n) word |= (uint32_t)rec[2 + k + j] << (8 * j);
+                            d[k >> 2] = word;                       // the rest of the row keeps the table's zero fill
+                        }
+                    }
                 }
             }
+            // the warp's 32 consecutive positions straddle at most two words of the presence bitmap
+            const uint32_t m = __ballot_sync(0xFFFFFFFFu, occupied);
+            const int64_t pos0 = (int64_t)ref.page_index * per_page + s0;
+            const int sh = (int)(pos0 & 31);
+            if (lane == 0 && (m << sh)) atomicOr(present + (pos0 >> 5), m << sh);
+            if (lane == 1 && sh && (m >> (32 - sh))) atomicOr(present + (pos0 >> 5) + 1, m >> (32 - sh));
         }
-        // the warp's 32 consecutive positions straddle at most two words of the presence bitmap
-        const uint32_t m = __ballot_sync(0xFFFFFFFFu, occupied);
-        const int64_t pos0 = (int64_t)ref.page_index * per_page + s0;
-        const int sh = (int)(pos0 & 31);
-        if (lane == 0 && (m << sh)) atomicOr(present + (pos0 >> 5), m << sh);
-        if (lane == 1 && sh && (m >> (32 - sh))) atomicOr(present + (pos0 >> 5) + 1, m >> (32 - sh));
     }
 }
 
@@ -259,16 +281,23 @@ extern "C" int32_t mbc_table_ingest_dbfile(mbc_ctx* ctx, const uint8_t* db_bytes
     PageRef* d_pages = nullptr;
     uint32_t* d_present = nullptr;
     int* d_any = nullptr;
-    size_t max_pages = 1;
-    for (auto& p : pages) max_pages = std::max(max_pages, p.size());
+    size_t total_pages = 0;
+    std::vector<size_t> page_off(ncols, 0);
+    for (int c = 0; c < ncols; ++c) { page_off[c] = total_pages; total_pages += pages[c].size(); }
+    std::vector<PageRef> all_pages;
+    all_pages.reserve(std::max<size_t>(total_pages, 1));
+    for (auto& p : pages) all_pages.insert(all_pages.end(), p.begin(), p.end());
     const size_t mask_bytes = (size_t)t->words_pad * 4;
     const unsigned mask_grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>((t->words_pad + 255) / 256, ctx->sm_count * 8));
     int32_t s = dev_alloc(ctx, (void**)&d_db, (size_t)db_len, false);
-    if (s == MBC_OK) s = dev_alloc(ctx, (void**)&d_pages, max_pages * sizeof(PageRef), false);
+    if (s == MBC_OK) s = dev_alloc(ctx, (void**)&d_pages, std::max<size_t>(total_pages, 1) * sizeof(PageRef), false);
     if (s == MBC_OK) s = dev_alloc(ctx, (void**)&d_present, mask_bytes, false);
     if (s == MBC_OK) s = dev_alloc(ctx, (void**)&d_any, sizeof(int), true);
     if (s == MBC_OK && !t->d_deleted) s = dev_alloc(ctx, (void**)&t->d_deleted, mask_bytes, true);
+    // one upload of the image and of every column's page list, then the decodes queue back to back (nothing waits in between)
     if (s == MBC_OK && cudaMemcpyAsync(d_db, db_bytes, (size_t)db_len, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) s = MBC_ERR_CUDA;
+    if (s == MBC_OK && total_pages &&
+        cudaMemcpyAsync(d_pages, all_pages.data(), total_pages * sizeof(PageRef), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) s = MBC_ERR_CUDA;
     begin_timing(ctx);
     for (int c = 0; c < ncols && s == MBC_OK; ++c) {
         const Column& col = t->cols[c];
@@ -276,22 +305,19 @@ extern "C" int32_t mbc_table_ingest_dbfile(mbc_ctx* ctx, const uint8_t* db_bytes
         const int per_page = (kPage - kDpFixed) / (4 + rec);
         if (cudaMemsetAsync(d_present, 0, mask_bytes, ctx->stream) != cudaSuccess) { s = MBC_ERR_CUDA; break; }
         if (!pages[c].empty()) {
-            if (cudaMemcpyAsync(d_pages, pages[c].data(), pages[c].size() * sizeof(PageRef), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess ||
-                cudaStreamSynchronize(ctx->stream) != cudaSuccess) { s = MBC_ERR_CUDA; break; }
             const int64_t np = (int64_t)pages[c].size();
-            const unsigned grid = (unsigned)((np * 32 + 255) / 256);
-            decode_pages_kernel<<<grid, 256, 0, ctx->stream>>>(d_db, d_pages, np, per_page, col.type, col.width, col.stride, (uint8_t*)col.d, nrows,
-                                                               d_present);
+            const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>((np + kDecodeWarps - 1) / kDecodeWarps, (int64_t)ctx->sm_count * 8));
+            decode_pages_kernel<<<grid, kDecodeWarps * 32, 0, ctx->stream>>>(d_db, d_pages + page_off[c], np, per_page, col.type, col.width, col.stride,
+                                                                            (uint8_t*)col.d, nrows, d_present);
             ctx->launches++;
         }
         if (nrows > 0) {
             absent_rows_kernel<<<mask_grid, 256, 0, ctx->stream>>>(d_present, t->d_deleted, nrows, d_any);
             ctx->launches++;
         }
-        if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) s = MBC_ERR_CUDA;
     }
     end_timing(ctx);
-    if (s == MBC_OK && cudaGetLastError() != cudaSuccess) s = MBC_ERR_CUDA;
+    if (s == MBC_OK && (cudaStreamSynchronize(ctx->stream) != cudaSuccess || cudaGetLastError() != cudaSuccess)) s = MBC_ERR_CUDA;   // `all_pages` is pageable
 
     // ---- markedDeleted (BM.readBitSet :179-215): first record of every page of the <cf>.md chain, ORed in ----
     auto md = files.find(name + ".md");
