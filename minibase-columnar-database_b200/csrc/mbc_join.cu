@@ -420,14 +420,32 @@ __global__ void __launch_bounds__(256) join_minmax_kernel(const int32_t* key, Jo
     }
 }
 
+// Few groups (a low-cardinality key: C4's secondary variant has 1 000) would put every row's atomic on one of a few hundred
+// L2 addresses: the counts are then kept in a per-CTA shared-memory histogram and merged once per CTA and group.
+constexpr uint32_t kSmallGroups = 4096;
+
 __global__ void __launch_bounds__(256) join_outer_count_kernel(const __grid_constant__ EquiParams p) {
+    __shared__ uint32_t s_hist[kSmallGroups];
+    const bool small = p.g.mode == 0 && p.g.ngroups <= kSmallGroups;
+    if (small) {
+        for (uint32_t i = threadIdx.x; i < p.g.ngroups; i += blockDim.x) s_hist[i] = 0u;
+        __syncthreads();
+    }
     int selected = 0;
     for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < p.outer.nrows; o += (int64_t)gridDim.x * blockDim.x) {
         if (!side_selected(p.outer, o)) continue;
         long long g = group_of_outer(p.g, o, true);
         if (g < 0) { *p.overflow = 1; break; }
-        if (atomicAdd(p.n_outer + g, 1u) != 0u) p.overflow[1] = 1;
+        if (small) atomicAdd(&s_hist[g], 1u);
+        else if (atomicAdd(p.n_outer + g, 1u) != 0u) p.overflow[1] = 1;
         ++selected;
+    }
+    if (small) {
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < p.g.ngroups; i += blockDim.x) {
+            const uint32_t c = s_hist[i];
+            if (c && (atomicAdd(p.n_outer + i, c) != 0u || c > 1u)) p.overflow[1] = 1;      // some key on more than one outer row
+        }
     }
     // selected outer rows (dense-key test of the unique path): one atomic per warp, not one per row on a single address
     __syncwarp();
@@ -464,6 +482,12 @@ __global__ void __launch_bounds__(256) join_agg_pass_kernel(const __grid_constan
         ai[a] = (g.kind == MBC_AGG_MIN) ? (long long)INT32_MAX : (g.kind == MBC_AGG_MAX) ? (long long)INT32_MIN : 0ll;
         af[a] = (g.kind == MBC_AGG_MIN) ? (double)INFINITY : (g.kind == MBC_AGG_MAX) ? (double)-INFINITY : 0.0;
     }
+    __shared__ uint32_t s_hist[SIDE == 2 ? kSmallGroups : 1];
+    const bool small = SIDE == 2 && p.g.mode == 0 && p.g.ngroups <= kSmallGroups;
+    if (small) {
+        for (uint32_t i = threadIdx.x; i < p.g.ngroups; i += blockDim.x) s_hist[i] = 0u;
+        __syncthreads();
+    }
     const JoinSide& s = SIDE == 2 ? p.inner : p.outer;
     const uint64_t keep = l2_policy_evict_last();
     const int64_t nrows32 = (s.nrows + 31) & ~31ll;
@@ -473,7 +497,10 @@ __global__ void __launch_bounds__(256) join_agg_pass_kernel(const __grid_constan
             long long g = SIDE == 2 ? group_of_inner(p.g, r) : group_of_outer(p.g, r, false);
             if (g >= 0) {
                 weight = SIDE == 2 ? ld_keep_u32(p.n_outer + g, keep) : p.n_inner[g];
-                if (SIDE == 2 && weight) red_add_keep_u32(p.n_inner + g, 1u, keep);
+                if (SIDE == 2 && weight) {
+                    if (small) atomicAdd(&s_hist[g], 1u);
+                    else red_add_keep_u32(p.n_inner + g, 1u, keep);
+                }
             }
         }
         if (SIDE == 2 && p.inner_match) {
@@ -486,6 +513,13 @@ __global__ void __launch_bounds__(256) join_agg_pass_kernel(const __grid_constan
                 if ((g.side == 0 && SIDE == 2) || g.side == SIDE)
                     agg_fold(g, g.kind == MBC_AGG_COUNT || g.type == MBC_ATTR_INTEGER, ai[a], af[a], r, weight);
             }
+        }
+    }
+    if (small) {
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < p.g.ngroups; i += blockDim.x) {
+            const uint32_t c = s_hist[i];
+            if (c) atomicAdd(p.n_inner + i, c);
         }
     }
     // block reduction, one partial per block per aggregate (fixed order -> reproducible sums)
