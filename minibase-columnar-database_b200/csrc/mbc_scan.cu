@@ -302,7 +302,8 @@ static void plan_stream(mbc_ctx* ctx, ScanJob* job) {
     }
     if (off > (size_t)kStreamStageMax) return;
     if (!ctx->write_smem_set) {                                    // per device: opt in to > 48 KB of dynamic shared memory
-        if (cudaFuncSetAttribute(write_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStreamStageMax) != cudaSuccess ||
+        if (cudaFuncSetAttribute(write_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStreamStageMax + kListCap * 2) != cudaSuccess ||
+            cudaFuncSetAttribute(write_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStreamStageMax) != cudaSuccess ||
             cudaFuncSetAttribute(write_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStreamStageMax) != cudaSuccess) {
             cudaGetLastError();
             return;
@@ -598,6 +599,11 @@ static int32_t launch_job(ScanJob* job, bool first) {
                 (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, write_kernel<true>, kScanThreads, write_smem) != cudaSuccess || per_sm < 1))
                 per_sm = 1;
             write_kernel<true><<<std::min(p.ntiles, ctx->sm_count * per_sm), kScanThreads, write_smem, ctx->stream>>>(p);
+        } else if (stream_now && (!job->stream_forced || p.stream_min <= kSparseMax) && !getenv("MBC_STREAM_LEAN_OFF")) {
+            // armed by the density hint (or forced for every dense group): the lean kernel -- every dense group streams, the
+            // list shares the dynamic area
+            const size_t dyn = std::max<size_t>(write_smem + kSubRows * 2, (size_t)kListCap * 2);
+            write_stream_kernel<<<p.ntiles, kScanThreads, dyn, ctx->stream>>>(p);
         } else {
             write_kernel<false><<<p.ntiles, kScanThreads, write_smem, ctx->stream>>>(p);
         }

@@ -764,24 +764,44 @@ __device__ __forceinline__ void agg_fold4(const DevAgg& g, unsigned long long& a
     }
 }
 
-__device__ __forceinline__ void write_dense_tile_stream(const ScanParams& p, const int tile, uint8_t* s_stage, uint16_t* s_list, uint32_t* s_wtot,
-                                                        unsigned long long (*s_aggw)[kWarpsPerCta]) {
+// The tile's count, output offset and every step's bitmap word are independent loads: issued together (and, in
+// write_stream_kernel, together with the group's offsets), one DRAM/L2 round trip ahead of the column loads instead of one per step.
+constexpr int kStreamSteps = kTileRows / kSubRows;
+struct StreamTile {
+    uint32_t bits[kStreamSteps];
+    long long base;
+    int T;
+};
+__device__ __forceinline__ StreamTile stream_tile_load(const ScanParams& p, const int tile) {
+    StreamTile t;
+#pragma unroll
+    for (int sub = 0; sub < kStreamSteps; ++sub)                   // rows past the table hold no set bits
+        t.bits[sub] = __ldg(p.out_bitmap + (((int64_t)tile * kTileRows + sub * kSubRows) >> 5) + (threadIdx.x >> 3));
+    t.base = (long long)__ldg(p.tile_out + tile);
+    t.T = (int)__ldg(p.tile_counts + tile);
+    return t;
+}
+
+__device__ __forceinline__ void write_dense_tile_stream(const ScanParams& p, const int tile, const StreamTile& st_in, uint8_t* s_stage,
+                                                        uint16_t* s_list, uint32_t* s_wtot, unsigned long long (*s_aggw)[kWarpsPerCta]) {
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
-    const int T = (int)p.tile_counts[tile];
+    constexpr int kSteps = kStreamSteps;
+    const int T = st_in.T;
+    long long base = st_in.base;
     if (T == 0) {                                                  // block-uniform: nothing qualifies in this tile
         if (tid < p.nagg) p.partials[(size_t)tid * p.total_tiles + p.tile_base + tile] = agg_identity(p.aggs[tid]);
         return;
     }
-    long long base = (long long)p.tile_out[tile];
     unsigned long long acc[kMaxAgg];
 #pragma unroll
     for (int a = 0; a < kMaxAgg; ++a) acc[a] = a < p.nagg ? agg_identity(p.aggs[a]) : 0ull;
-    for (int sub = 0; sub < kTileRows / kSubRows; ++sub) {
-        const int64_t row0 = (int64_t)tile * kTileRows + sub * kSubRows;   // rows past the table hold no set bits
+#pragma unroll
+    for (int sub = 0; sub < kSteps; ++sub) {
+        const int64_t row0 = (int64_t)tile * kTileRows + sub * kSubRows;
         const int64_t my_row = row0 + tid * kVec;
-        const uint32_t bits = (__ldg(p.out_bitmap + (row0 >> 5) + (tid >> 3)) >> ((tid & 7) * 4)) & 0xFu;
+        const uint32_t bits = (st_in.bits[sub] >> ((tid & 7) * 4)) & 0xFu;
         // rank of this thread's first survivor among the step's survivors
         const int cnt = __popc(bits);
         int incl = cnt;
@@ -1034,7 +1054,7 @@ __global__ void __launch_bounds__(kScanThreads, MBC_WRITE_MIN_CTAS) write_kernel
             const int tl = blockIdx.x + (it0 + j) * gridDim.x;
             const int g0 = tl & ~(kGroupTiles - 1);
             const long long gtot = (long long)(p.tile_out[g0 + min(kGroupTiles, p.ntiles - g0)] - p.tile_out[g0]);
-            if (p.stream_dense && gtot >= p.stream_min) write_dense_tile_stream(p, tl, s_stage, s_list, s_wtot, s_aggw);
+            if (p.stream_dense && gtot >= p.stream_min) write_dense_tile_stream(p, tl, stream_tile_load(p, tl), s_stage, s_list, s_wtot, s_aggw);
             else write_dense_tile(p, tl, s_list, s_wtot, s_aggw);
         }
     }
@@ -1046,7 +1066,7 @@ __global__ void __launch_bounds__(kScanThreads, MBC_WRITE_MIN_CTAS) write_kernel
     const long long base = (long long)p.tile_out[tile0];
     const int total = (int)((long long)p.tile_out[tile0 + ntl] - base);
     if (total > kSparseMax) {                                      // block-uniform: dense group, every CTA writes its own tile
-        if (p.stream_dense && total >= p.stream_min) write_dense_tile_stream(p, tile, s_stage, s_list, s_wtot, s_aggw);
+        if (p.stream_dense && total >= p.stream_min) write_dense_tile_stream(p, tile, stream_tile_load(p, tile), s_stage, s_list, s_wtot, s_aggw);
         else write_dense_tile(p, tile, s_list, s_wtot, s_aggw);
         return;
     }
@@ -1057,6 +1077,36 @@ __global__ void __launch_bounds__(kScanThreads, MBC_WRITE_MIN_CTAS) write_kernel
     }
     write_sparse_group(p, tile0, ntl, base, total, s_list, s_wtot);
   }
+}
+
+// Write pass of a scan that is expected to be dense (armed by the density hint): one CTA per tile like write_kernel<false>, but
+// dense groups ALWAYS stream (write_dense_tile_stream) and the gather path is not compiled in, so the kernel fits 5 CTAs per
+// SM (48 registers; the rank -> row list lives in the dynamic shared memory next to the staging area): the streaming path is
+// bound by the DRAM round trip of every 1024-row step, i.e. by how many steps an SM keeps in flight.
+#ifndef MBC_STREAM_MIN_CTAS
+#define MBC_STREAM_MIN_CTAS 5
+#endif
+__global__ void __launch_bounds__(kScanThreads, MBC_STREAM_MIN_CTAS) write_stream_kernel(const __grid_constant__ ScanParams p) {
+    extern __shared__ __align__(16) uint8_t s_dyn[];               // [list: kListCap or kSubRows u16][staging of the streaming path]
+    __shared__ uint32_t s_wtot[kWarpsPerCta];
+    __shared__ unsigned long long s_aggw[kMaxAgg][kWarpsPerCta];
+    uint16_t* s_list = reinterpret_cast<uint16_t*>(s_dyn);
+    const int tid = threadIdx.x;
+    const int tile = blockIdx.x;
+    const int tile0 = tile & ~(kGroupTiles - 1);
+    const int ntl = min(kGroupTiles, p.ntiles - tile0);
+    const StreamTile mine = stream_tile_load(p, tile);             // issued with the group's offsets: one round trip
+    const long long base = (long long)__ldg(p.tile_out + tile0);
+    const int total = (int)((long long)__ldg(p.tile_out + tile0 + ntl) - base);
+    if (total > kSparseMax) {                                      // block-uniform: dense group, every CTA streams its own tile
+        write_dense_tile_stream(p, tile, mine, s_dyn + kSubRows * 2, s_list, s_wtot, s_aggw);
+        return;
+    }
+    if (tile != tile0 || total == 0) {
+        if (tid < p.nagg) p.partials[(size_t)tid * p.total_tiles + p.tile_base + tile] = agg_identity(p.aggs[tid]);
+        return;
+    }
+    write_sparse_group(p, tile0, ntl, base, total, s_list, s_wtot);   // the list takes the whole dynamic area here (>= kListCap u16)
 }
 
 // Reduce the per-tile partials of one aggregate (fixed association => reproducible sums): thread i folds
