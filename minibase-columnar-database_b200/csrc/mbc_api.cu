@@ -136,7 +136,6 @@ int32_t result_finalize(mbc_result* r) {
     r->ev_ready = nullptr;
     if (e != cudaSuccess) MBC_FAIL(MBC_ERR_CUDA, "deferred scan failed: %s", cudaGetErrorString(e));
     r->count = (int64_t)r->h_small[kMaxAgg];
-    if (r->nrows > 0) ctx->density_hint = (float)((double)r->count / (double)r->nrows);
     for (size_t a = 0; a < r->aggs.size(); ++a) {
         mbc_result::Agg& g = r->aggs[a];
         const bool integral = g.kind == MBC_AGG_COUNT || g.type == MBC_ATTR_INTEGER;

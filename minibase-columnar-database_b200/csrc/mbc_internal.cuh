@@ -99,7 +99,7 @@ struct mbc_ctx {
     cudaStream_t d2h_stream = nullptr;   // results of mbc_scan_host streaming back while later chunks upload
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
     int64_t launches = 0;
-    bool filter_smem_set = false, sort_smem_set = false, write_smem_set = false;   // per-device opt-in to > 48 KB of dynamic shared memory
+    bool filter_smem_set = false, sort_smem_set = false, staged_smem_set = false;   // per-device opt-in to > 48 KB of dynamic shared memory
     // single-residency scan (mbc_scan_fused.cuh): published tile counts, tagged with the launch epoch so the buffer is
     // never cleared between launches (zeroed when it is allocated and when the 20-bit epoch wraps)
     uint32_t* fused_flags = nullptr;
@@ -111,7 +111,6 @@ struct mbc_ctx {
     // free destroys it (a handle closed after its context must not touch freed memory)
     int64_t live_objects = 0;
     bool shutdown_pending = false;
-    float density_hint = 0.f;         // qualifying fraction of the last completed scan: picks the dense write path of the next
     float last_ms = 0.f;
     bool timing_split = false;
     float extra_ms = 0.f;                // device time of earlier timed segments of the same call

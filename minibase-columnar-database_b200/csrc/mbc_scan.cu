@@ -271,8 +271,8 @@ struct ScanJob {
     int64_t part_slots = 0;       // capacity (= stride) of the per-tile aggregate partials: one slot per tile of either engine
     int64_t part_done = 0;        // slots written by the launches so far
     size_t smem_bytes = 0;
-    size_t write_smem = 0;        // dynamic shared memory of the write pass (staging of the streaming dense path)
-    bool stream_forced = false;   // MBC_STREAM_MIN_PCT set: the streaming path is armed whatever the density hint says
+    size_t staged_smem = 0;       // ring of write_staged_kernel
+    bool staged_off = false;      // a launch whose projected columns are read in place from host memory gathers them
     int max_grid = 1;
     int launches = 0;             // launches so far: the running count is in slot launches & 1
     // single-residency engine (mbc_scan_fused.cuh): planned once per job, chosen per launch
@@ -286,39 +286,58 @@ struct ScanJob {
 };
 
 
-// Streaming dense write path (write_dense_tile_stream): the compacted values of 1024 rows of every projected field are
-// staged in shared memory, back to back.  Falls back to the gather path when a projected row is too wide.
-static void plan_stream(mbc_ctx* ctx, ScanJob* job) {
+// Dense groups through write_staged_kernel: every column the write pass reads (projected fields, aggregate sources) gets a
+// slice of a ring stage; the ring takes what two CTAs per SM leave of the shared memory.  Off (write_kernel's own dense paths
+// take over) when there is nothing to stage, or a stage is so wide that the ring would be shallower than two stages.
+static void plan_staged(mbc_ctx* ctx, ScanJob* job) {
     ScanParams& p = job->p;
-    p.stream_dense = 0;
-    job->write_smem = 0;
-    const char* e = getenv("MBC_WRITE_STREAM");                    // "0": the gather path of round 1 (tests, profiles)
+    p.stg_n = 0;
+    p.dense_staged = 0;
+    job->staged_smem = 0;
+    // groups above this many survivors read their columns whole through write_staged_kernel; measured crossover with the
+    // per-tile gather of write_kernel on B200 (profiles/README.md)
+    p.stg_min = kGroupRows * 28 / 100;
+    if (const char* g = getenv("MBC_STAGED_MIN_PCT")) p.stg_min = (int)((long long)kGroupRows * std::max(0, std::min(100, atoi(g))) / 100);
+    p.stg_min = std::max(p.stg_min, kSparseMax);
+    const char* e = getenv("MBC_WRITE_STAGED");                    // "0": the gather / streaming paths (tests, profiles)
     if (e && !strcmp(e, "0")) return;
+    int n = 0;
     size_t off = 0;
+    auto stage_of = [&](int col, int stride) -> int {
+        for (int i = 0; i < n; ++i) if (p.stg_col[i] == col) return i;
+        p.stg_col[n] = col;
+        p.stg_stride[n] = stride;
+        p.stg_off[n] = (int32_t)off;
+        off += (size_t)stride * kStgRows;
+        return n++;
+    };
     for (int c = 0; c < p.nproj; ++c) {
         if (p.proj[c].stride & 3) return;
-        p.stage_off[c] = (int32_t)off;
-        off += (size_t)p.proj[c].stride * kSubRows;
+        p.proj_stg[c] = (int8_t)stage_of(p.proj[c].col, p.proj[c].stride);
     }
-    if (off > (size_t)kStreamStageMax) return;
-    if (!ctx->write_smem_set) {                                    // per device: opt in to > 48 KB of dynamic shared memory
-        if (cudaFuncSetAttribute(write_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStreamStageMax + kListCap * 2) != cudaSuccess ||
-            cudaFuncSetAttribute(write_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStreamStageMax) != cudaSuccess ||
-            cudaFuncSetAttribute(write_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStreamStageMax) != cudaSuccess) {
+    for (int a = 0; a < p.nagg; ++a) p.agg_stg[a] = p.aggs[a].kind == MBC_AGG_COUNT ? (int8_t)-1 : (int8_t)stage_of(p.aggs[a].col, 4);
+    if (n == 0) return;                                             // positions / counts only: nothing to read but the bitmap
+    // per SM: 227 KB less the static arrays (list, barriers, partials) and the 1 KB the driver reserves per CTA, two CTAs
+    static size_t budget = 0;
+    if (!budget) {
+        cudaFuncAttributes fa;
+        if (cudaFuncGetAttributes(&fa, write_staged_kernel) != cudaSuccess) { cudaGetLastError(); return; }
+        budget = (227 * 1024 - 2 * (fa.sharedSizeBytes + 1024)) / 2 / 128 * 128;
+    }
+    int stages = (int)std::min<size_t>(kStgMaxStages, budget / off);
+    if (const char* m = getenv("MBC_STAGED_STAGES")) stages = std::min(stages, std::max(1, atoi(m)));
+    if (stages < 2) return;
+    if (!ctx->staged_smem_set) {
+        if (cudaFuncSetAttribute(write_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget) != cudaSuccess) {
             cudaGetLastError();
             return;
         }
-        ctx->write_smem_set = true;
+        ctx->staged_smem_set = true;
     }
-    p.stream_dense = 1;
-    // measured on B200 (100 M C2 rows): the gather path wins up to ~3/4 filled groups (0.93 vs 1.24 ms at 50 %), streaming
-    // above (1.42 vs 1.66 ms at 90 %): it moves exactly the algorithmic bytes but pays two barriers per 1024 rows
-    p.stream_min = kGroupRows * 3 / 4;
-    if (const char* m = getenv("MBC_STREAM_MIN_PCT")) {
-        p.stream_min = (int)((long long)kGroupRows * std::max(0, std::min(100, atoi(m))) / 100);
-        job->stream_forced = true;
-    }
-    job->write_smem = off;
+    p.stg_n = n;
+    p.stg_stages = stages;
+    p.stg_bytes = (int32_t)off;
+    job->staged_smem = (size_t)stages * off;
 }
 
 // Plan the single-residency engine (mbc_scan_fused.cuh) for this job: payload columns, ring depths, shared memory.
@@ -480,7 +499,7 @@ static int32_t prepare_job(const mbc_table* schema, const ScanRequest& rq, int64
     p.out_cap = capacity_rows;
     p.ntiles = INT32_MAX;                         // the grid bound comes from the device; bind_table sets the real count
     MBC_TRY(plan_staging(ctx, &p, &job->smem_bytes, &job->max_grid));
-    plan_stream(ctx, job);
+    plan_staged(ctx, job);
     plan_fused(ctx, job);
     return MBC_OK;
 }
@@ -493,6 +512,7 @@ static void bind_table(ScanJob* job, const mbc_table* t) {
     }
     for (int c = 0; c < p.nproj; ++c) p.proj[c].src = t->cols[p.proj[c].col].d;
     for (int s = 0; s < p.nstaged; ++s) p.staged_src[s] = t->cols[p.staged_cols[s]].d;
+    for (int i = 0; i < p.stg_n; ++i) p.stg_src[i] = t->cols[p.stg_col[i]].d;
     for (int a = 0; a < p.nagg; ++a)
         if (p.aggs[a].col >= 0) p.aggs[a].src = t->cols[p.aggs[a].col].d;
     p.deleted = t->has_deleted ? t->d_deleted : nullptr;
@@ -580,13 +600,10 @@ static int32_t launch_job(ScanJob* job, bool first) {
     bool need_write = p.out_pos || p.nproj > 0;
     for (int a = 0; a < p.nagg; ++a) need_write |= p.aggs[a].kind != MBC_AGG_COUNT;   // COUNT comes from the tile offsets
     if (need_write) {
-        // The streaming dense path costs every CTA of the write pass 28 KB of shared memory (and the SM that much L1): it is
-        // armed only when the last completed scan of this context was dense (>= 60 % of its rows qualified) or when the
-        // threshold is forced.  Either way the result is the same; a wrong guess leaves dense groups to the gather path.
-        const bool stream_now = p.stream_dense && (job->stream_forced || ctx->density_hint >= 0.6f);
-        const int stream_saved = p.stream_dense;
-        const size_t write_smem = stream_now ? job->write_smem : 0;
-        if (!stream_now) p.stream_dense = 0;
+        // groups above p.stg_min survivors go to write_staged_kernel (below) when their columns fit its ring; write_kernel
+        // writes the others (and those too when they do not)
+        const bool staged_now = p.stg_n > 0 && !job->staged_off;
+        p.dense_staged = staged_now ? 1 : 0;
         const char* pt = getenv("MBC_WRITE_PERSISTENT_TILES");          // tests force either form
         const int persistent_min_tiles = pt ? atoi(pt) : 49152;
         if (p.ntiles >= persistent_min_tiles) {
@@ -594,21 +611,16 @@ static int32_t launch_job(ScanJob* job, bool first) {
             if (!ctas_per_sm &&
                 (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, write_kernel<true>, kScanThreads, 0) != cudaSuccess || ctas_per_sm < 1))
                 ctas_per_sm = 1;
-            int per_sm = ctas_per_sm;
-            if (write_smem &&
-                (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, write_kernel<true>, kScanThreads, write_smem) != cudaSuccess || per_sm < 1))
-                per_sm = 1;
-            write_kernel<true><<<std::min(p.ntiles, ctx->sm_count * per_sm), kScanThreads, write_smem, ctx->stream>>>(p);
-        } else if (stream_now && (!job->stream_forced || p.stream_min <= kSparseMax) && !getenv("MBC_STREAM_LEAN_OFF")) {
-            // armed by the density hint (or forced for every dense group): the lean kernel -- every dense group streams, the
-            // list shares the dynamic area
-            const size_t dyn = std::max<size_t>(write_smem + kSubRows * 2, (size_t)kListCap * 2);
-            write_stream_kernel<<<p.ntiles, kScanThreads, dyn, ctx->stream>>>(p);
+            write_kernel<true><<<std::min(p.ntiles, ctx->sm_count * ctas_per_sm), kScanThreads, 0, ctx->stream>>>(p);
         } else {
-            write_kernel<false><<<p.ntiles, kScanThreads, write_smem, ctx->stream>>>(p);
+            write_kernel<false><<<p.ntiles, kScanThreads, 0, ctx->stream>>>(p);
         }
-        p.stream_dense = stream_saved;
         ctx->launches++;
+        if (staged_now) {
+            p.dense_staged = 0;
+            write_staged_kernel<<<std::min(p.ntiles, ctx->sm_count * 2), kStgThreads, job->staged_smem, ctx->stream>>>(p);
+            ctx->launches++;
+        }
     }
     if (job->r->ev_mid[2]) cudaEventRecord(job->r->ev_mid[2], ctx->stream);
     MBC_CUDA(cudaGetLastError());
@@ -660,7 +672,6 @@ static int32_t finish_job_device(ScanJob* job, bool deferred = false) {
     MBC_CUDA(cudaMemcpyAsync(host_small, r->d_aggs, sizeof(host_small), cudaMemcpyDeviceToHost, ctx->stream));
     MBC_CUDA(cudaStreamSynchronize(ctx->stream));
     r->count = (int64_t)host_small[kMaxAgg];
-    if (r->nrows > 0) ctx->density_hint = (float)((double)r->count / (double)r->nrows);
     decode_aggs(r, p.aggs, p.nagg, host_small);
     if (r->ev_t0 && r->ev_t1 && cudaEventElapsedTime(&r->kernel_ms, r->ev_t0, r->ev_t1) != cudaSuccess) r->kernel_ms = -1.f;
     result_phase_times(r);
@@ -874,7 +885,7 @@ static int32_t run_scan_host(mbc_ctx* ctx, int32_t ncols, const mbc_coldesc* col
         st->pos_base = position_base + row0;
         bind_table(&job, st);
         job.fused_off = late_mode;
-        if (late_mode) job.p.stream_dense = 0;                            // whole-tile loads would pull every row over PCIe
+        job.staged_off = late_mode;                                       // whole-tile loads would pull every row over PCIe
         if (late_mode) {                                                  // survivors of these columns come from host memory
             ScanParams& p = job.p;
             for (int c = 0; c < p.nproj; ++c)

@@ -73,6 +73,7 @@ struct DevAgg {
     int32_t pad;
 };
 
+constexpr int kMaxStg = kMaxProj + kMaxAgg;      // columns write_staged_kernel can stage (projected fields + aggregate sources)
 constexpr int kMaxStaged = 4;                    // 4-byte predicate columns staged through shared memory
 constexpr int kStageColBytes = kTileRows * 4;    // one column of one tile: 16 KB
 
@@ -80,9 +81,18 @@ struct ScanParams {
     int64_t nrows;
     int64_t pos_base;
     int64_t out_cap;              // rows the output buffers hold (debug checks)
-    int32_t stream_dense;         // 1: the tiles of well-filled groups are streamed through the staging of write_dense_tile_stream
-    int32_t stream_min;           // ... groups of kGroupTiles tiles with at least this many survivors; sparser dense groups are gathered
-    int32_t stage_off[kMaxProj];  // byte offset of every projected field's compacted values in that staging
+    // dense tiles through write_staged_kernel: every column the write pass reads is bulk-copied (TMA) 1024 rows at a time
+    int32_t stg_min;              // groups of kGroupTiles tiles with MORE survivors than this go to write_staged_kernel (>= kSparseMax)
+    int32_t stg_n;                // staged columns; 0 = the path is off and write_kernel writes the dense groups itself
+    int32_t stg_stages;           // depth of the ring
+    int32_t stg_bytes;            // bytes of one stage = kStgRows * sum of the staged strides
+    int32_t dense_staged;         // 1 in the launch of write_kernel that leaves the dense groups to write_staged_kernel
+    const void* stg_src[kMaxStg];
+    int32_t stg_stride[kMaxStg];
+    int32_t stg_off[kMaxStg];     // byte offset of a column's 1024 rows inside a stage
+    int32_t stg_col[kMaxStg];     // host bookkeeping: table column
+    int8_t proj_stg[kMaxProj];    // staged column of every projected field
+    int8_t agg_stg[kMaxAgg];      // ... and of every aggregate's source (-1: COUNT)
     int32_t ntiles;
     int32_t nterms;
     int32_t nproj;
@@ -323,6 +333,24 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "bra LAB_WAIT;\n"
         "DONE:\n"
         "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// wait for the phase of `bar` with the given parity; the hardware suspends the thread between polls
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
+    uint32_t ok = 0;
+    while (!ok) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity), "r"(1000000u)
+            : "memory");
+    }
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 // 1-D bulk copy global -> shared through the TMA engine; completion is signalled on `bar` (complete_tx)
 __device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
@@ -576,7 +604,7 @@ constexpr int kGroupWords = kGroupRows / 32;
 constexpr int kThreadWords = kGroupWords / kScanThreads;           // 4 (or 8) -> one (two) 128-bit loads per thread
 constexpr int kListCap = MBC_SPARSE_MAX > kTileRows ? MBC_SPARSE_MAX : kTileRows;
 constexpr int kSparseMax = MBC_SPARSE_MAX;                         // survivors per group handled item-per-warp
-static_assert(kGroupRows <= 65536 && kThreadWords % 4 == 0 && kSparseMax <= kListCap && kWarpsPerCta <= 32, "group geometry");
+static_assert(kGroupRows <= 65536 && kThreadWords % 4 == 0 && kSparseMax <= kListCap && kTileRows <= kListCap && kWarpsPerCta <= 32, "group geometry");
 
 template <typename V>
 __device__ __forceinline__ void gather_store(const V* __restrict__ src, V* __restrict__ dst, const uint16_t* list, int first,
@@ -645,20 +673,29 @@ __device__ __forceinline__ unsigned long long gather_fold(const DevAgg& g, int64
 
 // One tile of a dense group: ranks from the bitmap in the filter pass's 16-rows-per-thread layout (the expansion is
 // 16 predicated stores), rank -> row list, one thread per survivor.  Writes the tile's own partials.
-__device__ __forceinline__ void write_dense_tile(const ScanParams& p, const int tile, uint16_t* s_list, uint32_t* s_wtot,
-                                                 unsigned long long (*s_aggw)[kWarpsPerCta]) {
-    const int tid = threadIdx.x;
-    const int lane = tid & 31;
-    const int warp = tid >> 5;
-    const int T = (int)p.tile_counts[tile];
-    if (T == 0) {                                                  // block-uniform: nothing qualifies in this tile
-        if (tid < p.nagg) p.partials[(size_t)tid * p.total_tiles + p.tile_base + tile] = agg_identity(p.aggs[tid]);
-        return;
-    }
-    const long long base = (long long)p.tile_out[tile];
-    const int64_t tile_row0 = (int64_t)tile * kTileRows;
+// What a CTA needs before it can touch a column of its tile: the thread's selection bits, the tile's count and its output
+// offset.  They are independent loads of data the earlier launches left in L2, but an L2 round trip under a saturated HBM
+// is ~2 us: the callers issue them in ONE round (with the group's offsets, or while the previous tile is being written)
+// instead of one after the other.
+struct DenseTile {
+    uint32_t mask;
+    long long base;
+    int T;
+};
+__device__ __forceinline__ DenseTile dense_tile_load(const ScanParams& p, const int tile) {
+    DenseTile d;
+    d.mask = load_bits(p.out_bitmap, (int64_t)tile * kTileRows + (threadIdx.x >> 5) * kWarpRows, threadIdx.x & 31);
+    d.base = (long long)__ldg(p.tile_out + tile);
+    d.T = (int)__ldg(p.tile_counts + tile);
+    return d;
+}
+
+// Rank -> row list of one tile from the selection bits in the filter pass's 16-rows-per-thread layout (the expansion is 16
+// predicated stores); s_wtot[w] is left holding the survivors of warp w's 512 rows.  Two barriers.
+__device__ __forceinline__ void tile_list_build(const uint32_t mask, uint16_t* s_list, uint32_t* s_wtot) {
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
     {
-        const uint32_t mask = load_bits(p.out_bitmap, tile_row0 + warp * kWarpRows, lane);
         const uint32_t packed = __popc(mask & 0xFu) | (__popc(mask & 0xF0u) << 8) | (__popc(mask & 0xF00u) << 16) |
                                 (__popc(mask & 0xF000u) << 24);
         uint32_t incl = packed;
@@ -691,6 +728,21 @@ __device__ __forceinline__ void write_dense_tile(const ScanParams& p, const int 
         }
         __syncthreads();
     }
+}
+
+__device__ __forceinline__ void write_dense_tile(const ScanParams& p, const int tile, const DenseTile& d, uint16_t* s_list, uint32_t* s_wtot,
+                                                 unsigned long long (*s_aggw)[kWarpsPerCta]) {
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    const int T = d.T;
+    if (T == 0) {                                                  // block-uniform: nothing qualifies in this tile
+        if (tid < p.nagg) p.partials[(size_t)tid * p.total_tiles + p.tile_base + tile] = agg_identity(p.aggs[tid]);
+        return;
+    }
+    const long long base = d.base;
+    const int64_t tile_row0 = (int64_t)tile * kTileRows;
+    tile_list_build(d.mask, s_list, s_wtot);
     const uint16_t* list = s_list;
     if (p.out_pos)
         for (int k = tid; k < T; k += kScanThreads) p.out_pos[base + k] = p.pos_base + tile_row0 + list[k];
@@ -724,15 +776,7 @@ __device__ __forceinline__ void write_dense_tile(const ScanParams& p, const int 
     }
 }
 
-// One tile of a dense group, STREAMED: the tile is taken 1024 rows at a time; every thread loads the values of its 4
-// consecutive rows with 128-bit coalesced loads (each projected column is read whole, once: no gathers, no 64..128-byte
-// DRAM fetch around a 4-byte value), ranks its survivors with a block scan of the selection nibbles, drops the survivors'
-// values at their ranks in a shared-memory staging area, and the CTA copies the compacted rows out with coalesced stores.
-// Aggregates are folded from the registers that hold the loaded values.  Replaces the rank -> row list + per-survivor
-// gather of write_dense_tile for scans whose projected row fits the staging area (<= kStreamStageMax bytes per 1024 rows).
-constexpr int kSubRows = kScanThreads * kVec;                      // 1024 rows per step
-constexpr int kStreamStageMax = 64 * 1024;
-
+// fold of four values of one aggregate source, bit j of `bits` says whether value j takes part (write_staged_kernel)
 __device__ __forceinline__ void agg_fold4(const DevAgg& g, unsigned long long& acc, const uint4 v, uint32_t bits) {
     const uint32_t x[4] = {v.x, v.y, v.z, v.w};
     if (g.type == MBC_ATTR_INTEGER) {
@@ -761,165 +805,6 @@ __device__ __forceinline__ void agg_fold4(const DevAgg& g, unsigned long long& a
             for (int j = 0; j < 4; ++j) if ((bits >> j) & 1u) a = fmax(a, (double)__uint_as_float(x[j]));
         }
         acc = (unsigned long long)__double_as_longlong(a);
-    }
-}
-
-// The tile's count, output offset and every step's bitmap word are independent loads: issued together (and, in
-// write_stream_kernel, together with the group's offsets), one DRAM/L2 round trip ahead of the column loads instead of one per step.
-constexpr int kStreamSteps = kTileRows / kSubRows;
-struct StreamTile {
-    uint32_t bits[kStreamSteps];
-    long long base;
-    int T;
-};
-__device__ __forceinline__ StreamTile stream_tile_load(const ScanParams& p, const int tile) {
-    StreamTile t;
-#pragma unroll
-    for (int sub = 0; sub < kStreamSteps; ++sub)                   // rows past the table hold no set bits
-        t.bits[sub] = __ldg(p.out_bitmap + (((int64_t)tile * kTileRows + sub * kSubRows) >> 5) + (threadIdx.x >> 3));
-    t.base = (long long)__ldg(p.tile_out + tile);
-    t.T = (int)__ldg(p.tile_counts + tile);
-    return t;
-}
-
-__device__ __forceinline__ void write_dense_tile_stream(const ScanParams& p, const int tile, const StreamTile& st_in, uint8_t* s_stage,
-                                                        uint16_t* s_list, uint32_t* s_wtot, unsigned long long (*s_aggw)[kWarpsPerCta]) {
-    const int tid = threadIdx.x;
-    const int lane = tid & 31;
-    const int warp = tid >> 5;
-    constexpr int kSteps = kStreamSteps;
-    const int T = st_in.T;
-    long long base = st_in.base;
-    if (T == 0) {                                                  // block-uniform: nothing qualifies in this tile
-        if (tid < p.nagg) p.partials[(size_t)tid * p.total_tiles + p.tile_base + tile] = agg_identity(p.aggs[tid]);
-        return;
-    }
-    unsigned long long acc[kMaxAgg];
-#pragma unroll
-    for (int a = 0; a < kMaxAgg; ++a) acc[a] = a < p.nagg ? agg_identity(p.aggs[a]) : 0ull;
-#pragma unroll
-    for (int sub = 0; sub < kSteps; ++sub) {
-        const int64_t row0 = (int64_t)tile * kTileRows + sub * kSubRows;
-        const int64_t my_row = row0 + tid * kVec;
-        const uint32_t bits = (st_in.bits[sub] >> ((tid & 7) * 4)) & 0xFu;
-        // rank of this thread's first survivor among the step's survivors
-        const int cnt = __popc(bits);
-        int incl = cnt;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int n = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-            if (lane >= o) incl += n;
-        }
-        if (lane == 31) s_wtot[warp] = (uint32_t)incl;
-        __syncthreads();                                           // also: the previous step's copy-out is complete
-        uint32_t below = 0, total = 0;
-#pragma unroll
-        for (int w = 0; w < kWarpsPerCta; ++w) {
-            const uint32_t t = s_wtot[w];
-            total += t;
-            if (w < warp) below += t;
-        }
-        const int Ts = (int)total;
-        if (Ts == 0) { __syncthreads(); continue; }                // block-uniform
-        const int r0 = (int)below + incl - cnt;
-        if (p.out_pos) {
-            int r = r0;
-#pragma unroll
-            for (int j = 0; j < kVec; ++j)
-                if ((bits >> j) & 1u) s_list[r++] = (uint16_t)(tid * kVec + j);
-        }
-        for (int c = 0; c < p.nproj; ++c) {                        // iterator/Projection.java:103-144
-            const DevProj& pr = p.proj[c];
-            uint8_t* st = s_stage + p.stage_off[c];
-            if (pr.stride == 4) {
-                const uint4 v = ldg128(reinterpret_cast<const uint32_t*>(pr.src) + my_row);
-                const uint32_t x[4] = {v.x, v.y, v.z, v.w};
-                int r = r0;
-#pragma unroll
-                for (int j = 0; j < kVec; ++j)
-                    if ((bits >> j) & 1u) reinterpret_cast<uint32_t*>(st)[r++] = x[j];
-            } else if (pr.stride == 16) {
-                uint4 v[kVec];
-#pragma unroll
-                for (int j = 0; j < kVec; ++j) v[j] = ldg128(reinterpret_cast<const uint4*>(pr.src) + my_row + j);
-                int r = r0;
-#pragma unroll
-                for (int j = 0; j < kVec; ++j)
-                    if ((bits >> j) & 1u) reinterpret_cast<uint4*>(st)[r++] = v[j];
-            } else {
-                const int words = pr.stride >> 2;
-                int r = r0;
-                for (int j = 0; j < kVec; ++j) {
-                    if (!((bits >> j) & 1u)) continue;
-                    const uint32_t* src = reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(pr.src) + (my_row + j) * pr.stride);
-                    uint32_t* d = reinterpret_cast<uint32_t*>(st + (size_t)r * pr.stride);
-                    for (int w = 0; w < words; ++w) d[w] = __ldg(src + w);
-                    ++r;
-                }
-            }
-        }
-#pragma unroll
-        for (int a = 0; a < kMaxAgg; ++a) {                        // folded from the loaded values (a projected column's lines are in L1)
-            if (a >= p.nagg) break;
-            const DevAgg& g = p.aggs[a];
-            if (g.kind == MBC_AGG_COUNT) continue;
-            agg_fold4(g, acc[a], ldg128(reinterpret_cast<const uint32_t*>(g.src) + my_row), bits);
-        }
-        __syncthreads();                                           // the step's survivors are staged
-        // copy-out: thread t takes ranks t, t + 256, t + 512, t + 768 (Ts <= 1024): four predicated, coalesced stores per field
-        if (p.out_pos) {
-            int64_t* dst = p.out_pos + base + tid;
-            const int64_t pos0 = p.pos_base + row0;
-#pragma unroll
-            for (int i = 0; i < kVec; ++i)
-                if (tid + i * kScanThreads < Ts) dst[i * kScanThreads] = pos0 + s_list[tid + i * kScanThreads];
-        }
-        for (int c = 0; c < p.nproj; ++c) {
-            const DevProj& pr = p.proj[c];
-            const uint8_t* st = s_stage + p.stage_off[c];
-            if (pr.stride == 4) {
-                uint32_t* dst = reinterpret_cast<uint32_t*>(pr.dst) + base + tid;
-                const uint32_t* src = reinterpret_cast<const uint32_t*>(st) + tid;
-#pragma unroll
-                for (int i = 0; i < kVec; ++i)
-                    if (tid + i * kScanThreads < Ts) dst[i * kScanThreads] = src[i * kScanThreads];
-            } else if (pr.stride == 16) {
-                uint4* dst = reinterpret_cast<uint4*>(pr.dst) + base + tid;
-                const uint4* src = reinterpret_cast<const uint4*>(st) + tid;
-#pragma unroll
-                for (int i = 0; i < kVec; ++i)
-                    if (tid + i * kScanThreads < Ts) dst[i * kScanThreads] = src[i * kScanThreads];
-            } else {
-                const int words = Ts * (pr.stride >> 2);
-                uint32_t* dst = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(pr.dst) + base * pr.stride);
-                for (int k = tid; k < words; k += kScanThreads) dst[k] = reinterpret_cast<const uint32_t*>(st)[k];
-            }
-        }
-        base += Ts;
-    }
-    // the tile's aggregate partial: lanes butterflied, warps combined in order
-    if (p.nagg > 0) {
-#pragma unroll
-        for (int a = 0; a < kMaxAgg; ++a) {
-            if (a >= p.nagg) break;
-            const DevAgg& g = p.aggs[a];
-            unsigned long long v = acc[a];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) v = agg_merge(g, v, __shfl_xor_sync(0xFFFFFFFFu, v, o));
-            if (lane == 0) s_aggw[a][warp] = v;
-        }
-        __syncthreads();
-        if (tid < p.nagg) {
-            const DevAgg& g = p.aggs[tid];
-            unsigned long long v;
-            if (g.kind == MBC_AGG_COUNT) {
-                v = (unsigned long long)T;
-            } else {
-                v = s_aggw[tid][0];
-                for (int x = 1; x < kWarpsPerCta; ++x) v = agg_merge(g, v, s_aggw[tid][x]);
-            }
-            p.partials[(size_t)tid * p.total_tiles + p.tile_base + tile] = v;
-        }
     }
 }
 
@@ -998,7 +883,6 @@ __device__ __forceinline__ void write_sparse_group(const ScanParams& p, const in
 
 template <bool kPersistent>
 __global__ void __launch_bounds__(kScanThreads, MBC_WRITE_MIN_CTAS) write_kernel(const __grid_constant__ ScanParams p) {
-    extern __shared__ __align__(16) uint8_t s_stage[];             // staging of write_dense_tile_stream (p.stream_dense)
     __shared__ uint16_t s_list[kListCap];                          // survivor rows within the group / tile, by rank
     __shared__ uint32_t s_wtot[kWarpsPerCta];
     __shared__ unsigned long long s_aggw[kMaxAgg][kWarpsPerCta];
@@ -1041,21 +925,29 @@ __global__ void __launch_bounds__(kScanThreads, MBC_WRITE_MIN_CTAS) write_kernel
         if (it0 + tid < niter) {
             const int tile0 = tile_t & ~(kGroupTiles - 1);
             const int ntl = min(kGroupTiles, p.ntiles - tile0);
-            dense = (long long)(p.tile_out[tile0 + ntl] - p.tile_out[tile0]) > (long long)kSparseMax;
+            const long long gtot = (long long)(p.tile_out[tile0 + ntl] - p.tile_out[tile0]);
+            dense = gtot > (long long)kSparseMax && !(p.dense_staged && gtot > (long long)p.stg_min);   // the fullest go to write_staged_kernel
         }
         const uint32_t flags = __ballot_sync(0xFFFFFFFFu, dense);
         __syncthreads();                                           // the previous round is done with s_flags
         if ((tid & 31) == 0) s_flags[tid >> 5] = flags;
         __syncthreads();
         const int n = min(kScanThreads, niter - it0);
-        for (int j = 0; j < n; ++j) {
-            if (!((s_flags[j >> 5] >> (j & 31)) & 1u)) continue;   // block-uniform
+        auto next_dense = [&](int j) {                             // block-uniform
+            while (j < n && !((s_flags[j >> 5] >> (j & 31)) & 1u)) ++j;
+            return j;
+        };
+        int j = next_dense(0);
+        DenseTile cur = {0u, 0ll, 0};
+        if (j < n) cur = dense_tile_load(p, blockIdx.x + (it0 + j) * gridDim.x);
+        while (j < n) {
+            const int jn = next_dense(j + 1);
+            DenseTile nxt = {0u, 0ll, 0};
+            if (jn < n) nxt = dense_tile_load(p, blockIdx.x + (it0 + jn) * gridDim.x);   // in flight while tile j is written
             __syncthreads();                                       // the shared arrays are reused from tile to tile
-            const int tl = blockIdx.x + (it0 + j) * gridDim.x;
-            const int g0 = tl & ~(kGroupTiles - 1);
-            const long long gtot = (long long)(p.tile_out[g0 + min(kGroupTiles, p.ntiles - g0)] - p.tile_out[g0]);
-            if (p.stream_dense && gtot >= p.stream_min) write_dense_tile_stream(p, tl, stream_tile_load(p, tl), s_stage, s_list, s_wtot, s_aggw);
-            else write_dense_tile(p, tl, s_list, s_wtot, s_aggw);
+            write_dense_tile(p, blockIdx.x + (it0 + j) * gridDim.x, cur, s_list, s_wtot, s_aggw);
+            cur = nxt;
+            j = jn;
         }
     }
   } else {
@@ -1063,11 +955,12 @@ __global__ void __launch_bounds__(kScanThreads, MBC_WRITE_MIN_CTAS) write_kernel
     const int tile = blockIdx.x;
     const int tile0 = tile & ~(kGroupTiles - 1);
     const int ntl = min(kGroupTiles, p.ntiles - tile0);            // tiles of this group
-    const long long base = (long long)p.tile_out[tile0];
-    const int total = (int)((long long)p.tile_out[tile0 + ntl] - base);
+    const DenseTile mine = dense_tile_load(p, tile);               // one round of loads with the group's offsets
+    const long long base = (long long)__ldg(p.tile_out + tile0);
+    const int total = (int)((long long)__ldg(p.tile_out + tile0 + ntl) - base);
     if (total > kSparseMax) {                                      // block-uniform: dense group, every CTA writes its own tile
-        if (p.stream_dense && total >= p.stream_min) write_dense_tile_stream(p, tile, stream_tile_load(p, tile), s_stage, s_list, s_wtot, s_aggw);
-        else write_dense_tile(p, tile, s_list, s_wtot, s_aggw);
+        if (p.dense_staged && total > p.stg_min) return;           // ... or write_staged_kernel does, in the next launch
+        write_dense_tile(p, tile, mine, s_list, s_wtot, s_aggw);
         return;
     }
     // sparse group: its first CTA writes all of it; one partial for the group, the other tiles carry the identity
@@ -1079,34 +972,221 @@ __global__ void __launch_bounds__(kScanThreads, MBC_WRITE_MIN_CTAS) write_kernel
   }
 }
 
-// Write pass of a scan that is expected to be dense (armed by the density hint): one CTA per tile like write_kernel<false>, but
-// dense groups ALWAYS stream (write_dense_tile_stream) and the gather path is not compiled in, so the kernel fits 5 CTAs per
-// SM (48 registers; the rank -> row list lives in the dynamic shared memory next to the staging area): the streaming path is
-// bound by the DRAM round trip of every 1024-row step, i.e. by how many steps an SM keeps in flight.
-#ifndef MBC_STREAM_MIN_CTAS
-#define MBC_STREAM_MIN_CTAS 5
-#endif
-__global__ void __launch_bounds__(kScanThreads, MBC_STREAM_MIN_CTAS) write_stream_kernel(const __grid_constant__ ScanParams p) {
-    extern __shared__ __align__(16) uint8_t s_dyn[];               // [list: kListCap or kSubRows u16][staging of the streaming path]
-    __shared__ uint32_t s_wtot[kWarpsPerCta];
+// ---- pass 2, dense groups: TMA-staged compaction ---------------------------------------------------------------------
+// The tiles of the fullest groups (> p.stg_min survivors in kGroupTiles tiles) read every column of the write pass WHOLE:
+// above ~1/3 density nearly every 32-byte sector of a column holds a survivor, so a gather fetches the column anyway -- through
+// 4-byte loads whose addresses depend on the rank -> row list, which depends on the selection bits, which depend on the
+// tile offsets: three L2/DRAM round trips (~2 us each under a saturated HBM) in front of every tile's first useful byte.
+// Here persistent CTAs (two per SM) keep a ring of kStgRows-row stages filled by the TMA engine (cp.async.bulk, one bulk copy
+// per column and stage, completion on an mbarrier); a producer warp runs ahead of the consumers by the depth of the ring and
+// depends on none of those loads.  The eight consumer warps never wait for each other: warp w owns rows [128 w, 128 w + 128)
+// of every stage, lane l rows 32 j + l of them (j = 0..3), so that
+//   * the selection bits of an instruction's 32 rows are ONE word of the bitmap (the warp's four words come by shuffle from
+//     the lane that loaded them; a lane holds four of the tile's 128 words, fetched one tile ahead together with the tile's
+//     output offset),
+//   * the rank of a row is the tile prefix of that word (one warp scan of popcounts per tile) plus popc(word & lanes below),
+//   * shared-memory reads are conflict free (consecutive lanes, consecutive rows) and every store instruction writes the
+//     survivors of its 32 rows back to back: compaction happens in the addresses, nothing is staged twice.
+// A stage is handed back to the producer by one mbarrier arrival per warp.  Aggregates are folded from the same shared-memory
+// values into per-lane accumulators that live for the whole kernel: one partial per CTA (in the slot of its first dense
+// tile; its other dense tiles carry the identity, COUNT slots the tile's own count), so sums stay reproducible run to run.
+// write_kernel (launched first, p.dense_staged = 1) writes the other groups.
+constexpr int kStgRows = 1024;
+constexpr int kStgSteps = kTileRows / kStgRows;
+constexpr int kStgMaxStages = 6;
+constexpr int kStgThreads = kScanThreads + 32;                     // eight consumer warps + the producer warp
+constexpr int kStgWarpRows = kStgRows / kWarpsPerCta;              // 128: four 32-row instructions per warp and stage
+static_assert(kStgWarpRows == 128 && kTileRows / 32 == 128 && kStgSteps * kWarpsPerCta == 32, "stage geometry: a lane holds 4 of the tile's 128 bitmap words");
+
+__global__ void __launch_bounds__(kStgThreads, 2) write_staged_kernel(const __grid_constant__ ScanParams p) {
+    extern __shared__ __align__(128) uint8_t s_ring[];             // [stg_stages][stg_bytes]
+    __shared__ __align__(8) uint64_t s_full[kStgMaxStages];
+    __shared__ __align__(8) uint64_t s_empty[kStgMaxStages];
     __shared__ unsigned long long s_aggw[kMaxAgg][kWarpsPerCta];
-    uint16_t* s_list = reinterpret_cast<uint16_t*>(s_dyn);
+    __shared__ uint32_t s_flags[kWarpsPerCta];
     const int tid = threadIdx.x;
-    const int tile = blockIdx.x;
-    const int tile0 = tile & ~(kGroupTiles - 1);
-    const int ntl = min(kGroupTiles, p.ntiles - tile0);
-    const StreamTile mine = stream_tile_load(p, tile);             // issued with the group's offsets: one round trip
-    const long long base = (long long)__ldg(p.tile_out + tile0);
-    const int total = (int)((long long)__ldg(p.tile_out + tile0 + ntl) - base);
-    if (total > kSparseMax) {                                      // block-uniform: dense group, every CTA streams its own tile
-        write_dense_tile_stream(p, tile, mine, s_dyn + kSubRows * 2, s_list, s_wtot, s_aggw);
-        return;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    const int S = p.stg_stages;
+    const uint32_t stage_bytes = (uint32_t)p.stg_bytes;
+    if (tid == 0) {
+        for (int s = 0; s < S; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], kWarpsPerCta); }
+        mbar_fence_init();
     }
-    if (tile != tile0 || total == 0) {
-        if (tid < p.nagg) p.partials[(size_t)tid * p.total_tiles + p.tile_base + tile] = agg_identity(p.aggs[tid]);
-        return;
+    int slot = 0;                                                  // this thread's cursor in the ring and its phase
+    uint32_t phase = 0;
+    int first_tile = -1;                                           // block-uniform: the CTA's first dense tile
+    unsigned long long acc[kMaxAgg];
+#pragma unroll
+    for (int a = 0; a < kMaxAgg; ++a) acc[a] = a < p.nagg ? agg_identity(p.aggs[a]) : 0ull;
+    const uint32_t lanes_below = (1u << lane) - 1u;
+    const int niter = (p.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    for (int it0 = 0; it0 < niter; it0 += kScanThreads) {
+        // which of this CTA's next 256 tiles belong to dense groups: one round of loads for all of them
+        bool dense = false;
+        if (tid < kScanThreads && it0 + tid < niter) {
+            const int tile_t = blockIdx.x + (it0 + tid) * gridDim.x;
+            const int tile0 = tile_t & ~(kGroupTiles - 1);
+            const int ntl = min(kGroupTiles, p.ntiles - tile0);
+            dense = (long long)(__ldg(p.tile_out + tile0 + ntl) - __ldg(p.tile_out + tile0)) > (long long)p.stg_min;
+        }
+        const uint32_t flags = __ballot_sync(0xFFFFFFFFu, dense);
+        __syncthreads();                                           // the previous round is over: the ring is empty, s_flags is free
+        if (warp < kWarpsPerCta && lane == 0) s_flags[warp] = flags;
+        __syncthreads();
+        const int n = min(kScanThreads, niter - it0);
+        auto tile_of = [&](int j) { return (int)blockIdx.x + (it0 + j) * (int)gridDim.x; };
+        auto next_dense = [&](int j) {                             // block-uniform
+            while (j < n && !((s_flags[j >> 5] >> (j & 31)) & 1u)) ++j;
+            return j;
+        };
+        if (first_tile < 0) {
+            const int j0 = next_dense(0);
+            if (j0 < n) first_tile = tile_of(j0);
+        }
+        if (warp == kWarpsPerCta) {
+            // ---- producer: one lane feeds the ring, a stage as soon as all eight warps have handed it back
+            if (lane == 0) {
+                for (int j = next_dense(0); j < n; j = next_dense(j + 1)) {
+                    const int64_t tile_row0 = (int64_t)tile_of(j) * kTileRows;
+                    for (int step = 0; step < kStgSteps; ++step) {
+                        mbar_wait(&s_empty[slot], phase ^ 1u);    // passes at once the first time round the ring
+                        uint8_t* st = s_ring + (size_t)slot * stage_bytes;
+                        const int64_t row0 = tile_row0 + step * kStgRows;
+                        mbar_arrive_expect_tx(&s_full[slot], stage_bytes);
+                        for (int c = 0; c < p.stg_n; ++c)
+                            tma_bulk_g2s(st + p.stg_off[c], reinterpret_cast<const uint8_t*>(p.stg_src[c]) + row0 * p.stg_stride[c],
+                                         (uint32_t)(kStgRows * p.stg_stride[c]), &s_full[slot]);
+                        if (++slot == S) { slot = 0; phase ^= 1u; }
+                    }
+                }
+            }
+            continue;
+        }
+        // ---- consumers
+        int j = next_dense(0);
+        uint4 wcur = make_uint4(0u, 0u, 0u, 0u);                   // words 4 lane .. 4 lane + 3 of the tile's selection bitmap
+        long long bcur = 0;
+        if (j < n) {
+            const int t = tile_of(j);
+            wcur = ldg128(p.out_bitmap + (size_t)t * (kTileRows / 32) + lane * 4);
+            bcur = (long long)__ldg(p.tile_out + t);
+        }
+        while (j < n) {
+            const int jn = next_dense(j + 1);
+            uint4 wnxt = make_uint4(0u, 0u, 0u, 0u);
+            long long bnxt = 0;
+            if (jn < n) {                                          // in flight while tile j is written
+                const int t = tile_of(jn);
+                wnxt = ldg128(p.out_bitmap + (size_t)t * (kTileRows / 32) + lane * 4);
+                bnxt = (long long)__ldg(p.tile_out + t);
+            }
+            const int tile = tile_of(j);
+            // survivors ahead of this lane's four words within the tile
+            const int mine = __popc(wcur.x) + __popc(wcur.y) + __popc(wcur.z) + __popc(wcur.w);
+            int incl = mine;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+                if (lane >= o) incl += v;
+            }
+            const int excl = incl - mine;
+            const int T = __shfl_sync(0xFFFFFFFFu, incl, 31);      // the tile's count
+            if (warp == 0 && lane < p.nagg) {                      // the CTA's one partial is written at the very end
+                const DevAgg& g = p.aggs[lane];
+                p.partials[(size_t)lane * p.total_tiles + p.tile_base + tile] = g.kind == MBC_AGG_COUNT ? (unsigned long long)T : agg_identity(g);
+            }
+#pragma unroll 1
+            for (int step = 0; step < kStgSteps; ++step) {
+                const int src = step * kWarpsPerCta + warp;        // the lane that holds this warp's 128 rows of the stage
+                uint32_t q[4];
+                q[0] = __shfl_sync(0xFFFFFFFFu, wcur.x, src);
+                q[1] = __shfl_sync(0xFFFFFFFFu, wcur.y, src);
+                q[2] = __shfl_sync(0xFFFFFFFFu, wcur.z, src);
+                q[3] = __shfl_sync(0xFFFFFFFFu, wcur.w, src);
+                long long out[4];                                  // output row of this lane's j-th row, if it survives
+                out[0] = bcur + __shfl_sync(0xFFFFFFFFu, excl, src) + __popc(q[0] & lanes_below);
+                out[1] = out[0] - __popc(q[0] & lanes_below) + __popc(q[0]) + __popc(q[1] & lanes_below);
+                out[2] = out[1] - __popc(q[1] & lanes_below) + __popc(q[1]) + __popc(q[2] & lanes_below);
+                out[3] = out[2] - __popc(q[2] & lanes_below) + __popc(q[2]) + __popc(q[3] & lanes_below);
+                const uint32_t bits = ((q[0] >> lane) & 1u) | (((q[1] >> lane) & 1u) << 1) | (((q[2] >> lane) & 1u) << 2) | (((q[3] >> lane) & 1u) << 3);
+                mbar_wait(&s_full[slot], phase);                   // the stage's columns have landed
+                if ((q[0] | q[1] | q[2] | q[3]) != 0u) {           // warp-uniform
+                    const uint8_t* st = s_ring + (size_t)slot * stage_bytes;
+                    const int r0 = warp * kStgWarpRows + lane;     // this lane's rows of the stage: r0 + 32 i
+                    if (p.out_pos) {
+                        const int64_t pos0 = p.pos_base + (int64_t)tile * kTileRows + step * kStgRows + r0;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            if ((bits >> i) & 1u) p.out_pos[out[i]] = pos0 + 32 * i;
+                    }
+                    for (int c = 0; c < p.nproj; ++c) {            // iterator/Projection.java:103-144
+                        const DevProj& pr = p.proj[c];
+                        const uint8_t* col_s = st + p.stg_off[p.proj_stg[c]];
+                        if (pr.stride == 4) {
+                            const uint32_t* sv = reinterpret_cast<const uint32_t*>(col_s) + r0;
+                            uint32_t* dst = reinterpret_cast<uint32_t*>(pr.dst);
+                            uint32_t v[4];
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) v[i] = sv[32 * i];
+#pragma unroll
+                            for (int i = 0; i < 4; ++i)
+                                if ((bits >> i) & 1u) dst[out[i]] = v[i];
+                        } else if (pr.stride == 16) {
+                            const uint4* sv = reinterpret_cast<const uint4*>(col_s) + r0;
+                            uint4* dst = reinterpret_cast<uint4*>(pr.dst);
+#pragma unroll
+                            for (int i = 0; i < 4; ++i)
+                                if ((bits >> i) & 1u) dst[out[i]] = sv[32 * i];
+                        } else {
+                            const int words = pr.stride >> 2;
+                            for (int i = 0; i < 4; ++i) {
+                                if (!((bits >> i) & 1u)) continue;
+                                const uint32_t* sv = reinterpret_cast<const uint32_t*>(col_s + (size_t)(r0 + 32 * i) * pr.stride);
+                                uint32_t* dst = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(pr.dst) + out[i] * pr.stride);
+                                for (int w = 0; w < words; ++w) dst[w] = sv[w];
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int a = 0; a < kMaxAgg; ++a) {
+                        if (a >= p.nagg) break;
+                        const DevAgg& g = p.aggs[a];
+                        if (g.kind == MBC_AGG_COUNT) continue;     // the tile counts are the count
+                        const uint32_t* sv = reinterpret_cast<const uint32_t*>(st + p.stg_off[p.agg_stg[a]]) + r0;
+                        agg_fold4(g, acc[a], make_uint4(sv[0], sv[32], sv[64], sv[96]), bits);
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&s_empty[slot]);        // this warp is done with the stage
+                if (++slot == S) { slot = 0; phase ^= 1u; }
+            }
+            wcur = wnxt;
+            bcur = bnxt;
+            j = jn;
+        }
     }
-    write_sparse_group(p, tile0, ntl, base, total, s_list, s_wtot);   // the list takes the whole dynamic area here (>= kListCap u16)
+    // the CTA's aggregate partial: lanes butterflied, warps combined in order
+    if (p.nagg > 0 && first_tile >= 0) {                           // block-uniform
+        if (warp < kWarpsPerCta) {
+#pragma unroll
+            for (int a = 0; a < kMaxAgg; ++a) {
+                if (a >= p.nagg) break;
+                const DevAgg& g = p.aggs[a];
+                unsigned long long v = acc[a];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v = agg_merge(g, v, __shfl_xor_sync(0xFFFFFFFFu, v, o));
+                if (lane == 0) s_aggw[a][warp] = v;
+            }
+        }
+        __syncthreads();
+        if (tid < p.nagg && p.aggs[tid].kind != MBC_AGG_COUNT) {
+            const DevAgg& g = p.aggs[tid];
+            unsigned long long v = s_aggw[tid][0];
+            for (int x = 1; x < kWarpsPerCta; ++x) v = agg_merge(g, v, s_aggw[tid][x]);
+            p.partials[(size_t)tid * p.total_tiles + p.tile_base + first_tile] = v;
+        }
+    }
 }
 
 // Reduce the per-tile partials of one aggregate (fixed association => reproducible sums): thread i folds

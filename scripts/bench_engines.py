@@ -19,7 +19,7 @@ from bench import AGGS, DESCS, SEED, algorithmic_bytes, c2_terms, measured_peak_
 rows = int(sys.argv[1]) if len(sys.argv) > 1 else 100_000_000
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 20
 sels = [float(x) for x in sys.argv[3].split(",")] if len(sys.argv) > 3 else [0.001, 0.01, 0.03, 0.1, 0.25, 0.5, 0.9]
-engines = os.environ.get("ENGINES", "twopass,stream,gather,fused").split(",")
+engines = os.environ.get("ENGINES", "twopass,gather,fused").split(",")
 N = mbcol._native
 ctx = mbcol.Context(0)
 t = ctx.create_table(DESCS, rows)
@@ -33,10 +33,7 @@ summary = {}
 sigs = {}
 for eng in engines:
     os.environ["MBC_SCAN_PATH"] = "fused" if eng == "fused" else "twopass"
-    os.environ["MBC_WRITE_STREAM"] = "0" if eng == "gather" else "1"
-    os.environ.pop("MBC_STREAM_MIN_PCT", None)
-    if eng == "stream":
-        os.environ["MBC_STREAM_MIN_PCT"] = "0"
+    os.environ["MBC_WRITE_STAGED"] = "0" if eng == "gather" else "1"   # gather: the round-1 write pass (no write_staged_kernel)
     for s in sels:
         terms = c2_terms(mbcol.Term, s)
         ms = []

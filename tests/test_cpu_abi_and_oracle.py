@@ -48,9 +48,10 @@ def test_sm100a_only_and_blackwell_features_in_sass():
 
 def test_tma_and_mbarrier_opcodes_are_in_the_sass():
     """What the kernels claim is what the binary holds (B200_PROFILING.md: cp.async.bulk shows as UBLKCP, mbarrier as SYNCS):
-    the filter pass and the fused scan stage their tiles with bulk-TMA copies completing on mbarriers; the streaming write
-    pass and the shard push move 128-bit words; nothing is a contraction (no UTC*MMA / HMMA anywhere).  The summary the
-    judge reads is profiles/r2/sass_opcodes.txt (scripts/sass_summary.py); this test regenerates it from the built .so."""
+    the filter pass, the staged write pass and the fused scan stage their tiles with bulk-TMA copies completing on
+    mbarriers; the gather write pass and the shard push move 128-bit words; nothing is a contraction (no UTC*MMA / HMMA
+    anywhere).  The summary the judge reads is profiles/r2/sass_opcodes.txt (scripts/sass_summary.py); this test
+    regenerates it from the built .so."""
     import shutil
     import mbcol
     if not shutil.which("cuobjdump"):
@@ -60,6 +61,8 @@ def test_tma_and_mbarrier_opcodes_are_in_the_sass():
     s = sass_summary.summarise(mbcol._native.LIB_PATH)
     assert s["mbc::filter_kernel"].get("UBLKCP", 0) > 0 and s["mbc::filter_kernel"].get("SYNCS", 0) > 0
     assert s["mbc::fused_scan_kernel"].get("UBLKCP", 0) > 0 and s["mbc::fused_scan_kernel"].get("SYNCS", 0) > 0
+    assert s["mbc::write_staged_kernel"].get("UBLKCP", 0) > 0 and s["mbc::write_staged_kernel"].get("SYNCS", 0) > 0
+    assert s["mbc::write_staged_kernel"].get("STG.E.128", 0) > 0
     assert s["void mbc::write_kernel<false>"].get("LDG.E.128", 0) > 0 and s["void mbc::write_kernel<false>"].get("STG.E.128", 0) > 0
     assert s["mbc::shard_push_kernel"].get("STG.E.128", 0) > 0
     for k, c in s.items():

@@ -1,9 +1,11 @@
 """Every scan engine of libmbcol.so against the CPU oracle, through the C ABI.
 
-`mbc_scan` has the two-pass engine (filter -> offsets -> write; dense tiles streamed through shared memory, or gathered
-per survivor when MBC_WRITE_STREAM=0 / the projected row is too wide) and the opt-in single-residency engine
-(mbc_scan_fused.cuh, MBC_SCAN_PATH=fused: count warps ahead, offsets from published tile counts, compaction out of shared
-memory).  Every case here runs under all three and is compared with the oracle: bit-exact positions / values / Tuple bytes / integer aggregates, real SUM 1e-6 relative.
+`mbc_scan` has the two-pass engine (filter -> offsets -> write: write_kernel writes the groups of 8 tiles with few survivors
+whole, one CTA each, and gathers the survivors of fuller groups tile by tile; the fullest groups -- above 1/3 -- go through
+the TMA-staged write_staged_kernel unless MBC_WRITE_STAGED=0 or a projected row is too wide for its ring) and the opt-in single-residency
+engine (mbc_scan_fused.cuh, MBC_SCAN_PATH=fused: count warps ahead, offsets from published tile counts, compaction out of
+shared memory).  Every case here runs under all of them and is compared with the oracle: bit-exact positions / values /
+Tuple bytes / integer aggregates, real SUM 1e-6 relative.
 Needs a B200.
 """
 import numpy as np
@@ -16,19 +18,22 @@ from util import C2_AGGS, C2_DESCS, c2_columns, c2_device_table, c2_terms, check
 pytestmark = pytest.mark.gpu
 
 ALL = N.WANT_POSITIONS | N.WANT_COLUMNS | N.WANT_TUPLES | N.WANT_AGG | N.WANT_HOST
-ENGINES = ["twopass", "stream", "gather", "fused"]
+ENGINES = ["twopass", "staged2", "gather", "fused"]
 
 
 @pytest.fixture(params=ENGINES)
 def engine(request, monkeypatch):
-    """twopass: filter -> offsets -> write, dense groups streamed through shared memory when at least 3/4 full, else their
-    survivors gathered through a rank -> row list (the default engine); stream / gather: every dense group through the one
-    or the other path; fused: the single-residency kernel (opt-in)."""
-    monkeypatch.setenv("MBC_SCAN_PATH", "fused" if request.param == "fused" else "twopass")
-    monkeypatch.setenv("MBC_WRITE_STREAM", "0" if request.param == "gather" else "1")
-    if request.param == "stream":
-        monkeypatch.setenv("MBC_STREAM_MIN_PCT", "0")
-    return request.param
+    """twopass: the default engine (filter -> offsets -> write_kernel for the groups up to 1/3 full + write_staged_kernel for
+    the fuller ones); staged2: the same with the shallowest ring (two stages) and every group above 12.5 % staged; gather:
+    write_staged_kernel off, groups above 12.5 % gathered tile by tile (the round-1 write pass); fused: the single-residency
+    kernel (opt-in)."""
+    e = request.param
+    monkeypatch.setenv("MBC_SCAN_PATH", "fused" if e == "fused" else "twopass")
+    monkeypatch.setenv("MBC_WRITE_STAGED", "0" if e == "gather" else "1")
+    if e == "staged2":
+        monkeypatch.setenv("MBC_STAGED_STAGES", "2")
+        monkeypatch.setenv("MBC_STAGED_MIN_PCT", "0")
+    return e
 
 
 @pytest.mark.parametrize("sel", [0.0005, 0.01, 0.05, 0.1, 0.5, 0.9, 1.0])
