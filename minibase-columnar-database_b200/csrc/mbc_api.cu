@@ -188,6 +188,13 @@ int32_t mbc_init(int32_t device_id, mbc_ctx** out) {
         MBC_FAIL(MBC_ERR_NODEVICE, "mbc_init: device %d is sm_%d%d; libmbcol.so carries sm_100a code only",
                  device_id, prop.major, prop.minor);
     MBC_CUDA(cudaSetDevice(device_id));
+    if (const char* g = getenv("MBC_L2_FETCH")) {                   // experiment knob: L2 fetch granularity on a miss (32 / 64 / 128)
+        cudaError_t le = cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(g));
+        size_t got = 0;
+        cudaDeviceGetLimit(&got, cudaLimitMaxL2FetchGranularity);
+        fprintf(stderr, "[mbc] L2 fetch granularity: asked %s, set -> %s, now %zu\n", g, cudaGetErrorString(le), got);
+        cudaGetLastError();
+    }
     mbc_ctx* ctx = new mbc_ctx();
     ctx->device = device_id;
     ctx->sm_count = prop.multiProcessorCount;

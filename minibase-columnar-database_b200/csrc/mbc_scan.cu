@@ -499,6 +499,21 @@ static int32_t prepare_job(const mbc_table* schema, const ScanRequest& rq, int64
     p.out_cap = capacity_rows;
     p.ntiles = INT32_MAX;                         // the grid bound comes from the device; bind_table sets the real count
     MBC_TRY(plan_staging(ctx, &p, &job->smem_bytes, &job->max_grid));
+    // who loads an aggregate's source values in the gather paths of write_kernel: the projection of the same column if there
+    // is one, else the first aggregate of that column on behalf of all of them
+    memset(p.proj_aggs, 0, sizeof(p.proj_aggs));
+    memset(p.agg_group, 0, sizeof(p.agg_group));
+    for (int a = 0; a < p.nagg; ++a) {
+        if (p.aggs[a].kind == MBC_AGG_COUNT) continue;
+        int owner = -1;
+        for (int c = 0; c < p.nproj && owner < 0; ++c)
+            if (p.proj[c].col == p.aggs[a].col && p.proj[c].stride == 4) owner = c;
+        if (owner >= 0) { p.proj_aggs[owner] |= (uint8_t)(1u << a); continue; }
+        int first = a;
+        for (int b = 0; b < a; ++b)
+            if (p.aggs[b].kind != MBC_AGG_COUNT && p.aggs[b].col == p.aggs[a].col) { first = b; break; }
+        p.agg_group[first] |= (uint8_t)(1u << a);
+    }
     plan_staged(ctx, job);
     plan_fused(ctx, job);
     return MBC_OK;

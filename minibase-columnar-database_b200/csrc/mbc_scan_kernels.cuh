@@ -82,6 +82,8 @@ struct ScanParams {
     int64_t pos_base;
     int64_t out_cap;              // rows the output buffers hold (debug checks)
     // dense tiles through write_staged_kernel: every column the write pass reads is bulk-copied (TMA) 1024 rows at a time
+    uint8_t proj_aggs[kMaxProj];  // aggregates folded from the values gathered for projected field c (same column, 4-byte): bit a
+    uint8_t agg_group[kMaxAgg];   // other aggregates: bit mask of those sharing a's source column, on the group's first member (else 0)
     int32_t stg_min;              // groups of kGroupTiles tiles with MORE survivors than this go to write_staged_kernel (>= kSparseMax)
     int32_t stg_n;                // staged columns; 0 = the path is off and write_kernel writes the dense groups itself
     int32_t stg_stages;           // depth of the ring
@@ -624,6 +626,33 @@ __device__ __forceinline__ void gather_store(const V* __restrict__ src, V* __res
     }
 }
 
+// gather of one 4-byte column that also feeds aggregates: every value is loaded ONCE, stored (dst may be null) and folded
+// into the accumulators of the aggregates in `amask` (agg_fold4 is defined below)
+__device__ __forceinline__ void agg_fold4(const DevAgg& g, unsigned long long& acc, const uint4 v, uint32_t bits);
+static_assert(kMaxAgg <= 8 && kGatherBatch == 4, "aggregate masks are bytes; folds take four values");
+__device__ __forceinline__ void gather_store_fold(const ScanParams& p, const uint32_t* __restrict__ src, uint32_t* __restrict__ dst,
+                                                  const uint16_t* list, const int first, const int step, const int n, const uint32_t amask,
+                                                  unsigned long long (&acc)[kMaxAgg]) {
+    for (int k0 = first; k0 < n; k0 += step * kGatherBatch) {
+        uint32_t v[kGatherBatch];
+        uint32_t ok = 0;
+#pragma unroll
+        for (int b = 0; b < kGatherBatch; ++b) {
+            const int k = k0 + b * step;
+            v[b] = 0u;
+            if (k < n) { v[b] = __ldg(src + list[k]); ok |= 1u << b; }
+        }
+        if (dst) {
+#pragma unroll
+            for (int b = 0; b < kGatherBatch; ++b)
+                if ((ok >> b) & 1u) dst[k0 + b * step] = v[b];
+        }
+#pragma unroll
+        for (int a = 0; a < kMaxAgg; ++a)
+            if ((amask >> a) & 1u) agg_fold4(p.aggs[a], acc[a], make_uint4(v[0], v[1], v[2], v[3]), ok);
+    }
+}
+
 __device__ __forceinline__ void gather_store_wide(const DevProj& pr, int64_t row0, long long out0, const uint16_t* list, int first,
                                                   int step, int n) {
     const int words = pr.stride >> 2;
@@ -746,20 +775,36 @@ __device__ __forceinline__ void write_dense_tile(const ScanParams& p, const int 
     const uint16_t* list = s_list;
     if (p.out_pos)
         for (int k = tid; k < T; k += kScanThreads) p.out_pos[base + k] = p.pos_base + tile_row0 + list[k];
+    // aggregates are folded from the values gathered for projection when their column is projected (one load per value),
+    // else from one gather per distinct source column; per-thread accumulators, one butterfly per warp, warps combined in order
+    unsigned long long acc[kMaxAgg];
+#pragma unroll
+    for (int a = 0; a < kMaxAgg; ++a) acc[a] = a < p.nagg ? agg_identity(p.aggs[a]) : 0ull;
     for (int c = 0; c < p.nproj; ++c) {                            // iterator/Projection.java:103-144
         const DevProj& pr = p.proj[c];
-        if (pr.stride == 4)
-            gather_store(reinterpret_cast<const uint32_t*>(pr.src) + tile_row0, reinterpret_cast<uint32_t*>(pr.dst) + base, list, tid, kScanThreads, T);
-        else if (pr.stride == 16)
+        if (pr.stride == 4) {
+            if (p.proj_aggs[c])
+                gather_store_fold(p, reinterpret_cast<const uint32_t*>(pr.src) + tile_row0, reinterpret_cast<uint32_t*>(pr.dst) + base, list, tid,
+                                  kScanThreads, T, p.proj_aggs[c], acc);
+            else
+                gather_store(reinterpret_cast<const uint32_t*>(pr.src) + tile_row0, reinterpret_cast<uint32_t*>(pr.dst) + base, list, tid, kScanThreads, T);
+        } else if (pr.stride == 16) {
             gather_store(reinterpret_cast<const uint4*>(pr.src) + tile_row0, reinterpret_cast<uint4*>(pr.dst) + base, list, tid, kScanThreads, T);
-        else
+        } else {
             gather_store_wide(pr, tile_row0, base, list, tid, kScanThreads, T);
+        }
     }
-    // aggregates: per-thread fold over its survivors, one butterfly per warp, warps combined in order
-    for (int a = 0; a < p.nagg; ++a) {
+    for (int a = 0; a < p.nagg; ++a)
+        if (p.agg_group[a])
+            gather_store_fold(p, reinterpret_cast<const uint32_t*>(p.aggs[a].src) + tile_row0, nullptr, list, tid, kScanThreads, T, p.agg_group[a], acc);
+#pragma unroll
+    for (int a = 0; a < kMaxAgg; ++a) {
+        if (a >= p.nagg) break;
         const DevAgg& g = p.aggs[a];
         if (g.kind == MBC_AGG_COUNT) continue;                     // the tile count is the count
-        const unsigned long long v = gather_fold(g, tile_row0, list, tid, kScanThreads, T);
+        unsigned long long v = acc[a];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v = agg_merge(g, v, __shfl_xor_sync(0xFFFFFFFFu, v, o));
         if (lane == 0) s_aggw[a][warp] = v;
     }
     __syncthreads();
@@ -805,6 +850,26 @@ __device__ __forceinline__ void agg_fold4(const DevAgg& g, unsigned long long& a
             for (int j = 0; j < 4; ++j) if ((bits >> j) & 1u) a = fmax(a, (double)__uint_as_float(x[j]));
         }
         acc = (unsigned long long)__double_as_longlong(a);
+    }
+}
+
+// one work item of write_sparse_group (one warp): a 4-byte column gathered once for its projection (dst may be null) and for
+// the aggregates in amask; their partials of the group go to slot part0
+__device__ __forceinline__ void group_fold_item(const ScanParams& p, const uint32_t* src, uint32_t* dst, const uint16_t* list, const int T,
+                                                const uint32_t amask, const size_t part0) {
+    const int lane = threadIdx.x & 31;
+    unsigned long long acc[kMaxAgg];
+#pragma unroll
+    for (int a = 0; a < kMaxAgg; ++a) acc[a] = ((amask >> a) & 1u) ? agg_identity(p.aggs[a]) : 0ull;
+    gather_store_fold(p, src, dst, list, lane, 32, T, amask, acc);
+#pragma unroll
+    for (int a = 0; a < kMaxAgg; ++a) {
+        if (!((amask >> a) & 1u)) continue;
+        const DevAgg& g = p.aggs[a];
+        unsigned long long v = acc[a];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v = agg_merge(g, v, __shfl_xor_sync(0xFFFFFFFFu, v, o));
+        if (lane == 0) p.partials[(size_t)a * p.total_tiles + part0] = v;
     }
 }
 
@@ -865,7 +930,10 @@ __device__ __forceinline__ void write_sparse_group(const ScanParams& p, const in
                 for (int k = lane; k < T; k += 32) p.out_pos[base + k] = p.pos_base + row0 + list[k];
         } else if (item <= p.nproj) {                              // iterator/Projection.java:103-144
             const DevProj& pr = p.proj[item - 1];
-            if (pr.stride == 4)
+            const uint32_t amask = p.proj_aggs[item - 1];
+            if (pr.stride == 4 && amask)
+                group_fold_item(p, reinterpret_cast<const uint32_t*>(pr.src) + row0, reinterpret_cast<uint32_t*>(pr.dst) + base, list, T, amask, part0);
+            else if (pr.stride == 4)
                 gather_store(reinterpret_cast<const uint32_t*>(pr.src) + row0, reinterpret_cast<uint32_t*>(pr.dst) + base, list, lane, 32, T);
             else if (pr.stride == 16)
                 gather_store(reinterpret_cast<const uint4*>(pr.src) + row0, reinterpret_cast<uint4*>(pr.dst) + base, list, lane, 32, T);
@@ -874,8 +942,11 @@ __device__ __forceinline__ void write_sparse_group(const ScanParams& p, const in
         } else {
             const int a = item - 1 - p.nproj;
             const DevAgg& g = p.aggs[a];
-            const unsigned long long v = (g.kind == MBC_AGG_COUNT) ? (unsigned long long)T : gather_fold(g, row0, list, lane, 32, T);
-            if (lane == 0) p.partials[(size_t)a * p.total_tiles + part0] = v;
+            if (g.kind == MBC_AGG_COUNT) {
+                if (lane == 0) p.partials[(size_t)a * p.total_tiles + part0] = (unsigned long long)T;
+            } else if (p.agg_group[a]) {                           // every aggregate of this source column, from one gather
+                group_fold_item(p, reinterpret_cast<const uint32_t*>(g.src) + row0, nullptr, list, T, p.agg_group[a], part0);
+            }
         }
     }
 }

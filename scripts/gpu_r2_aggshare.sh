@@ -1,0 +1,11 @@
+#!/bin/bash
+# Aggregates folded from the values gathered for projection: parity of the scan tests, timing per selectivity, C2 and C5 steps.
+set -x
+cd /root/repo
+mkdir -p gpurun_out
+timeout -s KILL 900 python -m pytest tests/test_scan_engines_gpu.py tests/test_scan_gpu.py tests/test_edges_gpu.py -m gpu -x -q --timeout 600 2>&1 | tail -12 > gpurun_out/aggshare_tests.log
+cat gpurun_out/aggshare_tests.log
+ENGINES=twopass timeout -s KILL 400 python scripts/bench_engines.py 100000000 15 0.001,0.01,0.1,0.15,0.25,0.33,0.5,0.9 > gpurun_out/aggshare_eng.log 2>&1
+grep -h median_ms gpurun_out/aggshare_eng.log | cut -c1-170
+timeout -s KILL 300 python bench.py --no-e2e --steps 20 --warmup 5 > gpurun_out/aggshare_c2.log 2>&1; tail -1 gpurun_out/aggshare_c2.log | cut -c1-600
+timeout -s KILL 300 python bench.py --workload c5 --no-e2e --steps 20 --warmup 5 > gpurun_out/aggshare_c5.log 2>&1; tail -1 gpurun_out/aggshare_c5.log | cut -c1-400
