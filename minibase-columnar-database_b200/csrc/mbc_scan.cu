@@ -241,6 +241,7 @@ struct Workspace {
     unsigned long long* tile_out;
     unsigned long long* partials;
     unsigned long long* agg_out;  // [kMaxAgg] aggregates, [kMaxAgg] = the count (agg_finish_kernel)
+    uint8_t* group_class;         // one byte per group of kGroupTiles tiles
 };
 
 static int32_t carve_workspace(mbc_ctx* ctx, int64_t launch_tiles, int64_t part_slots, int nagg, Workspace* w) {
@@ -248,7 +249,8 @@ static int32_t carve_workspace(mbc_ctx* ctx, int64_t launch_tiles, int64_t part_
     size_t counts_bytes = (size_t)round_up(launch_tiles * 4, 64);
     size_t out_bytes = (size_t)round_up((launch_tiles + 1) * 8, 64);
     size_t partial_bytes = (size_t)std::max(nagg, 1) * part_slots * 8;
-    size_t total = head + counts_bytes + out_bytes + partial_bytes + 64;
+    size_t class_bytes = (size_t)round_up(launch_tiles / kGroupTiles + 1, 64);
+    size_t total = head + counts_bytes + out_bytes + partial_bytes + class_bytes + 64;
     MBC_TRY(ensure_workspace(ctx, total));
     char* b = (char*)ctx->ws;
     w->count = (long long*)b;
@@ -256,6 +258,7 @@ static int32_t carve_workspace(mbc_ctx* ctx, int64_t launch_tiles, int64_t part_
     w->tile_counts = (uint32_t*)(b + head);
     w->tile_out = (unsigned long long*)(b + head + counts_bytes);
     w->partials = (unsigned long long*)(b + head + counts_bytes + out_bytes);
+    w->group_class = (uint8_t*)(b + head + counts_bytes + out_bytes + partial_bytes);
     return MBC_OK;
 }
 
@@ -494,6 +497,7 @@ static int32_t prepare_job(const mbc_table* schema, const ScanRequest& rq, int64
     p.total_tiles = (int)job->part_slots;
     p.tile_counts = job->w.tile_counts;
     p.tile_out = job->w.tile_out;
+    p.group_class = job->w.group_class;
     p.partials = job->w.partials;
     p.out_pos = r->d_pos;
     p.out_cap = capacity_rows;
@@ -607,7 +611,8 @@ static int32_t launch_job(ScanJob* job, bool first) {
     }
     if (job->r->ev_mid[0]) cudaEventRecord(job->r->ev_mid[0], ctx->stream);
     tile_offsets_kernel<<<(p.ntiles + kOffsetsPerBlock - 1) / kOffsetsPerBlock, 1024, 0, ctx->stream>>>(p.tile_counts, p.ntiles, p.tile_out,
-                                                                                                      p.count_in, p.count_out, p.work_counter);
+                                                                                                      p.count_in, p.count_out, p.work_counter,
+                                                                                                      p.group_class, kSparseMax, p.stg_min);
     job->launches++;
     ctx->launches += 2;
     job->part_done += p.ntiles;

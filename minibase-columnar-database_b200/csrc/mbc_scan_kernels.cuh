@@ -111,6 +111,7 @@ struct ScanParams {
     uint32_t* out_bitmap;
     uint32_t* tile_counts;        // qualifying rows per tile (pass 1 -> pass 2)
     unsigned long long* tile_out; // global output offset of every tile (tile_offsets_kernel)
+    uint8_t* group_class;         // per group of kGroupTiles tiles (tile_offsets_kernel): kGroupEmpty / Sparse / Mid / Full
     const long long* count_in;    // running output offset before this launch (chunked scans append); NULL = 0
     long long* count_out;         // ... and after it (a different slot)
     unsigned int* work_counter;   // group tickets of the write pass (zeroed by tile_offsets_kernel)
@@ -520,9 +521,14 @@ __global__ void __launch_bounds__(kScanThreads) select_bitmap_kernel(const uint3
 // `start` is the running output offset left by the previous launch of a chunked scan (0 for the first launch); the
 // last block publishes the new running offset in a DIFFERENT slot, since other blocks may still be reading the old one.
 constexpr int kOffsetsPerBlock = 4096;
+// How the write pass treats a group of 8 tiles, by its survivors: nothing to do / written whole by one CTA / gathered tile by
+// tile / read whole through write_staged_kernel.  One byte per group, written next to the offsets: the CTAs of the write pass
+// that have nothing to do (most of them, at either end of the density range) find out from a line that sits in their SM's L1
+// instead of waiting ~1 us for the group's offsets from L2.
+enum : uint8_t { kGroupEmpty = 0, kGroupSparse = 1, kGroupMid = 2, kGroupFull = 3 };
 __global__ void __launch_bounds__(1024) tile_offsets_kernel(const uint32_t* counts, int ntiles, unsigned long long* tile_base,
                                                             const long long* running_in, long long* running_out,
-                                                            unsigned int* work_counter) {
+                                                            unsigned int* work_counter, uint8_t* group_class, int sparse_max, int full_min) {
     __shared__ unsigned long long s_warp[32];
     __shared__ unsigned long long s_prefix;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -542,6 +548,12 @@ __global__ void __launch_bounds__(1024) tile_offsets_kernel(const uint32_t* coun
     if (i0 + 2 >= ntiles) q.z = 0u;
     if (i0 + 3 >= ntiles) q.w = 0u;
     const unsigned long long mine = (unsigned long long)q.x + q.y + q.z + q.w;
+    {   // a group is the quads of two neighbouring threads (first_quad is even; kGroupTiles == 8 is asserted where it is defined)
+        const unsigned long long gtot = mine + __shfl_xor_sync(0xFFFFFFFFu, mine, 1);
+        if (!(tid & 1) && i0 < ntiles)
+            group_class[i0 / 8] = gtot == 0 ? kGroupEmpty : gtot <= (unsigned long long)sparse_max ? kGroupSparse
+                                              : gtot <= (unsigned long long)full_min ? kGroupMid : kGroupFull;
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) before += __shfl_xor_sync(0xFFFFFFFFu, before, o);
     unsigned long long incl = mine;
@@ -606,6 +618,7 @@ constexpr int kGroupWords = kGroupRows / 32;
 constexpr int kThreadWords = kGroupWords / kScanThreads;           // 4 (or 8) -> one (two) 128-bit loads per thread
 constexpr int kListCap = MBC_SPARSE_MAX > kTileRows ? MBC_SPARSE_MAX : kTileRows;
 constexpr int kSparseMax = MBC_SPARSE_MAX;                         // survivors per group handled item-per-warp
+static_assert(kGroupTiles == 8, "tile_offsets_kernel classifies groups of two quads of tiles");
 static_assert(kGroupRows <= 65536 && kThreadWords % 4 == 0 && kSparseMax <= kListCap && kTileRows <= kListCap && kWarpsPerCta <= 32, "group geometry");
 
 template <typename V>
@@ -874,8 +887,24 @@ __device__ __forceinline__ void group_fold_item(const ScanParams& p, const uint3
 }
 
 // A sparse group (0 < total <= kSparseMax survivors in ntl tiles from tile0), written by one CTA.
+// The thread's words of a group's selection bitmap: loaded by the caller TOGETHER with the group's offsets (they do not depend
+// on them), one memory round trip instead of two in front of a chain that is nothing but round trips.
+struct GroupBits {
+    uint4 q[kThreadWords / 4];
+};
+__device__ __forceinline__ GroupBits group_bits_load(const ScanParams& p, const int tile0, const int ntl) {
+    GroupBits b;
+    const int word0 = threadIdx.x * kThreadWords;
+#pragma unroll
+    for (int q = 0; q < kThreadWords; q += 4) {
+        b.q[q / 4] = make_uint4(0u, 0u, 0u, 0u);
+        if (word0 + q < ntl * (kTileRows / 32)) b.q[q / 4] = ldg128(p.out_bitmap + (size_t)tile0 * (kTileRows / 32) + word0 + q);
+    }
+    return b;
+}
+
 __device__ __forceinline__ void write_sparse_group(const ScanParams& p, const int tile0, const int ntl, const long long base, const int total,
-                                                   uint16_t* s_list, uint32_t* s_wtot) {
+                                                   const GroupBits& pre, uint16_t* s_list, uint32_t* s_wtot) {
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
@@ -887,8 +916,7 @@ __device__ __forceinline__ void write_sparse_group(const ScanParams& p, const in
     int cnt = 0;
 #pragma unroll
     for (int q = 0; q < kThreadWords; q += 4) {
-        uint4 v = make_uint4(0u, 0u, 0u, 0u);
-        if (word0 + q < ntl * (kTileRows / 32)) v = *reinterpret_cast<const uint4*>(p.out_bitmap + (row0 >> 5) + word0 + q);
+        const uint4 v = pre.q[q / 4];
         w[q] = v.x; w[q + 1] = v.y; w[q + 2] = v.z; w[q + 3] = v.w;
         cnt += __popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w);
     }
@@ -978,15 +1006,18 @@ __global__ void __launch_bounds__(kScanThreads, MBC_WRITE_MIN_CTAS) write_kernel
         if (tid == 0) ticket = (int)atomicAdd(p.work_counter, 1u);
         const int tile0 = g * kGroupTiles;
         const int ntl = min(kGroupTiles, p.ntiles - tile0);
-        const long long base = (long long)p.tile_out[tile0];
-        const int total = (int)((long long)p.tile_out[tile0 + ntl] - base);
-        if (total > kSparseMax) continue;                          // block-uniform
+        const uint32_t cls = __ldg(p.group_class + g);
+        if (cls >= kGroupMid) continue;                            // block-uniform: written tile by tile, below or by write_staged_kernel
+        GroupBits bits;
+        if (cls == kGroupSparse) bits = group_bits_load(p, tile0, ntl);   // one round of loads with the group's offsets
+        const long long base = (long long)__ldg(p.tile_out + tile0);
+        const int total = (int)((long long)__ldg(p.tile_out + tile0 + ntl) - base);
         for (int i = tid; i < p.nagg * ntl; i += kScanThreads) {   // one partial for the group (below), identity elsewhere
             const int a = i / ntl, t = i % ntl;
             if (t > 0 || total == 0) p.partials[(size_t)a * p.total_tiles + p.tile_base + tile0 + t] = agg_identity(p.aggs[a]);
         }
         if (total == 0) continue;
-        write_sparse_group(p, tile0, ntl, base, total, s_list, s_wtot);
+        write_sparse_group(p, tile0, ntl, base, total, bits, s_list, s_wtot);
     }
     const int niter = (p.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     for (int it0 = 0; it0 < niter; it0 += kScanThreads) {
@@ -995,18 +1026,21 @@ __global__ void __launch_bounds__(kScanThreads, MBC_WRITE_MIN_CTAS) write_kernel
         bool dense = false;
         if (it0 + tid < niter) {
             const int tile0 = tile_t & ~(kGroupTiles - 1);
-            const int ntl = min(kGroupTiles, p.ntiles - tile0);
-            const long long gtot = (long long)(p.tile_out[tile0 + ntl] - p.tile_out[tile0]);
-            dense = gtot > (long long)kSparseMax && !(p.dense_staged && gtot > (long long)p.stg_min);   // the fullest go to write_staged_kernel
+            const uint32_t cls = __ldg(p.group_class + tile0 / kGroupTiles);
+            dense = cls == kGroupMid || (cls == kGroupFull && !p.dense_staged);   // the fullest go to write_staged_kernel
         }
         const uint32_t flags = __ballot_sync(0xFFFFFFFFu, dense);
-        __syncthreads();                                           // the previous round is done with s_flags
+        if (!__syncthreads_or(dense)) continue;                    // (the previous round is done with s_flags)
         if ((tid & 31) == 0) s_flags[tid >> 5] = flags;
         __syncthreads();
         const int n = min(kScanThreads, niter - it0);
-        auto next_dense = [&](int j) {                             // block-uniform
-            while (j < n && !((s_flags[j >> 5] >> (j & 31)) & 1u)) ++j;
-            return j;
+        auto next_dense = [&](int j) {                             // block-uniform: first flagged tile at or after j (flags beyond n are 0)
+            while (j < kScanThreads) {
+                const uint32_t w = s_flags[j >> 5] >> (j & 31);
+                if (w) return j + __ffs(w) - 1;
+                j = (j | 31) + 1;
+            }
+            return n;
         };
         int j = next_dense(0);
         DenseTile cur = {0u, 0ll, 0};
@@ -1022,24 +1056,25 @@ __global__ void __launch_bounds__(kScanThreads, MBC_WRITE_MIN_CTAS) write_kernel
         }
     }
   } else {
-    // One CTA per tile: the hardware scheduler balances them (2 % faster than the persistent form on 10^4 tiles).
+    // One CTA per tile: the hardware scheduler balances them.  Most CTAs have nothing to write (the tiles of a sparse group
+    // but its first, the tiles write_staged_kernel takes) and learn it from the group's class byte.
     const int tile = blockIdx.x;
     const int tile0 = tile & ~(kGroupTiles - 1);
-    const int ntl = min(kGroupTiles, p.ntiles - tile0);            // tiles of this group
-    const DenseTile mine = dense_tile_load(p, tile);               // one round of loads with the group's offsets
-    const long long base = (long long)__ldg(p.tile_out + tile0);
-    const int total = (int)((long long)__ldg(p.tile_out + tile0 + ntl) - base);
-    if (total > kSparseMax) {                                      // block-uniform: dense group, every CTA writes its own tile
-        if (p.dense_staged && total > p.stg_min) return;           // ... or write_staged_kernel does, in the next launch
-        write_dense_tile(p, tile, mine, s_list, s_wtot, s_aggw);
-        return;
-    }
-    // sparse group: its first CTA writes all of it; one partial for the group, the other tiles carry the identity
-    if (tile != tile0 || total == 0) {
+    const uint32_t cls = __ldg(p.group_class + tile / kGroupTiles);
+    if (cls == kGroupFull && p.dense_staged) return;               // block-uniform: write_staged_kernel's, partials included
+    if (cls == kGroupEmpty || (cls == kGroupSparse && tile != tile0)) {   // one partial for a sparse group, the identity elsewhere
         if (tid < p.nagg) p.partials[(size_t)tid * p.total_tiles + p.tile_base + tile] = agg_identity(p.aggs[tid]);
         return;
     }
-    write_sparse_group(p, tile0, ntl, base, total, s_list, s_wtot);
+    if (cls != kGroupSparse) {                                     // every CTA of the group gathers its own tile
+        write_dense_tile(p, tile, dense_tile_load(p, tile), s_list, s_wtot, s_aggw);
+        return;
+    }
+    const int ntl = min(kGroupTiles, p.ntiles - tile0);            // tiles of this group
+    const GroupBits bits = group_bits_load(p, tile0, ntl);         // one round of loads with the group's offsets
+    const long long base = (long long)__ldg(p.tile_out + tile0);
+    const int total = (int)((long long)__ldg(p.tile_out + tile0 + ntl) - base);
+    write_sparse_group(p, tile0, ntl, base, total, bits, s_list, s_wtot);
   }
 }
 
@@ -1097,19 +1132,21 @@ __global__ void __launch_bounds__(kStgThreads, 2) write_staged_kernel(const __gr
         bool dense = false;
         if (tid < kScanThreads && it0 + tid < niter) {
             const int tile_t = blockIdx.x + (it0 + tid) * gridDim.x;
-            const int tile0 = tile_t & ~(kGroupTiles - 1);
-            const int ntl = min(kGroupTiles, p.ntiles - tile0);
-            dense = (long long)(__ldg(p.tile_out + tile0 + ntl) - __ldg(p.tile_out + tile0)) > (long long)p.stg_min;
+            dense = __ldg(p.group_class + tile_t / kGroupTiles) == kGroupFull;
         }
         const uint32_t flags = __ballot_sync(0xFFFFFFFFu, dense);
-        __syncthreads();                                           // the previous round is over: the ring is empty, s_flags is free
+        if (!__syncthreads_or(dense)) continue;                    // (the previous round is over: the ring is empty, s_flags is free)
         if (warp < kWarpsPerCta && lane == 0) s_flags[warp] = flags;
         __syncthreads();
         const int n = min(kScanThreads, niter - it0);
         auto tile_of = [&](int j) { return (int)blockIdx.x + (it0 + j) * (int)gridDim.x; };
-        auto next_dense = [&](int j) {                             // block-uniform
-            while (j < n && !((s_flags[j >> 5] >> (j & 31)) & 1u)) ++j;
-            return j;
+        auto next_dense = [&](int j) {                             // block-uniform: first flagged tile at or after j (flags beyond n are 0)
+            while (j < kScanThreads) {
+                const uint32_t w = s_flags[j >> 5] >> (j & 31);
+                if (w) return j + __ffs(w) - 1;
+                j = (j | 31) + 1;
+            }
+            return n;
         };
         if (first_tile < 0) {
             const int j0 = next_dense(0);
