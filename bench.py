@@ -226,6 +226,8 @@ def workload_config(wl: Workload, args, rows_per_gpu, world):
                            "push of step i runs beside the scans of step i+1; the last one is drained inside the timed region")
     else:
         cfg["sharding"] = "single GPU"
+        cfg["pipelining"] = ("the scans of step i+1 are queued before the host reads the counts of step i (results are double "
+                             "buffered); every step's counts are read and its results freed inside the timed region")
     return cfg
 
 
@@ -337,11 +339,22 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             counts[s] = res.count
             if record:
                 kernel_ms[s].append(res.kernel_ms)
-                phase_ms[s].append(res.phase_ms)
         if rank == 0:
             collected["total"], collected["counts"] = shard.collect()
             shard.release()
         shard.fence()                                               # the frees below are stream-ordered behind the push
+        for res in results:
+            res.close()
+
+    def read_previous(record=False):
+        """N=1: the host reads the counts of the PREVIOUS step (and frees its results) after this step's scans are queued, so
+        the GPU is not idle while the host waits and launches; every step's results are read inside the timed region."""
+        results = list(pending)
+        pending.clear()
+        for s, res in zip(wl.sels, results):                        # the host reads every count (this is the wait)
+            counts[s] = res.count
+            if record:
+                kernel_ms[s].append(res.kernel_ms)
         for res in results:
             res.close()
 
@@ -351,15 +364,9 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             results.append(table.scan(terms[s], proj=wl.proj, want=want_dev, aggs=wl.aggs))   # the scans queue back to back
         if world > 1:
             exchange_previous(record)                               # step i-1's rows travel while step i's scans run
-            pending.extend(results)
-            return
-        for s, res in zip(wl.sels, results):                        # the host reads every count (this is the wait)
-            counts[s] = res.count
-            if record:
-                kernel_ms[s].append(res.kernel_ms)
-                phase_ms[s].append(res.phase_ms)
-        for res in results:
-            res.close()
+        else:
+            read_previous(record)
+        pending.extend(results)
 
     def barrier():
         if world > 1:
@@ -370,6 +377,8 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         step()
     if world > 1:
         exchange_previous()
+    else:
+        read_previous()
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -381,6 +390,8 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         step(record=True)
     if world > 1:
         exchange_previous(record=True)                              # the last step's exchange is inside the timed region
+    else:
+        read_previous(record=True)                                  # ... and so is the read of the last step's results
     e1.record(stream)
     barrier()
     ms = e0.elapsed_time(e1)
@@ -398,6 +409,15 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         allp = [torch.zeros_like(pm) for _ in range(world)]
         dist.all_gather(allp, pm)
         push_ms = [round(float(x.item()), 4) for x in allp]
+    # ---- per-kernel device times: a separate, untimed pass with the three extra events per scan switched on ---------------
+    os.environ["MBC_PHASE_EVENTS"] = "1"
+    for _ in range(min(args.steps, 5)):
+        rs = [table.scan(terms[s], proj=wl.proj, want=want_dev, aggs=wl.aggs) for s in wl.sels]
+        for s, r_ in zip(wl.sels, rs):
+            _ = r_.count
+            phase_ms[s].append(r_.phase_ms)
+            r_.close()
+    os.environ.pop("MBC_PHASE_EVENTS", None)
     # ---- scan-only time of the same shard (no gather): what the multi-GPU step is compared with ----------------------
     scan_only_ms = None
     if world > 1:
@@ -511,7 +531,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         achieved_dev = tot_bytes / (tot_ms * 1e-3) / 1e9             # on the sum of the scans' device times (no gaps)
         # per kernel (CUDA events between the launches of every scan)
         kernels = {}
-        names = ("pass 1 (fused_scan_kernel when one launch does the scan, else filter_kernel)", "tile_offsets_kernel", "write_kernel", "agg_finish_kernel")
+        names = ("pass 1 (fused_scan_kernel when one launch does the scan, else filter_kernel)", "tile_offsets_kernel", "write pass (write_kernel + write_staged_kernel)", "agg_finish_kernel")
         for s in wl.sels:
             ph = np.asarray(phase_ms[s], dtype=np.float64).mean(0)
             for i, name in enumerate(names):
@@ -532,7 +552,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                    "single_thread_rows_per_s": v1, "java_probe": java_probe(),
                    "sample": f"{sample} rows of the {wl.name.upper()} table per scan x {nscan} selectivities (all threads) and "
                              f"{sample // 4} rows (1 thread); oracle/mbc_oracle.cpp orc_scan"}
-        roofline = {"bound": "hbm", "kernel": "mbc_scan: fused_scan_kernel (single residency) or filter_kernel + tile_offsets_kernel + write_kernel, then agg_finish_kernel",
+        roofline = {"bound": "hbm", "kernel": "mbc_scan: filter_kernel + tile_offsets_kernel + write_kernel + write_staged_kernel + agg_finish_kernel (or the opt-in fused_scan_kernel)",
                     "achieved": achieved_step, "peak": peak, "unit": "GB/s", "frac": achieved_step / peak,
                     "frac_of_nominal_8000": achieved_step / 8000.0, "peak_source": peak_src,
                     "basis": "algorithmic bytes of the step (SURVEY 8d) / ms_per_step",

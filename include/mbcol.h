@@ -290,7 +290,8 @@ int64_t        mbc_result_count(const mbc_result* r);
 /* Device time of the kernels that produced this result (CUDA events around them), ms; < 0 if unknown. */
 float          mbc_result_kernel_ms(const mbc_result* r);
 /* The same per kernel for a scan over a resident table: ms4 = {pass 1 (filter_kernel / select_bitmap_kernel),
- * tile_offsets_kernel, write_kernel, agg_finish_kernel}; -1 where unknown. */
+ * tile_offsets_kernel, write pass (write_kernel + write_staged_kernel), agg_finish_kernel}; -1 where unknown.  The three
+ * extra events between the launches are recorded only when the environment has MBC_PHASE_EVENTS set (profiling). */
 int32_t        mbc_result_phase_ms(const mbc_result* r, float* ms4);
 /* ascending positions, int64 (host; needs MBC_WANT_POSITIONS|MBC_WANT_HOST). For joins:
  * outer positions; mbc_result_positions2 gives the matching inner positions. */

@@ -276,6 +276,7 @@ struct ScanJob {
     size_t smem_bytes = 0;
     size_t staged_smem = 0;       // ring of write_staged_kernel
     bool staged_off = false;      // a launch whose projected columns are read in place from host memory gathers them
+    bool pdl_tail = false;        // the last thing queued was a kernel of this job launched by launch_job (agg_finish may follow it with PDL)
     int max_grid = 1;
     int launches = 0;             // launches so far: the running count is in slot launches & 1
     // single-residency engine (mbc_scan_fused.cuh): planned once per job, chosen per launch
@@ -540,6 +541,29 @@ static void bind_table(ScanJob* job, const mbc_table* t) {
     p.ntiles = (int)((t->nrows + kTileRows - 1) / kTileRows);
 }
 
+// Launch with (or without) programmatic dependent launch: the kernel may be scheduled while its predecessor in the stream
+// is still running and blocks in pdl_wait() until that has completed (mbc_scan_kernels.cuh).  Opt-in (MBC_PDL=1): measured on
+// B200 it does not pay here -- C2 step 1.769 ms with, 1.761 ms without; C5 1.009 vs 0.985 ms; the 25 % scan 0.84 vs 0.81 ms:
+// the early CTAs of a successor sit on registers and shared memory its predecessor's last waves could use.
+static bool pdl_enabled() {
+    static const int on = [] { const char* e = getenv("MBC_PDL"); return e ? atoi(e) : 0; }();
+    return on != 0;
+}
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_after(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
+
 // the launches over the bound table; its tiles take the next slots of the partials array
 static int32_t launch_job(ScanJob* job, bool first) {
     mbc_ctx* ctx = job->r->ctx;
@@ -610,9 +634,10 @@ static int32_t launch_job(ScanJob* job, bool first) {
         filter_kernel<<<job->grid_per_tiles(p.ntiles), kScanThreads, job->smem_bytes, ctx->stream>>>(p);
     }
     if (job->r->ev_mid[0]) cudaEventRecord(job->r->ev_mid[0], ctx->stream);
-    tile_offsets_kernel<<<(p.ntiles + kOffsetsPerBlock - 1) / kOffsetsPerBlock, 1024, 0, ctx->stream>>>(p.tile_counts, p.ntiles, p.tile_out,
-                                                                                                      p.count_in, p.count_out, p.work_counter,
-                                                                                                      p.group_class, kSparseMax, p.stg_min);
+    const bool pdl = pdl_enabled() && !job->r->ev_mid[0];          // events between the launches would serialise them anyway
+    launch_after(tile_offsets_kernel, dim3((p.ntiles + kOffsetsPerBlock - 1) / kOffsetsPerBlock), dim3(1024), 0, ctx->stream, pdl,
+                 (const uint32_t*)p.tile_counts, p.ntiles, p.tile_out, p.count_in, p.count_out, p.work_counter, p.group_class, (int)kSparseMax,
+                 (int)p.stg_min);
     job->launches++;
     ctx->launches += 2;
     job->part_done += p.ntiles;
@@ -631,18 +656,19 @@ static int32_t launch_job(ScanJob* job, bool first) {
             if (!ctas_per_sm &&
                 (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, write_kernel<true>, kScanThreads, 0) != cudaSuccess || ctas_per_sm < 1))
                 ctas_per_sm = 1;
-            write_kernel<true><<<std::min(p.ntiles, ctx->sm_count * ctas_per_sm), kScanThreads, 0, ctx->stream>>>(p);
+            launch_after(write_kernel<true>, dim3(std::min(p.ntiles, ctx->sm_count * ctas_per_sm)), dim3(kScanThreads), 0, ctx->stream, pdl, p);
         } else {
-            write_kernel<false><<<p.ntiles, kScanThreads, 0, ctx->stream>>>(p);
+            launch_after(write_kernel<false>, dim3(p.ntiles), dim3(kScanThreads), 0, ctx->stream, pdl, p);
         }
         ctx->launches++;
         if (staged_now) {
             p.dense_staged = 0;
-            write_staged_kernel<<<std::min(p.ntiles, ctx->sm_count * 2), kStgThreads, job->staged_smem, ctx->stream>>>(p);
+            launch_after(write_staged_kernel, dim3(std::min(p.ntiles, ctx->sm_count * 2)), dim3(kStgThreads), job->staged_smem, ctx->stream, pdl, p);
             ctx->launches++;
         }
     }
     if (job->r->ev_mid[2]) cudaEventRecord(job->r->ev_mid[2], ctx->stream);
+    job->pdl_tail = pdl;
     MBC_CUDA(cudaGetLastError());
     return MBC_OK;
 }
@@ -662,8 +688,10 @@ static int32_t finish_job_device(ScanJob* job, bool deferred = false) {
         } else {
             AggList list;
             memcpy(list.g, p.aggs, sizeof(list.g));
-            agg_finish_kernel<<<p.nagg, 1024, 0, ctx->stream>>>(job->w.partials, (int)job->part_slots, (int)job->part_done, list,
-                                                               job->w.agg_out, job->count_slot());
+            // (after the last launch of a resident scan; a chunked host scan has copies in between: plain launch)
+            const bool pdl = pdl_enabled() && job->pdl_tail;
+            launch_after(agg_finish_kernel, dim3(p.nagg), dim3(1024), 0, ctx->stream, pdl, (const unsigned long long*)job->w.partials,
+                         (int)job->part_slots, (int)job->part_done, list, job->w.agg_out, (const long long*)job->count_slot());
         }
         ctx->launches++;
         MBC_CUDA(cudaGetLastError());
@@ -730,7 +758,8 @@ int32_t run_scan(const ScanRequest& rq, mbc_result** out) {
         begin_timing(ctx);
         job.r->ev_t0 = event_get(ctx);
         job.r->ev_t1 = event_get(ctx);
-        for (auto& e : job.r->ev_mid) e = event_get(ctx);      // per-kernel times of a resident scan (mbc_result_phase_ms)
+        if (getenv("MBC_PHASE_EVENTS"))                        // per-kernel times of a resident scan (mbc_result_phase_ms): three
+            for (auto& e : job.r->ev_mid) e = event_get(ctx);  // more events between the launches, so only on request
         if (job.r->ev_t0) cudaEventRecord(job.r->ev_t0, ctx->stream);
         s = launch_job(&job, true);
     }
@@ -914,6 +943,7 @@ static int32_t run_scan_host(mbc_ctx* ctx, int32_t ncols, const mbc_coldesc* col
                 if (p.aggs[a].col >= 0 && late_ok[p.aggs[a].col]) p.aggs[a].src = host_dev[p.aggs[a].col] + (size_t)row0 * 4;
         }
         s = launch_job(&job, k == 0);
+        job.pdl_tail = false;                                             // copies and events follow the kernels of a chunk
         if (h_counts && s == MBC_OK &&
             cudaMemcpyAsync(&h_counts[k], job.count_slot(), 8, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) s = MBC_ERR_CUDA;
         cudaEventRecord(ev_done[b], ctx->stream);

@@ -310,6 +310,15 @@ __device__ __forceinline__ long long warp_sum_i64(long long v) {
     return v;
 }
 
+// ---- programmatic dependent launch (sm_90+) ------------------------------------------------------------------------
+// The kernels of one scan are launched back to back with programmaticStreamSerializationAllowed (mbc_scan.cu, MBC_PDL):
+// a kernel lets its successor's CTAs be scheduled as soon as all of its own are running (pdl_trigger, first statement), and
+// every successor blocks in pdl_wait (first statement) until its predecessor has completed and its writes are visible.  What
+// is saved is the launch latency and the ramp between the kernels; no kernel reads anything before the wait.  Both are no-ops
+// in a kernel launched without the attribute.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---- TMA bulk copy + mbarrier (sm_90+/sm_100a) -----------------------------------------------------
 
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
@@ -402,6 +411,7 @@ __device__ __forceinline__ unsigned long long agg_merge(const DevAgg& g, unsigne
 #define MBC_FILTER_CTAS 2
 #endif
 __global__ void __launch_bounds__(kScanThreads, MBC_FILTER_CTAS) filter_kernel(const __grid_constant__ ScanParams p) {
+    pdl_trigger();
     extern __shared__ __align__(128) uint8_t stage_mem[];          // [nstages][nstaged][kTileRows] uint32
     __shared__ __align__(8) uint64_t s_full[kMaxStages];
     __shared__ uint32_t s_wcnt[2][kWarpsPerCta];                   // by tile parity: see the note at the end of the loop
@@ -490,6 +500,7 @@ __global__ void __launch_bounds__(kScanThreads, MBC_FILTER_CTAS) filter_kernel(c
 __global__ void __launch_bounds__(kScanThreads) select_bitmap_kernel(const uint32_t* __restrict__ sel, const uint32_t* __restrict__ deleted,
                                                                      int64_t nrows, int ntiles, uint32_t* __restrict__ out,
                                                                      uint32_t* __restrict__ tile_counts) {
+    pdl_trigger();
     const int lane = threadIdx.x & 31;
     const int nwarps = gridDim.x * kWarpsPerCta;
     for (int tile = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5); tile < ntiles; tile += nwarps) {
@@ -529,6 +540,8 @@ enum : uint8_t { kGroupEmpty = 0, kGroupSparse = 1, kGroupMid = 2, kGroupFull = 
 __global__ void __launch_bounds__(1024) tile_offsets_kernel(const uint32_t* counts, int ntiles, unsigned long long* tile_base,
                                                             const long long* running_in, long long* running_out,
                                                             unsigned int* work_counter, uint8_t* group_class, int sparse_max, int full_min) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ unsigned long long s_warp[32];
     __shared__ unsigned long long s_prefix;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -982,6 +995,8 @@ __device__ __forceinline__ void write_sparse_group(const ScanParams& p, const in
 
 template <bool kPersistent>
 __global__ void __launch_bounds__(kScanThreads, MBC_WRITE_MIN_CTAS) write_kernel(const __grid_constant__ ScanParams p) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ uint16_t s_list[kListCap];                          // survivor rows within the group / tile, by rank
     __shared__ uint32_t s_wtot[kWarpsPerCta];
     __shared__ unsigned long long s_aggw[kMaxAgg][kWarpsPerCta];
@@ -1105,6 +1120,8 @@ constexpr int kStgWarpRows = kStgRows / kWarpsPerCta;              // 128: four 
 static_assert(kStgWarpRows == 128 && kTileRows / 32 == 128 && kStgSteps * kWarpsPerCta == 32, "stage geometry: a lane holds 4 of the tile's 128 bitmap words");
 
 __global__ void __launch_bounds__(kStgThreads, 2) write_staged_kernel(const __grid_constant__ ScanParams p) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ __align__(128) uint8_t s_ring[];             // [stg_stages][stg_bytes]
     __shared__ __align__(8) uint64_t s_full[kStgMaxStages];
     __shared__ __align__(8) uint64_t s_empty[kStgMaxStages];
@@ -1306,6 +1323,7 @@ struct AggList {
 __global__ void __launch_bounds__(1024) agg_finish_kernel(const unsigned long long* partials, int total_tiles,
                                                           int ntiles, const __grid_constant__ AggList list,
                                                           unsigned long long* out, const long long* count) {
+    pdl_wait();
     if (blockIdx.x == 0 && threadIdx.x == 0) out[kMaxAgg] = (unsigned long long)*count;   // aggregates + count leave in one copy
     const DevAgg g = list.g[blockIdx.x];
     const unsigned long long* src = partials + (size_t)blockIdx.x * total_tiles;
