@@ -349,7 +349,7 @@ static void plan_staged(mbc_ctx* ctx, ScanJob* job) {
 static void plan_fused(mbc_ctx* ctx, ScanJob* job) {
     job->fused_ok = false;
     // MBC_SCAN_PATH=fused opts in (tests, profiles).  Measured on B200 (profiles/README.md): the two-pass engine with the
-    // streaming dense write path is faster at every selectivity so far -- the fused kernel's three roles each sit close to
+    // TMA-staged dense write pass is faster at every selectivity -- the fused kernel's three roles each sit close to
     // the per-tile HBM time (term-program interpretation in the count warps, the ~2 us L2 round trip of the published
     // counts while HBM is saturated, ~800 instructions per tile and warp in the write warps), so it is not the default.
     const char* path = getenv("MBC_SCAN_PATH");

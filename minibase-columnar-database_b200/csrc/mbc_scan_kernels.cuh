@@ -22,13 +22,18 @@
 //     one register) and a CTA scan, so the output is written in ascending position order (the reference
 //     emits rows in position order; bit-exact position lists need order, not atomics) and no CTA ever
 //     waits for another;
-//   * survivors are written with one thread per SURVIVOR (a rank->row list in shared memory):
-//     projection columns are only gathered for qualifying rows (late materialisation), stores are
-//     coalesced, and the cost of the output phase is proportional to the selectivity; groups of 8
-//     tiles with few survivors are written by one CTA so that sparse scans do not pay a CTA's
-//     load -> scan -> gather -> store latency chain per tile;
-//   * COUNT/SUM/MIN/MAX partials are produced per tile and reduced in tile order by a second
-//     tiny kernel, so real-valued sums are reproducible run to run.
+//   * the write pass picks its method per GROUP of 8 tiles (32768 rows) from the group's survivor count, which the
+//     offsets kernel leaves as one class byte per group:
+//       - up to 12.5 %: one CTA writes the whole group (rank -> row list in shared memory, one work item -- positions, a
+//         projected column, the aggregates of a column -- per warp), so sparse scans do not pay a CTA's
+//         load -> scan -> gather -> store latency chain per tile and read only the survivors' sectors;
+//       - up to 28 %: every CTA gathers its own tile, one thread per SURVIVOR, coalesced stores;
+//       - above: write_staged_kernel reads the columns whole through a TMA ring and compacts out of shared memory with
+//         warp-autonomous ranks (one bitmap word per 32-row instruction): each column is read once, nothing waits on a
+//         list, and the kernel runs at the HBM roofline on the bytes it moves (measured 6.3 TB/s at 50 %);
+//     in the gather methods an aggregate whose column is projected is folded from the value loaded for the projection;
+//   * COUNT/SUM/MIN/MAX partials (per tile, per group or per CTA of write_staged_kernel, always in a slot of the
+//     per-tile array) are reduced in slot order by a second tiny kernel, so real-valued sums are reproducible run to run.
 #pragma once
 #include <cstring>
 #include <algorithm>
@@ -610,12 +615,14 @@ __global__ void __launch_bounds__(1024) tile_offsets_kernel(const uint32_t* coun
 }
 
 // ---- pass 2: ordered write of the survivors ----------------------------------------------------------------------
-// One CTA per tile; tiles form GROUPS of kGroupTiles.  In a dense group every CTA writes its own tile: ranks from the
-// bitmap, rank -> row list in shared memory, one thread per SURVIVOR, gathers issued in batches before the dependent
-// stores.  A sparse group (<= kSparseMax survivors) is written by its first CTA alone and the others exit: at low
-// selectivity a tile holds a few dozen survivors and a CTA's load -> scan -> gather -> store chain is pure latency,
-// so the group amortises it over 8x the rows.  There every thread owns kThreadWords consecutive words of the group's
-// selection bitmap (128-bit loads), a block scan of the popcounts ranks them, and the output columns go one per warp.
+// write_kernel: one CTA per tile; tiles form GROUPS of kGroupTiles, classified by tile_offsets_kernel.  In a kGroupMid group
+// (and a kGroupFull one when write_staged_kernel cannot take it) every CTA writes its own tile: ranks from the bitmap,
+// rank -> row list in shared memory, one thread per SURVIVOR, gathers issued in batches before the dependent stores.  A
+// kGroupSparse group (<= kSparseMax survivors) is written by its first CTA alone and the others exit: at low selectivity a
+// tile holds a few dozen survivors and a CTA's load -> scan -> gather -> store chain is pure latency, so the group amortises
+// it over 8x the rows.  There every thread owns kThreadWords consecutive words of the group's selection bitmap (128-bit
+// loads, issued together with the group's offsets), a block scan of the popcounts ranks them, and the output columns go one
+// per warp.
 #ifndef MBC_WRITE_MIN_CTAS
 #define MBC_WRITE_MIN_CTAS 4
 #endif
