@@ -635,9 +635,18 @@ static int32_t launch_job(ScanJob* job, bool first) {
     }
     if (job->r->ev_mid[0]) cudaEventRecord(job->r->ev_mid[0], ctx->stream);
     const bool pdl = pdl_enabled() && !job->r->ev_mid[0];          // events between the launches would serialise them anyway
+    // groups above p.stg_min survivors go to write_staged_kernel when their columns fit its ring; write_kernel writes the
+    // others (and those too when they do not).  Tables of >= 49 152 tiles take the persistent write_kernel (a sparse scan of
+    // 10^5 tiles saves the dispatch of as many idle CTAs: 0.78 vs 0.86 ms on 500 M rows at 0.01 %), whose tile-by-tile gather
+    // of mid groups is slow (250 M rows at 25 %: 2.67 ms against 1.93 ms with one CTA per tile) -- there every group above
+    // the sparse limit is staged (2.07 ms).
+    const bool staged_now = p.stg_n > 0 && !job->staged_off;
+    const char* pt = getenv("MBC_WRITE_PERSISTENT_TILES");              // tests force either form
+    const bool persistent = p.ntiles >= (pt ? atoi(pt) : 49152);
+    const int full_min = (persistent && staged_now && !getenv("MBC_STAGED_MIN_PCT")) ? kSparseMax : p.stg_min;
     launch_after(tile_offsets_kernel, dim3((p.ntiles + kOffsetsPerBlock - 1) / kOffsetsPerBlock), dim3(1024), 0, ctx->stream, pdl,
                  (const uint32_t*)p.tile_counts, p.ntiles, p.tile_out, p.count_in, p.count_out, p.work_counter, p.group_class, (int)kSparseMax,
-                 (int)p.stg_min);
+                 full_min);
     job->launches++;
     ctx->launches += 2;
     job->part_done += p.ntiles;
@@ -645,13 +654,8 @@ static int32_t launch_job(ScanJob* job, bool first) {
     bool need_write = p.out_pos || p.nproj > 0;
     for (int a = 0; a < p.nagg; ++a) need_write |= p.aggs[a].kind != MBC_AGG_COUNT;   // COUNT comes from the tile offsets
     if (need_write) {
-        // groups above p.stg_min survivors go to write_staged_kernel (below) when their columns fit its ring; write_kernel
-        // writes the others (and those too when they do not)
-        const bool staged_now = p.stg_n > 0 && !job->staged_off;
         p.dense_staged = staged_now ? 1 : 0;
-        const char* pt = getenv("MBC_WRITE_PERSISTENT_TILES");          // tests force either form
-        const int persistent_min_tiles = pt ? atoi(pt) : 49152;
-        if (p.ntiles >= persistent_min_tiles) {
+        if (persistent) {
             static int ctas_per_sm = 0;
             if (!ctas_per_sm &&
                 (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, write_kernel<true>, kScanThreads, 0) != cudaSuccess || ctas_per_sm < 1))

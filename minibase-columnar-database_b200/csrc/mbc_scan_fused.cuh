@@ -34,7 +34,7 @@
 namespace mbc {
 
 #ifndef MBC_FUSED_COUNT_GROUPS
-#define MBC_FUSED_COUNT_GROUPS 2
+#define MBC_FUSED_COUNT_GROUPS 1
 #endif
 constexpr int kFR = 2048;                                         // rows per tile
 constexpr int kFGroupWarps = kFR / kWarpRows;                     // count warps per group: a warp owns 512 rows (16 per thread)

@@ -152,8 +152,21 @@ def test_both_write_pass_forms(ctx, oracle, monkeypatch):
     assert 150_000 < exp["count"] < 160_000
     for force in ("1", "1000000000"):
         monkeypatch.setenv("MBC_WRITE_PERSISTENT_TILES", force)
-        res = t.scan(terms, proj=[2, 1, 0], want=ALL, aggs=aggs)
-        check_result(oracle, res, exp, [descs[2], descs[1], descs[0]])
+        # staged on: the fullest groups (persistent form: every group above the sparse limit) go through write_staged_kernel;
+        # staged off: write_kernel gathers them tile by tile (the persistent form's static stride over the dense tiles)
+        for staged in ("1", "0"):
+            monkeypatch.setenv("MBC_WRITE_STAGED", staged)
+            res = t.scan(terms, proj=[2, 1, 0], want=ALL, aggs=aggs)
+            check_result(oracle, res, exp, [descs[2], descs[1], descs[0]])
+            res.close()
+    # a mid-density stretch (20 % of the middle rows) under both forms, staged on
+    terms2 = [oracle.Term(oracle.OP_LT, ("col", 0), ("int", 20), 0)]
+    exp2 = oracle.scan(descs, cols, terms2, proj=[0, 2], aggs=aggs)
+    for force in ("1", "1000000000"):
+        monkeypatch.setenv("MBC_WRITE_PERSISTENT_TILES", force)
+        monkeypatch.setenv("MBC_WRITE_STAGED", "1")
+        res = t.scan(terms2, proj=[0, 2], want=ALL, aggs=aggs)
+        check_result(oracle, res, exp2, [descs[0], descs[2]])
         res.close()
     t.close()
 
