@@ -252,7 +252,7 @@ constexpr int kMaxPerThread = 8192 / kBuildThreads;        // rows of one chunk 
 // Fill of one chunk for <= 32 values (always chunk_rows = 8192): lane v assembles value v's word from one ballot per id
 // bit, so the cost does not depend on how many distinct values a warp sees.
 template <bool IDENT, bool FULL>
-__device__ __forceinline__ void fill_few_values(const BuildParams& p, uint32_t* sm, const int32_t (&pv)[kMaxPerThread], int nv, int v0,
+__device__ __forceinline__ void fill_few_values(const BuildParams& p, uint32_t* sm, const int32_t* __restrict__ vals, int nv, int v0,
                                                 int64_t row0) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int bits = 32 - __clz(max(nv - 1, 1));
@@ -267,11 +267,12 @@ __device__ __forceinline__ void fill_few_values(const BuildParams& p, uint32_t* 
         // rows past the end of the table hold the column's zero padding: the id table is only read for a row of the table
         // whose value lies inside [kmin, kmax] (0 may be far outside it)
         bool ok = FULL || row0 + threadIdx.x + q * kBuildThreads < p.nrows;
+        const int32_t val = vals[threadIdx.x + q * kBuildThreads];  // the chunk's values, bulk-copied into shared memory
         int id = -1;
         if (IDENT) {
-            id = pv[q] - base;
+            id = val - base;
         } else {
-            const uint32_t k = (uint32_t)((long long)pv[q] - p.h.kmin);
+            const uint32_t k = (uint32_t)((long long)val - p.h.kmin);
             if (ok && k < (uint32_t)p.h.range) id = (int)__ldg(p.h.id_of + k) - base;
         }
         ok = ok && (unsigned)id < (unsigned)nv;
@@ -295,7 +296,6 @@ __global__ void __launch_bounds__(kBuildThreads, 2) bitmap_build_kernel(const __
     const int lane = threadIdx.x & 31;
     const int per = p.chunk_rows / kBuildThreads;         // 2..16 rows per thread per chunk
     const bool fast = p.h.direct && !p.deleted;
-    const bool few = fast && p.nvalues_total <= 32 && p.chunk_rows == 8192;
     const int32_t* col32 = reinterpret_cast<const int32_t*>(p.col);
 
     for (int i = threadIdx.x; i < total_quads; i += kBuildThreads) sm4[i] = make_uint4(0, 0, 0, 0);
@@ -317,15 +317,7 @@ __global__ void __launch_bounds__(kBuildThreads, 2) bitmap_build_kernel(const __
     for (; chunk < p.nchunks; chunk += nctas) {
         const int64_t row0 = chunk * p.chunk_rows;
         const bool full = row0 + p.chunk_rows <= p.nrows;
-        if (few) {
-            if (p.identity) {
-                if (full) fill_few_values<true, true>(p, sm, pv, nv, v0, row0);
-                else fill_few_values<true, false>(p, sm, pv, nv, v0, row0);
-            } else {
-                if (full) fill_few_values<false, true>(p, sm, pv, nv, v0, row0);
-                else fill_few_values<false, false>(p, sm, pv, nv, v0, row0);
-            }
-        } else if (fast) {
+        if (fast) {
 #pragma unroll
             for (int q = 0; q < kMaxPerThread; ++q) {
                 if (q < per) {                                              // warp-uniform
@@ -374,6 +366,86 @@ __global__ void __launch_bounds__(kBuildThreads, 2) bitmap_build_kernel(const __
             sm4[src] = make_uint4(0, 0, 0, 0);
         }
         __syncthreads();
+    }
+}
+
+// <= 32 values, direct map, no deleted rows, 8192-row chunks: the same matrix and write-out, but the column is fed by a
+// ring of bulk-TMA copies (cp.async.bulk, 32 KB per chunk, completion on an mbarrier) that runs kFewStages chunks ahead.  The
+// generic kernel prefetches ONE chunk into registers and can only issue that prefetch after the fill that consumes the
+// registers, so every chunk exposed most of a DRAM round trip (measured 1.04 ms for the 500 M-row column G: 2.9 TB/s).
+constexpr int kFewStages = 2;
+constexpr int kFewRows = 8192;
+__device__ __forceinline__ uint32_t bm_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bm_mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "BM_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra BM_DONE;\n"
+        "bra BM_WAIT;\n"
+        "BM_DONE:\n"
+        "}" ::"r"(bm_smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bm_issue_chunk(int32_t* dst, const int32_t* src, uint64_t* bar) {
+    constexpr uint32_t bytes = kFewRows * 4;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bm_smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(bm_smem_u32(dst)), "l"(src),
+                 "r"(bytes), "r"(bm_smem_u32(bar))
+                 : "memory");
+}
+
+__global__ void __launch_bounds__(kBuildThreads, 2) bitmap_build_few_kernel(const __grid_constant__ BuildParams p) {
+    extern __shared__ uint4 sm4[];                        // [nv_per][256 words] matrix, then kFewStages x 8192 column values
+    __shared__ __align__(8) uint64_t s_full[kFewStages];
+    uint32_t* sm = reinterpret_cast<uint32_t*>(sm4);
+    const int nv = (int)p.nvalues_total;                  // one slice: npass == 1
+    constexpr int wpc = kFewRows / 32;
+    const int total_quads = p.nv_per * wpc / 4;
+    int32_t* ring = reinterpret_cast<int32_t*>(sm + (size_t)p.nv_per * wpc);
+    const int32_t* col32 = reinterpret_cast<const int32_t*>(p.col);
+    const int64_t nctas = gridDim.x;
+    for (int i = threadIdx.x; i < total_quads; i += kBuildThreads) sm4[i] = make_uint4(0, 0, 0, 0);
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kFewStages; ++s)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bm_smem_u32(&s_full[s])), "r"(1));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        for (int s = 0; s < kFewStages; ++s) {
+            const int64_t c = (int64_t)blockIdx.x + s * nctas;
+            if (c < p.nchunks) bm_issue_chunk(ring + (size_t)s * kFewRows, col32 + c * kFewRows, &s_full[s]);   // columns are padded: in bounds
+        }
+    }
+    __syncthreads();
+    const int qshift = 31 - __clz(wpc >> 2);
+    int slot = 0;
+    uint32_t phase = 0;
+    for (int64_t chunk = blockIdx.x; chunk < p.nchunks; chunk += nctas) {
+        const int64_t row0 = chunk * kFewRows;
+        const bool full = row0 + kFewRows <= p.nrows;
+        bm_mbar_wait(&s_full[slot], phase);               // this chunk's values have landed
+        const int32_t* vals = ring + (size_t)slot * kFewRows;
+        if (p.identity) {
+            if (full) fill_few_values<true, true>(p, sm, vals, nv, 0, row0);
+            else fill_few_values<true, false>(p, sm, vals, nv, 0, row0);
+        } else {
+            if (full) fill_few_values<false, true>(p, sm, vals, nv, 0, row0);
+            else fill_few_values<false, false>(p, sm, vals, nv, 0, row0);
+        }
+        __syncthreads();                                  // the matrix is complete and the stage is free
+        if (threadIdx.x == 0) {
+            const int64_t next = chunk + kFewStages * nctas;
+            if (next < p.nchunks) bm_issue_chunk(ring + (size_t)slot * kFewRows, col32 + next * kFewRows, &s_full[slot]);
+        }
+        uint4* dst4 = reinterpret_cast<uint4*>(p.bitmaps + chunk * p.nvalues_total * wpc);
+        for (int i = threadIdx.x; i < total_quads; i += kBuildThreads) {
+            const int v = i >> qshift;
+            const int src = (v << qshift) + ((i & ((1 << qshift) - 1)) ^ (v & 7));
+            if (v < nv) dst4[i] = sm4[src];                // (nv_per is nv rounded up to whole quads of values)
+            sm4[src] = make_uint4(0, 0, 0, 0);
+        }
+        __syncthreads();
+        if (++slot == kFewStages) { slot = 0; phase ^= 1u; }
     }
 }
 
@@ -614,11 +686,22 @@ extern "C" int32_t mbc_bitmap_build(mbc_table* t, int32_t col) {
             p.npass = (int)((D + p.nv_per - 1) / p.nv_per);
             p.identity = direct && D == (int64_t)h.range;
             size_t smem = (size_t)p.nv_per * (R / 8);
-            int per_sm = 1;
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bitmap_build_kernel, kBuildThreads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
-            int64_t grid = std::min<int64_t>(p.nchunks * p.npass, (int64_t)ctx->sm_count * per_sm);
-            grid = std::max<int64_t>(grid / p.npass, 1) * p.npass;           // every chunk stride carries all slices
-            bitmap_build_kernel<<<(int)grid, kBuildThreads, smem, ctx->stream>>>(p);
+            const bool few = direct && !deleted && D <= 32 && R == kFewRows && p.npass == 1 && !getenv("MBC_BM_FEW_OFF");
+            if (few) {
+                // <= 32 values: the column comes through a TMA ring (bitmap_build_few_kernel)
+                smem += (size_t)kFewStages * kFewRows * 4;
+                MBC_CUDA(cudaFuncSetAttribute(bitmap_build_few_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                int per_sm = 1;
+                if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bitmap_build_few_kernel, kBuildThreads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+                const int64_t grid = std::max<int64_t>(1, std::min<int64_t>(p.nchunks, (int64_t)ctx->sm_count * per_sm));
+                bitmap_build_few_kernel<<<(int)grid, kBuildThreads, smem, ctx->stream>>>(p);
+            } else {
+                int per_sm = 1;
+                if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bitmap_build_kernel, kBuildThreads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+                int64_t grid = std::min<int64_t>(p.nchunks * p.npass, (int64_t)ctx->sm_count * per_sm);
+                grid = std::max<int64_t>(grid / p.npass, 1) * p.npass;           // every chunk stride carries all slices
+                bitmap_build_kernel<<<(int)grid, kBuildThreads, smem, ctx->stream>>>(p);
+            }
             ctx->launches++;
         }
         end_timing(ctx);
