@@ -309,12 +309,6 @@ __device__ __forceinline__ uint32_t load_bits(const uint32_t* bm, int64_t warp_r
     return mask;
 }
 
-__device__ __forceinline__ long long warp_sum_i64(long long v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
-    return v;
-}
-
 // ---- programmatic dependent launch (sm_90+) ------------------------------------------------------------------------
 // The kernels of one scan are launched back to back with programmaticStreamSerializationAllowed (mbc_scan.cu, MBC_PDL):
 // a kernel lets its successor's CTAs be scheduled as soon as all of its own are running (pdl_trigger, first statement), and
@@ -325,8 +319,6 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // ---- TMA bulk copy + mbarrier (sm_90+/sm_100a) -----------------------------------------------------
-
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -694,43 +686,6 @@ __device__ __forceinline__ void gather_store_wide(const DevProj& pr, int64_t row
         uint32_t* dst = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(pr.dst) + (out0 + k) * pr.stride);
         for (int q = 0; q < words; ++q) dst[q] = __ldg(src + q);
     }
-}
-
-// fold of one aggregate over list[first], list[first + step], ...; the result is butterflied across the warp
-__device__ __forceinline__ unsigned long long gather_fold(const DevAgg& g, int64_t row0, const uint16_t* list, int first, int step, int n) {
-    const uint32_t* src = reinterpret_cast<const uint32_t*>(g.src) + row0;
-    if (g.type == MBC_ATTR_INTEGER) {
-        long long acc = (long long)agg_identity(g);
-        for (int k0 = first; k0 < n; k0 += step * kGatherBatch) {
-            uint32_t v[kGatherBatch];
-#pragma unroll
-            for (int b = 0; b < kGatherBatch; ++b) {
-                const int k = k0 + b * step;
-                if (k < n) v[b] = __ldg(src + list[k]);
-            }
-#pragma unroll
-            for (int b = 0; b < kGatherBatch; ++b)
-                if (k0 + b * step < n) acc = agg_combine<long long>(g.kind, acc, (long long)(int32_t)v[b]);
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) acc = agg_combine<long long>(g.kind, acc, __shfl_xor_sync(0xFFFFFFFFu, acc, o));
-        return (unsigned long long)acc;
-    }
-    double acc = __longlong_as_double((long long)agg_identity(g));
-    for (int k0 = first; k0 < n; k0 += step * kGatherBatch) {
-        uint32_t v[kGatherBatch];
-#pragma unroll
-        for (int b = 0; b < kGatherBatch; ++b) {
-            const int k = k0 + b * step;
-            if (k < n) v[b] = __ldg(src + list[k]);
-        }
-#pragma unroll
-        for (int b = 0; b < kGatherBatch; ++b)
-            if (k0 + b * step < n) acc = agg_combine<double>(g.kind, acc, (double)__uint_as_float(v[b]));
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc = agg_combine<double>(g.kind, acc, __shfl_xor_sync(0xFFFFFFFFu, acc, o));
-    return (unsigned long long)__double_as_longlong(acc);
 }
 
 // One tile of a dense group: ranks from the bitmap in the filter pass's 16-rows-per-thread layout (the expansion is
