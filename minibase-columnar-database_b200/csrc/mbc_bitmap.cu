@@ -76,9 +76,9 @@ __global__ void __launch_bounds__(256) column_minmax_kernel(const int32_t* col, 
         mn = min(mn, __shfl_xor_sync(0xFFFFFFFFu, mn, o));
         mx = max(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, o));
     }
-    if ((threadIdx.x & 31) == 0 && mn <= mx) {
-        atomicMin(out, mn);
-        atomicMax(out + 1, mx);
+    if ((threadIdx.x & 31) == 0 && mn <= mx) {                       // (a warp that saw no row keeps mn > mx)
+        atomicMin(out, (long long)mn);
+        atomicMax(out + 1, (long long)mx);
     }
 }
 
@@ -126,12 +126,12 @@ __global__ void __launch_bounds__(256) column_range_presence_kernel(const int32_
     __shared__ uint32_t sh[kMaxDirectRange / 32];
     for (uint32_t i = threadIdx.x; i < kMaxDirectRange / 32; i += blockDim.x) sh[i] = 0;
     __syncthreads();
-    long long mn = INT64_MAX, mx = INT64_MIN;
+    int mn = INT32_MAX, mx = INT32_MIN;                              // 32-bit min / max: one instruction each per value
     const int64_t step = (int64_t)gridDim.x * blockDim.x;
     int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     auto take = [&](int v) {
-        mn = min(mn, (long long)v);
-        mx = max(mx, (long long)v);
+        mn = min(mn, v);
+        mx = max(mx, v);
         const uint32_t k = (uint32_t)v & (kMaxDirectRange - 1);
         const uint32_t bit = 1u << (k & 31);
         if (!(sh[k >> 5] & bit)) atomicOr(&sh[k >> 5], bit);         // the bit is almost always already set
