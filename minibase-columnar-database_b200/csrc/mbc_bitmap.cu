@@ -251,14 +251,13 @@ constexpr int kMaxPerThread = 8192 / kBuildThreads;        // rows of one chunk 
 
 // Fill of one chunk for <= 32 values (always chunk_rows = 8192): lane v assembles value v's word from one ballot per id
 // bit, so the cost does not depend on how many distinct values a warp sees.
-template <bool IDENT, bool FULL>
+template <bool IDENT, bool FULL, int BITS>
 __device__ __forceinline__ void fill_few_values(const BuildParams& p, uint32_t* sm, const int32_t* __restrict__ vals, int nv, int v0,
                                                 int64_t row0) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int bits = 32 - __clz(max(nv - 1, 1));
-    uint32_t inv[5];
+    uint32_t inv[BITS];
 #pragma unroll
-    for (int k = 0; k < 5; ++k) inv[k] = ((lane >> k) & 1) ? 0u : ~0u;
+    for (int k = 0; k < BITS; ++k) inv[k] = ((lane >> k) & 1) ? 0u : ~0u;
     uint32_t* mine = sm + lane * (8192 / 32);
     const int sw = (lane & 7) << 2;
     const int base = IDENT ? (int)p.h.kmin + v0 : v0;
@@ -278,8 +277,7 @@ __device__ __forceinline__ void fill_few_values(const BuildParams& p, uint32_t* 
         ok = ok && (unsigned)id < (unsigned)nv;
         uint32_t w = __ballot_sync(0xFFFFFFFFu, ok);
 #pragma unroll
-        for (int k = 0; k < 5; ++k)
-            if (k < bits) w &= __ballot_sync(0xFFFFFFFFu, (id >> k) & 1) ^ inv[k];
+        for (int k = 0; k < BITS; ++k) w &= __ballot_sync(0xFFFFFFFFu, (id >> k) & 1) ^ inv[k];
         if (lane < nv) mine[(warp + q * (kBuildThreads / 32)) ^ sw] = w;
     }
 }
@@ -369,6 +367,17 @@ __global__ void __launch_bounds__(kBuildThreads, 2) bitmap_build_kernel(const __
     }
 }
 
+template <int BITS>
+__device__ __forceinline__ void fill_few_dispatch(const BuildParams& p, uint32_t* sm, const int32_t* vals, int nv, int64_t row0, bool full) {
+    if (p.identity) {
+        if (full) fill_few_values<true, true, BITS>(p, sm, vals, nv, 0, row0);
+        else fill_few_values<true, false, BITS>(p, sm, vals, nv, 0, row0);
+    } else {
+        if (full) fill_few_values<false, true, BITS>(p, sm, vals, nv, 0, row0);
+        else fill_few_values<false, false, BITS>(p, sm, vals, nv, 0, row0);
+    }
+}
+
 // <= 32 values, direct map, no deleted rows, 8192-row chunks: the same matrix and write-out, but the column is fed by a
 // ring of bulk-TMA copies (cp.async.bulk, 32 KB per chunk, completion on an mbarrier) that runs kFewStages chunks ahead.  The
 // generic kernel prefetches ONE chunk into registers and can only issue that prefetch after the fill that consumes the
@@ -418,6 +427,7 @@ __global__ void __launch_bounds__(kBuildThreads, 2) bitmap_build_few_kernel(cons
     }
     __syncthreads();
     const int qshift = 31 - __clz(wpc >> 2);
+    const int bits = 32 - __clz(max(nv - 1, 1));          // id bits: 1..5
     int slot = 0;
     uint32_t phase = 0;
     for (int64_t chunk = blockIdx.x; chunk < p.nchunks; chunk += nctas) {
@@ -425,12 +435,12 @@ __global__ void __launch_bounds__(kBuildThreads, 2) bitmap_build_few_kernel(cons
         const bool full = row0 + kFewRows <= p.nrows;
         bm_mbar_wait(&s_full[slot], phase);               // this chunk's values have landed
         const int32_t* vals = ring + (size_t)slot * kFewRows;
-        if (p.identity) {
-            if (full) fill_few_values<true, true>(p, sm, vals, nv, 0, row0);
-            else fill_few_values<true, false>(p, sm, vals, nv, 0, row0);
-        } else {
-            if (full) fill_few_values<false, true>(p, sm, vals, nv, 0, row0);
-            else fill_few_values<false, false>(p, sm, vals, nv, 0, row0);
+        switch (bits) {                                   // id bits as a template parameter: straight-line ballots
+            case 1: fill_few_dispatch<1>(p, sm, vals, nv, row0, full); break;
+            case 2: fill_few_dispatch<2>(p, sm, vals, nv, row0, full); break;
+            case 3: fill_few_dispatch<3>(p, sm, vals, nv, row0, full); break;
+            case 4: fill_few_dispatch<4>(p, sm, vals, nv, row0, full); break;
+            default: fill_few_dispatch<5>(p, sm, vals, nv, row0, full); break;
         }
         __syncthreads();                                  // the matrix is complete and the stage is free
         if (threadIdx.x == 0) {
